@@ -1,0 +1,144 @@
+"""blind_image_denoising_b200 -- B200-native hot path of `bfcnn` (drop-in for that path only).
+
+Public surface mirrors reference bfcnn/__init__.py:34-141 for the resnet denoiser family:
+`models`, `configs`, `CONFIGS_DICT`, `load_model`, `load_denoiser_model`,
+`load_default_denoiser`, plus the training-step mirrors in `.training`.
+No TensorFlow, no CPU fallback: every call ends in libbfcnn_b200.so (see `_native`).
+"""
+from __future__ import annotations
+
+import json
+import os
+import pathlib
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _native
+from .arch import (Arch, arch_from_config, arch_from_name, arch_from_variable_shapes,
+                   default_pipeline_config)
+from .denoiser import Denoiser
+from .tensorbundle import read_model_variables, write_model_variables
+from .weights import synthetic_variables
+
+__version__ = "0.1.0"
+DENOISER_STR = "denoiser"  # reference bfcnn/constants.py (DENOISER_STR)
+
+current_dir = pathlib.Path(__file__).parent.resolve()
+pretrained_dir = current_dir / "pretrained"
+configs_dir = current_dir / "configs"
+
+
+def load_config(config) -> Dict:
+    """reference bfcnn/utilities.py:59-83: dict passthrough or JSON path."""
+    if isinstance(config, dict):
+        return config
+    with open(str(config), "r") as f:
+        return json.load(f)
+
+
+# --------------------------------------------------------------------- configs (bfcnn/__init__.py:38-48)
+configs = [(os.path.basename(str(c)), load_config(str(c))) for c in sorted(configs_dir.glob("*.json"))]
+CONFIGS_DICT = {os.path.splitext(os.path.basename(str(c)))[0]: load_config(str(c))
+                for c in sorted(configs_dir.glob("*.json"))}
+
+
+# --------------------------------------------------------------------- weights on disk
+def _find_variables_dir(directory: pathlib.Path) -> Optional[pathlib.Path]:
+    """Accept `<dir>/saved_model/variables` (setup.py:59-73), `<dir>/denoiser/variables`
+    (export_model.py:117) and `<dir>/variables` (a SavedModel directory itself)."""
+    for sub in ("saved_model/variables", "denoiser/variables", "variables", "."):
+        d = directory / sub
+        if (d / "variables.index").exists():
+            return d
+    return None
+
+
+def _find_config(directory: pathlib.Path) -> Optional[pathlib.Path]:
+    for d in (directory, directory.parent):
+        if (d / "pipeline.json").exists():
+            return d / "pipeline.json"
+    return None
+
+
+def load_variables(path) -> List[np.ndarray]:
+    """Keras-order `hydra.variables` from a model directory or an `.npz` of the same list."""
+    path = pathlib.Path(path)
+    if path.is_file() and path.suffix == ".npz":
+        z = np.load(str(path))
+        return [z[k] for k in sorted(z.files, key=lambda s: int("".join(ch for ch in s if ch.isdigit()) or 0))]
+    vdir = _find_variables_dir(path)
+    if vdir is None:
+        raise ValueError("model_path [{0}] holds no variables.index".format(path))
+    return read_model_variables(str(vdir))
+
+
+def _build_denoiser(path, name: str = "", **kwargs) -> Denoiser:
+    path = pathlib.Path(path)
+    variables = load_variables(path)
+    arch = arch_from_variable_shapes([v.shape for v in variables])
+    cfg_path = _find_config(path if path.is_dir() else path.parent)
+    if cfg_path is not None:
+        cfg_arch = arch_from_config(load_config(cfg_path))
+        if cfg_arch != arch:
+            raise ValueError(f"pipeline.json describes {cfg_arch} but the checkpoint holds {arch}")
+    return Denoiser(arch, variables, name=name, **kwargs)
+
+
+# --------------------------------------------------------------------- registry (bfcnn/__init__.py:52-75)
+models: Dict[str, Dict] = {}
+if pretrained_dir.is_dir():
+    for directory in sorted(d for d in pretrained_dir.iterdir() if d.is_dir()):
+        model_name = str(directory.name)
+
+        def load_denoiser_module(directory=directory, model_name=model_name, **kwargs):
+            return _build_denoiser(directory, name=model_name, **kwargs)
+
+        saved = directory / "saved_model"
+        models[model_name] = {
+            "directory": directory,
+            DENOISER_STR: load_denoiser_module,
+            "configuration": str(directory / "pipeline.json"),
+            "saved_model_path": str(saved if saved.exists() else directory / DENOISER_STR),
+        }
+
+
+def load_model(model_path: str, **kwargs) -> Denoiser:
+    """reference bfcnn/__init__.py:81-97 (same argument checks and messages).
+
+    Returns a callable mapping uint8 [N,H,W,3] to the denoised uint8 tensor.
+    Keyword-only extras: device=0, precision="f16x3"|"f16"|"fp32", pad_pow2=True."""
+    if model_path is None or len(model_path) <= 0:
+        raise ValueError("model_path cannot be empty")
+    if model_path in models:
+        return models[model_path][DENOISER_STR](**kwargs)
+    if not os.path.exists(model_path):
+        raise ValueError("model_path [{0}] does not exist".format(model_path))
+    return _build_denoiser(model_path, name=os.path.basename(str(model_path).rstrip("/")), **kwargs)
+
+
+def load_denoiser_model(model_path: str, **kwargs) -> Denoiser:
+    """reference bfcnn/__init__.py:103-112."""
+    if model_path is None or len(model_path) <= 0:
+        raise ValueError("model_path cannot be empty")
+    if model_path in models:
+        return models[model_path][DENOISER_STR](**kwargs)
+    raise ValueError("model_path [{0}] does not exist".format(model_path))
+
+
+# reference bfcnn/__init__.py:119-122
+load_default_denoiser = list(models.values())[0][DENOISER_STR] if len(models) > 0 else None
+
+
+def synthetic_model(no_layers: int, seed: int = 0, **kwargs) -> Denoiser:
+    """A denoiser with deterministic synthetic weights (benchmarks, parity tests)."""
+    arch = Arch(no_layers=no_layers)
+    return Denoiser(arch, synthetic_variables(arch, seed), name=f"synthetic_1x{no_layers}", **kwargs)
+
+
+__all__ = [
+    "models", "configs", "CONFIGS_DICT", "load_model", "load_denoiser_model",
+    "load_default_denoiser", "load_config", "load_variables", "synthetic_model", "Denoiser", "Arch",
+    "arch_from_config", "arch_from_name", "default_pipeline_config", "synthetic_variables",
+    "read_model_variables", "write_model_variables",
+]

@@ -1,0 +1,280 @@
+// api.cu -- the extern "C" surface of libbfcnn_b200.so (include/bfcnn_b200.h)
+#include <math.h>
+#include <string.h>
+
+#include "kernels.cuh"
+
+using namespace bfcnn;
+
+namespace {
+
+int validate_arch(const bfcnn_arch* a) {
+  BF_REQUIRE(a != nullptr, "arch is NULL");
+  BF_REQUIRE(a->filters == C, "filters must be 16");
+  BF_REQUIRE(a->in_channels == 3 && a->out_channels == 3, "in/out channels must be 3");
+  BF_REQUIRE(a->no_layers >= 0 && a->no_layers <= 64, "no_layers must be in [0,64]");
+  BF_REQUIRE(a->base_kernel == 1 || a->base_kernel == 3 || a->base_kernel == 5 || a->base_kernel == 7,
+             "base_kernel must be 1, 3, 5 or 7");
+  BF_REQUIRE(a->head_filters >= 1 && a->head_filters <= 64, "head_filters must be in [1,64]");
+  BF_REQUIRE(a->bn_epsilon > 0.f, "bn_epsilon must be > 0");
+  return BFCNN_OK;
+}
+
+int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// utilities.py:736-751 emulation without the padded work
+Extent make_extent(const bfcnn_handle* h, int n, int height, int width, uint32_t flags) {
+  Extent e;
+  e.n = n; e.h = height; e.w = width;
+  if (flags & BFCNN_FLAG_NO_PAD_POW2) {
+    e.he = height; e.we = width;
+  } else {
+    const int R = (h->arch.base_kernel - 1) / 2 + 2 * h->arch.no_layers;
+    e.he = std::min(next_pow2(height), height + R);
+    e.we = std::min(next_pow2(width), width + R);
+  }
+  return e;
+}
+
+int check_images(int n, int height, int width) {
+  BF_REQUIRE(n >= 0 && height >= 0 && width >= 0, "negative image dimension");
+  BF_REQUIRE((long long)n * height * width * 3 < (1ll << 40), "image batch too large");
+  return BFCNN_OK;
+}
+
+int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int n, int height, int width,
+                 int precision, uint32_t flags, void* stream) {
+  BF_REQUIRE(h != nullptr, "handle is NULL");
+  BF_CHECK(check_images(n, height, width));
+  BF_REQUIRE(precision == BFCNN_PREC_FP32 || precision == BFCNN_PREC_F16 || precision == BFCNN_PREC_F16X3,
+             "unknown precision");
+  const size_t npx = (size_t)n * height * width;
+  if (npx == 0) return BFCNN_OK;  // empty batch / empty image: nothing to do
+  BF_REQUIRE(in != nullptr && out != nullptr, "in/out is NULL");
+  BF_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t in_bytes = npx * 3, out_bytes = npx * 3 * (out_u8 ? 1 : sizeof(float));
+
+  const uint8_t* d_in = in;
+  if (!(flags & BFCNN_FLAG_IN_DEVICE)) {
+    BF_CHECK(h->ws_in.reserve(in_bytes));
+    BF_CUDA(cudaMemcpyAsync(h->ws_in.p, in, in_bytes, cudaMemcpyHostToDevice, st));
+    d_in = h->ws_in.as<uint8_t>();
+  }
+  void* d_out = out;
+  if (!(flags & BFCNN_FLAG_OUT_DEVICE)) {
+    BF_CHECK(h->ws_out.reserve(out_bytes));
+    d_out = h->ws_out.p;
+  }
+  const Extent e = make_extent(h, n, height, width, flags);
+
+  BF_CUDA(cudaEventRecord(h->ev0, st));
+  if (precision == BFCNN_PREC_FP32) {
+    const size_t feat = (size_t)e.n * e.he * e.we * C * sizeof(float);
+    BF_CHECK(h->ws_feat[0].reserve(feat));
+    BF_CHECK(h->ws_feat[1].reserve(feat));
+    float* X = h->ws_feat[0].as<float>();
+    float* T = h->ws_feat[1].as<float>();
+    BF_CHECK(launch_base_conv(h, d_in, true, X, h->d_base_f32.as<float>(), e, st));
+    for (int i = 0; i < h->arch.no_layers; ++i) {
+      const float* wa = h->d_conv_f32.as<float>() + (size_t)(2 * i) * 9 * C * C;
+      const float* wb = h->d_conv_f32.as<float>() + (size_t)(2 * i + 1) * 9 * C * C;
+      const float* bb = h->d_bias_f32.as<float>() + (size_t)(2 * i + 1) * C;
+      BF_CHECK(launch_conv3x3_f32(h, X, T, wa, nullptr, nullptr, nullptr, true, e, st));
+      BF_CHECK(launch_conv3x3_f32(h, T, X, wb, bb, X, nullptr, false, e, st));
+    }
+    BF_CHECK(launch_head(h, X, d_out, out_u8, h->d_head_f32.as<float>(), e, st));
+  } else {
+    BF_CHECK(run_fused_stack(h, d_in, d_out, out_u8, e, precision, st));
+  }
+  BF_CUDA(cudaEventRecord(h->ev1, st));
+  h->ev_valid = true;
+
+  if (!(flags & BFCNN_FLAG_OUT_DEVICE)) {
+    BF_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    BF_CUDA(cudaStreamSynchronize(st));
+  }
+  return BFCNN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bfcnn_abi_version(void) { return BFCNN_ABI_VERSION; }
+
+const char* bfcnn_last_error(void) { return bfcnn::get_error(); }
+
+int bfcnn_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return BFCNN_ERR_CUDA;
+  }
+  return n;
+}
+
+int64_t bfcnn_num_weights(const bfcnn_arch* arch) {
+  if (validate_arch(arch) != BFCNN_OK) return BFCNN_ERR_INVALID_ARGUMENT;
+  VarLayout L;
+  L.build(*arch);
+  return (int64_t)L.total;
+}
+
+int64_t bfcnn_num_trainable(const bfcnn_arch* arch) {
+  if (validate_arch(arch) != BFCNN_OK) return BFCNN_ERR_INVALID_ARGUMENT;
+  VarLayout L;
+  L.build(*arch);
+  return (int64_t)L.t_total;
+}
+
+int bfcnn_create(const bfcnn_arch* arch, const float* weights, size_t n_floats, int device, bfcnn_handle** out) {
+  BF_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  BF_CHECK(validate_arch(arch));
+  BF_REQUIRE(weights != nullptr, "weights is NULL");
+  int ndev = 0;
+  BF_CUDA(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) {
+    set_error("no CUDA device visible: libbfcnn_b200 has no CPU path");
+    return BFCNN_ERR_CUDA;
+  }
+  BF_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  BF_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return BFCNN_ERR_UNSUPPORTED;
+  }
+  bfcnn_handle* h = new (std::nothrow) bfcnn_handle();
+  if (!h) { set_error("out of host memory"); return BFCNN_ERR_OUT_OF_MEMORY; }
+  h->arch = *arch;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->lay.build(*arch);
+  if (n_floats != h->lay.total) {
+    set_error("invalid argument: expected %zu weight floats, got %zu", h->lay.total, n_floats);
+    delete h;
+    return BFCNN_ERR_INVALID_ARGUMENT;
+  }
+  h->h_vars.assign(weights, weights + n_floats);
+  int s = pack_weights(h);
+  if (s == BFCNN_OK && cudaEventCreate(&h->ev0) != cudaSuccess) s = BFCNN_ERR_CUDA;
+  if (s == BFCNN_OK && cudaEventCreate(&h->ev1) != cudaSuccess) s = BFCNN_ERR_CUDA;
+  if (s != BFCNN_OK) { bfcnn_destroy(h); return s; }
+  *out = h;
+  return BFCNN_OK;
+}
+
+void bfcnn_destroy(bfcnn_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  h->d_vars.release(); h->d_base_f32.release(); h->d_conv_f32.release(); h->d_bias_f32.release();
+  h->d_head_f32.release(); h->d_conv_frag.release(); h->d_base_frag.release();
+  h->ws_in.release(); h->ws_out.release();
+  for (auto& b : h->ws_feat) b.release();
+  h->ws_train.release(); h->ws_stats.release(); h->ws_grads.release();
+  h->adam_m.release(); h->adam_v.release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+}
+
+int bfcnn_set_weights(bfcnn_handle* h, const float* weights, size_t n_floats) {
+  BF_REQUIRE(h != nullptr && weights != nullptr, "NULL argument");
+  if (n_floats != h->lay.total) {
+    set_error("invalid argument: expected %zu weight floats, got %zu", h->lay.total, n_floats);
+    return BFCNN_ERR_INVALID_ARGUMENT;
+  }
+  BF_CUDA(cudaSetDevice(h->device));
+  BF_CUDA(cudaDeviceSynchronize());
+  h->h_vars.assign(weights, weights + n_floats);
+  return pack_weights(h);
+}
+
+int bfcnn_get_weights(bfcnn_handle* h, float* weights, size_t n_floats) {
+  BF_REQUIRE(h != nullptr && weights != nullptr, "NULL argument");
+  if (n_floats != h->lay.total) {
+    set_error("invalid argument: expected %zu weight floats, got %zu", h->lay.total, n_floats);
+    return BFCNN_ERR_INVALID_ARGUMENT;
+  }
+  BF_CUDA(cudaSetDevice(h->device));
+  // the device copy is authoritative (training updates it in place)
+  BF_CUDA(cudaDeviceSynchronize());
+  BF_CUDA(cudaMemcpy(h->h_vars.data(), h->d_vars.p, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+  memcpy(weights, h->h_vars.data(), n_floats * sizeof(float));
+  return BFCNN_OK;
+}
+
+int bfcnn_denoise_u8(bfcnn_handle* h, const uint8_t* in, uint8_t* out, int n, int height, int width,
+                     int precision, uint32_t flags, void* stream) {
+  return denoise_impl(h, in, out, true, n, height, width, precision, flags, stream);
+}
+
+int bfcnn_denoise_f32(bfcnn_handle* h, const uint8_t* in, float* out, int n, int height, int width,
+                      int precision, uint32_t flags, void* stream) {
+  return denoise_impl(h, in, out, false, n, height, width, precision, flags, stream);
+}
+
+int64_t bfcnn_launch_count(const bfcnn_handle* h) { return h ? h->launches : 0; }
+
+int bfcnn_last_stack_ms(bfcnn_handle* h, float* ms) {
+  BF_REQUIRE(h != nullptr && ms != nullptr, "NULL argument");
+  BF_REQUIRE(h->ev_valid, "no denoise call has been timed yet");
+  BF_CUDA(cudaSetDevice(h->device));
+  BF_CUDA(cudaEventSynchronize(h->ev1));
+  BF_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return BFCNN_OK;
+}
+
+int bfcnn_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, float* noisy_f32, int n,
+                  int height, int width, uint64_t seed, uint64_t sample_offset, const bfcnn_noise_cfg* cfg,
+                  void* stream) {
+  BF_REQUIRE(h != nullptr && cfg != nullptr, "NULL argument");
+  BF_CHECK(check_images(n, height, width));
+  if ((size_t)n * height * width == 0) return BFCNN_OK;
+  BF_REQUIRE(clean_u8 != nullptr && noisy_f32 != nullptr, "NULL image pointer");
+  BF_CUDA(cudaSetDevice(h->device));
+  return run_corrupt(h, clean_u8, clean_f32, noisy_f32, n, height, width, seed, sample_offset, cfg,
+                     (cudaStream_t)stream);
+}
+
+int bfcnn_loss(bfcnn_handle* h, const float* gt, const float* pred, int n, int height, int width,
+               const bfcnn_loss_cfg* cfg, float* out4, void* stream) {
+  BF_REQUIRE(h != nullptr && cfg != nullptr && out4 != nullptr, "NULL argument");
+  BF_CHECK(check_images(n, height, width));
+  BF_REQUIRE((size_t)n * height * width > 0, "loss of an empty batch is undefined");
+  BF_REQUIRE(gt != nullptr && pred != nullptr, "NULL image pointer");
+  BF_CUDA(cudaSetDevice(h->device));
+  return run_loss(h, gt, pred, n, height, width, cfg, out4, (cudaStream_t)stream);
+}
+
+int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int n, int height, int width,
+                     const bfcnn_loss_cfg* cfg, float* flat_grads, float* losses4, int update_moving,
+                     void* stream) {
+  BF_REQUIRE(h != nullptr && cfg != nullptr && losses4 != nullptr, "NULL argument");
+  BF_CHECK(check_images(n, height, width));
+  BF_REQUIRE((size_t)n * height * width > 0, "train step on an empty batch is undefined");
+  BF_REQUIRE(clean != nullptr && noisy != nullptr && flat_grads != nullptr, "NULL pointer");
+  BF_CUDA(cudaSetDevice(h->device));
+  return run_train_step(h, clean, noisy, n, height, width, cfg, flat_grads, losses4, update_moving,
+                        (cudaStream_t)stream);
+}
+
+int bfcnn_adam_step(bfcnn_handle* h, const float* flat_grads, float grad_scale, const bfcnn_adam_cfg* cfg,
+                    int64_t step, void* stream) {
+  BF_REQUIRE(h != nullptr && cfg != nullptr && flat_grads != nullptr, "NULL argument");
+  BF_REQUIRE(step >= 1, "step counts from 1");
+  BF_CUDA(cudaSetDevice(h->device));
+  return run_adam_step(h, flat_grads, grad_scale, cfg, step, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// common.cuh -- handle, error plumbing and shared geometry of libbfcnn_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bfcnn_b200.h"
+
+namespace bfcnn {
+
+constexpr int C = 16;  // channels of every backbone conv
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define BF_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      bfcnn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                         \
+      return (_e == cudaErrorMemoryAllocation) ? BFCNN_ERR_OUT_OF_MEMORY : BFCNN_ERR_CUDA; \
+    }                                                                                     \
+  } while (0)
+
+#define BF_CHECK(expr)            \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != BFCNN_OK) return _s; \
+  } while (0)
+
+#define BF_REQUIRE(cond, msg)                      \
+  do {                                             \
+    if (!(cond)) {                                 \
+      bfcnn::set_error("invalid argument: %s", msg); \
+      return BFCNN_ERR_INVALID_ARGUMENT;           \
+    }                                              \
+  } while (0)
+
+// A grow-only device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t n);
+  void release();
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Offsets (in floats) of the Keras-order flat variable vector.
+struct VarLayout {
+  int N, k0, F;
+  size_t base;                   // [k0,k0,3,16]
+  std::vector<size_t> wa, wb, gamma, mean, var;
+  size_t h0, h1, total;
+  // trainable subset (Keras trainable_variables order): base, (wa, wb, gamma)*N, h0, h1
+  size_t t_base;
+  std::vector<size_t> t_wa, t_wb, t_gamma;
+  size_t t_h0, t_h1, t_total;
+  void build(const bfcnn_arch& a);
+};
+
+// Work extent of one denoise call: the image lives on a pow2 canvas with raw
+// zeros bottom/right; only rows < He = min(Hc, H+R) and cols < We = min(Wc, W+R) can
+// influence the cropped output, so every feature map is computed on [0,He) x [0,We).
+struct Extent {
+  int n, h, w;    // image
+  int he, we;     // work extent
+};
+
+}  // namespace bfcnn
+
+struct bfcnn_handle {
+  bfcnn_arch arch;
+  int device = 0;
+  bfcnn::VarLayout lay;
+  std::vector<float> h_vars;  // Keras-order host copy
+
+  // raw variables on the device (training reads/updates these)
+  bfcnn::DevBuf d_vars;
+  // inference-time folded / packed weights
+  bfcnn::DevBuf d_base_f32;   // [k0*k0*3][16]
+  bfcnn::DevBuf d_conv_f32;   // [2N][9][16 cin][16 cout], conv_b folded with BN scale
+  bfcnn::DevBuf d_bias_f32;   // [2N][16], zero for conv_a, BN constant for conv_b
+  bfcnn::DevBuf d_head_f32;   // [16][4] collapsed head (4th column zero)
+  bfcnn::DevBuf d_conv_frag;  // HMMA B fragments: [2N][hi/lo][9][2][32] uint2
+  bfcnn::DevBuf d_base_frag;  // HMMA B fragments of the base conv (K padded to 32)
+  bool packed_valid = false;
+
+  // workspaces
+  bfcnn::DevBuf ws_in, ws_out;          // staging for host<->device images
+  bfcnn::DevBuf ws_feat[3];             // feature maps
+  bfcnn::DevBuf ws_train;               // saved activations for backward
+  bfcnn::DevBuf ws_stats;               // BN batch statistics, reductions
+  bfcnn::DevBuf ws_grads;               // scratch gradients
+  bfcnn::DevBuf adam_m, adam_v;         // Adam moments over the trainable vector
+
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int sm_count = 148;
+};
+
+namespace bfcnn {
+int pack_weights(bfcnn_handle* h);  // host fold + upload (host_pack.cu)
+}

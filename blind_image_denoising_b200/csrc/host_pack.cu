@@ -1,0 +1,139 @@
+// host_pack.cu -- variable layout, BN folding, head collapse and packing into kernel layouts.
+//
+// Folding: Keras BatchNormalization(center=False) still subtracts the moving mean,
+// so conv_b + BN(inference) == conv with w' = w*gamma/sqrt(var+eps) plus the per-channel
+// constant b' = -mean*gamma/sqrt(var+eps)   (backbone_resnet.py:129-135, constants.py:9).
+// The two linear 1x1 head convs (model.py:297-340) multiply into one [16,3] matrix.
+// All folding is done in double and rounded once.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace bfcnn {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int DevBuf::reserve(size_t n) {
+  if (n <= bytes) return BFCNN_OK;
+  release();
+  const size_t want = (n + 255) & ~size_t(255);
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? BFCNN_ERR_OUT_OF_MEMORY : BFCNN_ERR_CUDA;
+  }
+  bytes = want;
+  return BFCNN_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+void VarLayout::build(const bfcnn_arch& a) {
+  N = a.no_layers; k0 = a.base_kernel; F = a.head_filters;
+  wa.assign(N, 0); wb.assign(N, 0); gamma.assign(N, 0); mean.assign(N, 0); var.assign(N, 0);
+  t_wa.assign(N, 0); t_wb.assign(N, 0); t_gamma.assign(N, 0);
+  size_t o = 0, t = 0;
+  base = o; t_base = t; o += (size_t)k0 * k0 * 3 * C; t += (size_t)k0 * k0 * 3 * C;
+  for (int i = 0; i < N; ++i) {
+    wa[i] = o; t_wa[i] = t; o += 9 * C * C; t += 9 * C * C;
+    wb[i] = o; t_wb[i] = t; o += 9 * C * C; t += 9 * C * C;
+    gamma[i] = o; t_gamma[i] = t; o += C; t += C;
+    mean[i] = o; o += C;
+    var[i] = o; o += C;
+  }
+  h0 = o; t_h0 = t; o += (size_t)C * F; t += (size_t)C * F;
+  h1 = o; t_h1 = t; o += (size_t)F * 3; t += (size_t)F * 3;
+  total = o; t_total = t;
+}
+
+// B fragment of mma.m16n8k16 (B is K x N "col"): lane holds
+//   reg0 = {B[2q][g], B[2q+1][g]}, reg1 = {B[2q+8][g], B[2q+9][g]},  g = lane>>2, q = lane&3
+// with K = cin, N = cout - 8*ntile.
+static void pack_frag(const float* w /*[16 cin][16 cout]*/, int ntile, uint32_t* dst /*[32][2]*/, bool lo) {
+  for (int lane = 0; lane < 32; ++lane) {
+    const int g = lane >> 2, q = lane & 3;
+    const int co = ntile * 8 + g;
+    __half hv[4];
+    const int ks[4] = {2 * q, 2 * q + 1, 2 * q + 8, 2 * q + 9};
+    for (int i = 0; i < 4; ++i) {
+      const float v = w[ks[i] * C + co];
+      const __half hi = __float2half_rn(v);
+      hv[i] = lo ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
+    uint16_t b[4];
+    memcpy(b, hv, sizeof(b));
+    dst[lane * 2 + 0] = (uint32_t)b[0] | ((uint32_t)b[1] << 16);
+    dst[lane * 2 + 1] = (uint32_t)b[2] | ((uint32_t)b[3] << 16);
+  }
+}
+
+int pack_weights(bfcnn_handle* h) {
+  const VarLayout& L = h->lay;
+  const float* v = h->h_vars.data();
+  const int N = L.N, k0 = L.k0, F = L.F;
+  const double eps = (double)h->arch.bn_epsilon;
+
+  std::vector<float> conv((size_t)2 * N * 9 * C * C), bias((size_t)2 * N * C, 0.f), head(C * 4, 0.f);
+  for (int i = 0; i < N; ++i) {
+    memcpy(&conv[(size_t)(2 * i) * 9 * C * C], v + L.wa[i], sizeof(float) * 9 * C * C);
+    double s[C];
+    for (int c = 0; c < C; ++c) {
+      s[c] = (double)v[L.gamma[i] + c] / sqrt((double)v[L.var[i] + c] + eps);
+      bias[(size_t)(2 * i + 1) * C + c] = (float)(-(double)v[L.mean[i] + c] * s[c]);
+    }
+    float* dst = &conv[(size_t)(2 * i + 1) * 9 * C * C];
+    for (int k = 0; k < 9 * C; ++k)
+      for (int c = 0; c < C; ++c) dst[k * C + c] = (float)((double)v[L.wb[i] + k * C + c] * s[c]);
+  }
+  for (int ci = 0; ci < C; ++ci)
+    for (int o = 0; o < 3; ++o) {
+      double a = 0.0;
+      for (int f = 0; f < F; ++f) a += (double)v[L.h0 + ci * F + f] * (double)v[L.h1 + f * 3 + o];
+      head[ci * 4 + o] = (float)a;
+    }
+
+  // HMMA fragments: [conv 2N][plane hi/lo][tap 9][ntile 2][lane 32][2] uint32
+  std::vector<uint32_t> frag((size_t)2 * N * 2 * 9 * 2 * 64);
+  for (int l = 0; l < 2 * N; ++l)
+    for (int pl = 0; pl < 2; ++pl)
+      for (int tap = 0; tap < 9; ++tap)
+        for (int nt = 0; nt < 2; ++nt)
+          pack_frag(&conv[((size_t)l * 9 + tap) * C * C], nt,
+                    &frag[((((size_t)l * 2 + pl) * 9 + tap) * 2 + nt) * 64], pl == 1);
+
+  BF_CUDA(cudaSetDevice(h->device));
+  const size_t nbase = (size_t)k0 * k0 * 3 * C;
+  BF_CHECK(h->d_vars.reserve(L.total * sizeof(float)));
+  BF_CHECK(h->d_base_f32.reserve(nbase * sizeof(float)));
+  BF_CHECK(h->d_conv_f32.reserve(std::max<size_t>(conv.size(), 1) * sizeof(float)));
+  BF_CHECK(h->d_bias_f32.reserve(std::max<size_t>(bias.size(), 1) * sizeof(float)));
+  BF_CHECK(h->d_head_f32.reserve(head.size() * sizeof(float)));
+  BF_CHECK(h->d_conv_frag.reserve(std::max<size_t>(frag.size(), 1) * sizeof(uint32_t)));
+  BF_CUDA(cudaMemcpy(h->d_vars.p, v, L.total * sizeof(float), cudaMemcpyHostToDevice));
+  BF_CUDA(cudaMemcpy(h->d_base_f32.p, v + L.base, nbase * sizeof(float), cudaMemcpyHostToDevice));
+  if (N > 0) {
+    BF_CUDA(cudaMemcpy(h->d_conv_f32.p, conv.data(), conv.size() * sizeof(float), cudaMemcpyHostToDevice));
+    BF_CUDA(cudaMemcpy(h->d_bias_f32.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    BF_CUDA(cudaMemcpy(h->d_conv_frag.p, frag.data(), frag.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  BF_CUDA(cudaMemcpy(h->d_head_f32.p, head.data(), head.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->packed_valid = true;
+  return BFCNN_OK;
+}
+
+}  // namespace bfcnn

@@ -1,0 +1,39 @@
+// kernels.cuh -- launchers shared between the translation units of libbfcnn_b200.so
+#pragma once
+#include <algorithm>
+#include "common.cuh"
+
+namespace bfcnn {
+
+// model.py:342 tanh(2y)*0.51, then utilities.py:435-443 (clip(+-0.5)+0.5)*255
+__device__ __forceinline__ float head_activation(float y) {
+  float t = tanhf(2.0f * y) * 0.51f;
+  t = fminf(fmaxf(t, -0.5f), 0.5f);
+  return (t + 0.5f) * 255.0f;
+}
+
+// ---- conv_f32.cu
+int launch_base_conv(bfcnn_handle* h, const void* img, bool img_is_u8, float* out, const float* w,
+                     const Extent& e, cudaStream_t st);
+int launch_conv3x3_f32(bfcnn_handle* h, const float* in, float* out, const float* w, const float* bias,
+                       const float* res, double* stats, bool relu, const Extent& e, cudaStream_t st);
+int launch_head(bfcnn_handle* h, const float* feat, void* out, bool out_u8, const float* wh,
+                const Extent& e, cudaStream_t st);
+
+// ---- fused_f16.cu: the fused tensor-core stack (F16 / F16X3)
+int run_fused_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
+                    int precision, cudaStream_t st);
+
+// ---- train.cu
+int run_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, float* noisy_f32, int n,
+                int height, int width, uint64_t seed, uint64_t sample_offset,
+                const bfcnn_noise_cfg* cfg, cudaStream_t st);
+int run_loss(bfcnn_handle* h, const float* gt, const float* pred, int n, int height, int width,
+             const bfcnn_loss_cfg* cfg, float* out4, cudaStream_t st);
+int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int n, int height,
+                   int width, const bfcnn_loss_cfg* cfg, float* flat_grads, float* losses4,
+                   int update_moving, cudaStream_t st);
+int run_adam_step(bfcnn_handle* h, const float* flat_grads, float grad_scale, const bfcnn_adam_cfg* cfg,
+                  int64_t step, cudaStream_t st);
+
+}  // namespace bfcnn

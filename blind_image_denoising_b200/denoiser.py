@@ -1,0 +1,117 @@
+"""Host-side mirror of the reference's inference callable.
+
+`Denoiser.__call__(uint8[N,H,W,3]) -> uint8[N,H,W,3]` has the signature and semantics of
+`DenoiserModule.__call__` (reference bfcnn/module_denoiser.py:39-75), which is what
+`bfcnn.load_model(name)` returns in the reference (bfcnn/__init__.py:81-97).  All arithmetic
+runs in libbfcnn_b200.so on a B200; this file only moves pointers.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from .arch import Arch
+from .weights import flatten_variables, unflatten_variables
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+class Denoiser:
+    """One model instance bound to one GPU (one handle per device)."""
+
+    def __init__(self, arch: Arch, variables: Sequence[np.ndarray], *, device: int = 0,
+                 precision: str = "f16x3", pad_pow2: bool = True, name: str = ""):
+        self._lib = _native.load_library()
+        self.arch = arch
+        self.name = name
+        self.device = int(device)
+        self.precision = precision
+        self.pad_pow2 = bool(pad_pow2)
+        if precision not in _native.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_native.PRECISIONS)}")
+        flat = np.ascontiguousarray(flatten_variables(arch, variables), dtype=np.float32)
+        carch = arch.to_c()
+        h = ctypes.c_void_p()
+        _native.check(self._lib.bfcnn_create(ctypes.byref(carch), flat.ctypes.data, flat.size,
+                                             self.device, ctypes.byref(h)))
+        self._h = h
+
+    # ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bfcnn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def get_weights(self):
+        flat = np.empty(self.arch.num_weights(), dtype=np.float32)
+        _native.check(self._lib.bfcnn_get_weights(self._h, flat.ctypes.data, flat.size))
+        return unflatten_variables(self.arch, flat)
+
+    def set_weights(self, variables: Sequence[np.ndarray]):
+        flat = np.ascontiguousarray(flatten_variables(self.arch, variables), dtype=np.float32)
+        _native.check(self._lib.bfcnn_set_weights(self._h, flat.ctypes.data, flat.size))
+
+    def launch_count(self) -> int:
+        return int(self._lib.bfcnn_launch_count(self._h))
+
+    def last_stack_ms(self) -> float:
+        ms = ctypes.c_float()
+        _native.check(self._lib.bfcnn_last_stack_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    # ------------------------------------------------------------------
+    def __call__(self, image, *, precision: Optional[str] = None, pad_pow2: Optional[bool] = None,
+                 return_float: bool = False, out=None):
+        """uint8 [N,H,W,3] (numpy, torch-CPU or torch-CUDA) -> same container type.
+
+        return_float=True returns the float32 prediction before round/cast (0..255)."""
+        prec = _native.PRECISIONS[precision or self.precision]
+        flags = 0 if (self.pad_pow2 if pad_pow2 is None else pad_pow2) else _native.FLAG_NO_PAD_POW2
+        fn = self._lib.bfcnn_denoise_f32 if return_float else self._lib.bfcnn_denoise_u8
+
+        if _is_torch(image):
+            import torch
+            if image.dtype != torch.uint8:
+                raise TypeError("image must be uint8")  # tf.TensorSpec(dtype=tf.uint8), module_denoiser.py:44
+            if image.dim() != 4 or image.shape[-1] != 3:
+                raise ValueError("image must have shape [N,H,W,3]")
+            x = image.contiguous()
+            n, h, w, _ = x.shape
+            odt = torch.float32 if return_float else torch.uint8
+            if out is None:
+                out = torch.empty((n, h, w, 3), dtype=odt, device=x.device)
+            stream = None
+            if x.is_cuda:
+                if x.device.index != self.device:
+                    raise ValueError(f"tensor is on cuda:{x.device.index}, model on cuda:{self.device}")
+                flags |= _native.FLAG_IN_DEVICE | _native.FLAG_OUT_DEVICE
+                stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            _native.check(fn(self._h, x.data_ptr(), out.data_ptr(), n, h, w, prec, flags, stream))
+            return out
+
+        x = np.asarray(image)
+        if x.dtype != np.uint8:
+            raise TypeError("image must be uint8")
+        if x.ndim != 4 or x.shape[-1] != 3:
+            raise ValueError("image must have shape [N,H,W,3]")
+        x = np.ascontiguousarray(x)
+        n, h, w, _ = x.shape
+        if out is None:
+            out = np.empty((n, h, w, 3), dtype=np.float32 if return_float else np.uint8)
+        _native.check(fn(self._h, x.ctypes.data, out.ctypes.data, n, h, w, prec, flags, None))
+        return out

@@ -1,0 +1,165 @@
+/*
+ * bfcnn_b200.h -- C ABI of libbfcnn_b200.so: the B200 (sm_100a) hot path of the bfcnn
+ * bias-free ResNet denoiser (resnet_color_1xN_bn_16x3x3) and of the training step
+ * that feeds it.
+ *
+ * The reference (NikolasMarkou/blind_image_denoising, bfcnn 3.2.0) is pure
+ * Python/TensorFlow and has NO FFI layer; its "operator interface" for
+ * this path is a handful of Python callables.  Each entry point below names the
+ * reference callable (file:line under /root/reference) whose arithmetic it replaces.
+ * The Python package `blind_image_denoising_b200` (and its `bfcnn` alias) binds these
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (BFCNN_OK) or a negative bfcnn_status; the message of
+ *     the last failure on the calling thread is available from bfcnn_last_error();
+ *   - nothing throws across the ABI and nothing ever falls back to the CPU: without a
+ *     usable CUDA device every compute call fails with BFCNN_ERR_CUDA;
+ *   - the caller owns every in/out buffer; the handle owns weights and workspaces;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *     calls on one handle are stream-ordered and not re-entrant; one handle per device;
+ *   - images are NHWC uint8 / float32, C = 3; weights are ONE flat float32 vector in
+ *     Keras `hydra.variables` order (see bfcnn_num_weights).
+ */
+#ifndef BFCNN_B200_H_
+#define BFCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFCNN_ABI_VERSION 1
+
+typedef enum bfcnn_status {
+  BFCNN_OK = 0,
+  BFCNN_ERR_INVALID_ARGUMENT = -1,
+  BFCNN_ERR_CUDA = -2,
+  BFCNN_ERR_OUT_OF_MEMORY = -3,
+  BFCNN_ERR_UNSUPPORTED = -4,
+  BFCNN_ERR_INTERNAL = -5
+} bfcnn_status;
+
+/* Arithmetic the conv stack runs in (bfcnn_denoise_*). */
+typedef enum bfcnn_precision {
+  BFCNN_PREC_FP32 = 0,   /* FP32 FFMA, layer by layer: the reference-grade path            */
+  BFCNN_PREC_F16 = 1,    /* fused tensor-core stack, fp16 operands, fp32 accumulate         */
+  BFCNN_PREC_F16X3 = 2   /* fused tensor-core stack, fp16 hi/lo split (3 MMAs): fp32-grade  */
+} bfcnn_precision;
+
+/* Flags of bfcnn_denoise_*. */
+#define BFCNN_FLAG_IN_DEVICE   1u  /* `in` is a device pointer (else host)                        */
+#define BFCNN_FLAG_OUT_DEVICE  2u  /* `out` is a device pointer (else host)                       */
+#define BFCNN_FLAG_NO_PAD_POW2 4u  /* do NOT emulate pad_to_power_of_2 (utilities.py:736-751)     */
+
+/* Hyper-parameters of bfcnn/backbone_resnet.py:19-49 + bfcnn/model.py:267-275 for the
+ * 16-channel, two-3x3-convs-per-block family. */
+typedef struct bfcnn_arch {
+  int32_t no_layers;     /* N residual blocks                      */
+  int32_t base_kernel;   /* k0 of the base conv (odd, <= 7)        */
+  int32_t filters;       /* 16                                     */
+  int32_t head_filters;  /* F of the 1x1 head (model.py:268)       */
+  int32_t in_channels;   /* 3                                      */
+  int32_t out_channels;  /* 3                                      */
+  float bn_epsilon;      /* constants.py:9  (1e-3)                 */
+  float bn_momentum;     /* constants.py:11 (0.995)                */
+} bfcnn_arch;
+
+/* dataset.py:94-99,170-187 noise ranges + the sub-sampling corruption of README.md:49-55. */
+typedef struct bfcnn_noise_cfg {
+  float additive_min, additive_max;             /* sigma_add ~ U(min,max); max<=0 disables  */
+  float multiplicative_min, multiplicative_max; /* sigma_mul ~ U(min,max); max<=0 disables  */
+  int32_t random_left_right;                    /* dataset.py:141-148                       */
+  int32_t random_up_down;                       /* dataset.py:150-158                       */
+  int32_t subsample;                            /* 1: w.p. 1/2 decimate x2 + nearest up x2  */
+  int32_t round_values;                         /* dataset.py:228                           */
+} bfcnn_noise_cfg;
+
+/* loss.py:152-187 configuration (ssim_multiplier must be 0 on this path). */
+typedef struct bfcnn_loss_cfg {
+  float hinge;           /* loss.py:165 */
+  float cutoff;          /* loss.py:166 */
+  float mae_multiplier;  /* loss.py:169 */
+  float mse_multiplier;  /* loss.py:177 */
+  float regularization;  /* loss.py:181 */
+} bfcnn_loss_cfg;
+
+/* fused Adam of optimizer.py:145-224 (row N1). */
+typedef struct bfcnn_adam_cfg {
+  float learning_rate, beta_1, beta_2, epsilon;
+  float global_clipnorm; /* <= 0 disables (optimizer.py:169) */
+} bfcnn_adam_cfg;
+
+typedef struct bfcnn_handle bfcnn_handle;
+
+/* ---- library ---------------------------------------------------------------- */
+int bfcnn_abi_version(void);
+const char* bfcnn_last_error(void);
+/* number of visible CUDA devices, or a negative status (never "0 and carry on"). */
+int bfcnn_device_count(void);
+/* floats in the flat Keras-order variable vector / in the trainable subset. */
+int64_t bfcnn_num_weights(const bfcnn_arch* arch);
+int64_t bfcnn_num_trainable(const bfcnn_arch* arch);
+
+/* ---- model ------------------------------------------------------------------
+ * replaces: bfcnn.load_model / tf.saved_model.load (bfcnn/__init__.py:81-97) and
+ * model_builder (bfcnn/model.py:58-162) for this family.  `weights` (host) holds
+ * bfcnn_num_weights(arch) floats: base kernel [k0,k0,3,16] HWIO, then per block
+ * W_a, W_b [3,3,16,16], gamma, moving_mean, moving_var [16], then head [1,1,16,F],
+ * [1,1,F,3].  BN is folded into W_b + a per-channel constant at load. */
+int bfcnn_create(const bfcnn_arch* arch, const float* weights, size_t n_floats, int device,
+                 bfcnn_handle** out);
+void bfcnn_destroy(bfcnn_handle* h);
+int bfcnn_set_weights(bfcnn_handle* h, const float* weights, size_t n_floats);
+int bfcnn_get_weights(bfcnn_handle* h, float* weights, size_t n_floats);
+
+/* ---- inference ----------------------------------------------------------------
+ * replaces: DenoiserModule.__call__ (bfcnn/module_denoiser.py:39-75):
+ * uint8 NHWC -> float -> [pow2 canvas] -> normalise -> resnet -> head -> tanh(2y)*0.51
+ * -> denormalise -> [crop] -> round-half-even -> uint8 NHWC. */
+int bfcnn_denoise_u8(bfcnn_handle* h, const uint8_t* in, uint8_t* out, int n, int height, int width,
+                     int precision, uint32_t flags, void* stream);
+/* same, but returns the pre-round float32 prediction (0..255 scale) for parity checks. */
+int bfcnn_denoise_f32(bfcnn_handle* h, const uint8_t* in, float* out, int n, int height, int width,
+                      int precision, uint32_t flags, void* stream);
+/* kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t bfcnn_launch_count(const bfcnn_handle* h);
+/* record/elapse device time spent in the conv-stack kernels of the LAST denoise call
+ * (events on the caller's stream; ms).  Used for the roofline of the dominant kernel. */
+int bfcnn_last_stack_ms(bfcnn_handle* h, float* ms);
+
+/* ---- training step -------------------------------------------------------------
+ * replaces: dataset_builder.prepare_data_fn (bfcnn/dataset.py:120-238).
+ * clean_u8 [n,h,w,3] -> clean_f32, noisy_f32 [n,h,w,3] (device pointers).  Sample s
+ * uses Philox4x32-10 stream (seed, sample_offset + s): bit-identical to the oracle. */
+int bfcnn_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, float* noisy_f32,
+                  int n, int height, int width, uint64_t seed, uint64_t sample_offset,
+                  const bfcnn_noise_cfg* cfg, void* stream);
+
+/* replaces: loss_function_builder(...)["denoiser"] (bfcnn/loss.py:190-247), ssim off.
+ * gt, pred: device float32 [n,h,w,3]; out4 (host): total, mae, rmse, hinged-mae. */
+int bfcnn_loss(bfcnn_handle* h, const float* gt, const float* pred, int n, int height, int width,
+               const bfcnn_loss_cfg* cfg, float* out4, void* stream);
+
+/* replaces: train_step_single_gpu (bfcnn/train_loop.py:263-312): forward with BN batch
+ * statistics, hinged-MAE (+RMSE) loss, L1/L2 weight regularisation, backward.
+ * clean, noisy: device float32 [n,h,w,3] (0..255).  flat_grads: device float32
+ * [bfcnn_num_trainable] in Keras trainable_variables order (the buffer a data-parallel
+ * caller all-reduces).  losses4 (host): total, denoiser total, mae, regularisation.
+ * update_moving != 0 applies the BN moving-statistics update (momentum 0.995). */
+int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int n, int height,
+                     int width, const bfcnn_loss_cfg* cfg, float* flat_grads, float* losses4,
+                     int update_moving, void* stream);
+
+/* replaces: optimizer.apply_gradients with keras Adam + global_clipnorm
+ * (bfcnn/optimizer.py:145-224, bfcnn/train_loop.py:314-321, 421-434).  flat_grads is
+ * the (all-reduced, averaged) device gradient; step counts from 1. */
+int bfcnn_adam_step(bfcnn_handle* h, const float* flat_grads, float grad_scale,
+                    const bfcnn_adam_cfg* cfg, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFCNN_B200_H_ */
