@@ -84,8 +84,8 @@ int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int
       const float* wa = h->d_conv_f32.as<float>() + (size_t)(2 * i) * 9 * C * C;
       const float* wb = h->d_conv_f32.as<float>() + (size_t)(2 * i + 1) * 9 * C * C;
       const float* bb = h->d_bias_f32.as<float>() + (size_t)(2 * i + 1) * C;
-      BF_CHECK(launch_conv3x3_f32(h, X, T, wa, nullptr, nullptr, nullptr, true, e, st));
-      BF_CHECK(launch_conv3x3_f32(h, T, X, wb, bb, X, nullptr, false, e, st));
+      BF_CHECK(launch_conv3x3_f32(h, X, T, wa, nullptr, nullptr, nullptr, CONV_RELU, e, st));
+      BF_CHECK(launch_conv3x3_f32(h, T, X, wb, bb, X, nullptr, CONV_RESIDUAL, e, st));
     }
     BF_CHECK(launch_head(h, X, d_out, out_u8, h->d_head_f32.as<float>(), e, st));
   } else {

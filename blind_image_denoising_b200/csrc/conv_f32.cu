@@ -93,12 +93,12 @@ constexpr size_t CT_SMEM = (size_t)(CT_IN_FLOATS + CT_W_FLOATS + 2 * C) * sizeof
 
 __device__ __forceinline__ int ct_plane_base(int c) { return c * CT_PLANE + 8 * (c >> 2); }
 
-template <bool RELU, bool RESIDUAL, bool STATS>
+template <bool RELU, bool RESIDUAL, bool STATS, bool MASK>
 __global__ void __launch_bounds__(256, 2)
 conv3x3_c16_kernel(const float* __restrict__ in, float* __restrict__ out,
                    const float* __restrict__ w,      // [9][16 cin][16 cout]
                    const float* __restrict__ bias,   // [16] or nullptr
-                   const float* __restrict__ res,    // NHWC residual or nullptr
+                   const float* __restrict__ res,    // NHWC residual (RESIDUAL) / ReLU mask source (MASK)
                    double* __restrict__ stats,       // [2][16] sum, sumsq (STATS)
                    int he, int we) {
   extern __shared__ __align__(16) float smem[];
@@ -198,6 +198,11 @@ conv3x3_c16_kernel(const float* __restrict__ in, float* __restrict__ out,
           const float4 rv = *reinterpret_cast<const float4*>(res + o + 4 * q);
           r.x += rv.x; r.y += rv.y; r.z += rv.z; r.w += rv.w;
         }
+        if (MASK) {  // ReLU backward: pass the gradient where the saved activation is > 0
+          const float4 mv = *reinterpret_cast<const float4*>(res + o + 4 * q);
+          r.x = mv.x > 0.f ? r.x : 0.f; r.y = mv.y > 0.f ? r.y : 0.f;
+          r.z = mv.z > 0.f ? r.z : 0.f; r.w = mv.w > 0.f ? r.w : 0.f;
+        }
         *reinterpret_cast<float4*>(out + o + 4 * q) = r;
       }
     }
@@ -219,32 +224,40 @@ conv3x3_c16_kernel(const float* __restrict__ in, float* __restrict__ out,
 }
 
 int launch_conv3x3_f32(bfcnn_handle* h, const float* in, float* out, const float* w, const float* bias,
-                       const float* res, double* stats, bool relu, const Extent& e, cudaStream_t st) {
+                       const float* res, double* stats, ConvEpi epi, const Extent& e, cudaStream_t st) {
   static bool attr_set = false;
   auto set_attr = [](const void* f) {
     return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM);
   };
   if (!attr_set) {
-    BF_CUDA(set_attr((const void*)conv3x3_c16_kernel<true, false, false>));
-    BF_CUDA(set_attr((const void*)conv3x3_c16_kernel<false, true, false>));
-    BF_CUDA(set_attr((const void*)conv3x3_c16_kernel<false, false, false>));
-    BF_CUDA(set_attr((const void*)conv3x3_c16_kernel<false, false, true>));
+    BF_CUDA(set_attr((const void*)conv3x3_c16_kernel<true, false, false, false>));
+    BF_CUDA(set_attr((const void*)conv3x3_c16_kernel<false, true, false, false>));
+    BF_CUDA(set_attr((const void*)conv3x3_c16_kernel<false, false, false, false>));
+    BF_CUDA(set_attr((const void*)conv3x3_c16_kernel<false, false, true, false>));
+    BF_CUDA(set_attr((const void*)conv3x3_c16_kernel<false, false, false, true>));
     attr_set = true;
   }
   dim3 grid((e.we + CT_W - 1) / CT_W, (e.he + CT_H - 1) / CT_H, e.n);
   BF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "image too large for the FP32 conv grid");
-  if (stats != nullptr) {
-    BF_REQUIRE(!relu && res == nullptr, "stats variant is conv-only");
-    conv3x3_c16_kernel<false, false, true><<<grid, 256, CT_SMEM, st>>>(in, out, w, bias, nullptr, stats, e.he, e.we);
-  } else if (relu && res == nullptr) {
-    conv3x3_c16_kernel<true, false, false><<<grid, 256, CT_SMEM, st>>>(in, out, w, bias, nullptr, nullptr, e.he, e.we);
-  } else if (!relu && res != nullptr) {
-    conv3x3_c16_kernel<false, true, false><<<grid, 256, CT_SMEM, st>>>(in, out, w, bias, res, nullptr, e.he, e.we);
-  } else if (!relu && res == nullptr) {
-    conv3x3_c16_kernel<false, false, false><<<grid, 256, CT_SMEM, st>>>(in, out, w, bias, nullptr, nullptr, e.he, e.we);
-  } else {
-    set_error("unsupported conv epilogue combination");
-    return BFCNN_ERR_INTERNAL;
+  switch (epi) {
+    case CONV_STATS:
+      conv3x3_c16_kernel<false, false, true, false><<<grid, 256, CT_SMEM, st>>>(in, out, w, bias, nullptr, stats, e.he, e.we);
+      break;
+    case CONV_RELU:
+      conv3x3_c16_kernel<true, false, false, false><<<grid, 256, CT_SMEM, st>>>(in, out, w, bias, nullptr, nullptr, e.he, e.we);
+      break;
+    case CONV_RESIDUAL:
+      conv3x3_c16_kernel<false, true, false, false><<<grid, 256, CT_SMEM, st>>>(in, out, w, bias, res, nullptr, e.he, e.we);
+      break;
+    case CONV_MASK:
+      conv3x3_c16_kernel<false, false, false, true><<<grid, 256, CT_SMEM, st>>>(in, out, w, bias, res, nullptr, e.he, e.we);
+      break;
+    case CONV_PLAIN:
+      conv3x3_c16_kernel<false, false, false, false><<<grid, 256, CT_SMEM, st>>>(in, out, w, bias, nullptr, nullptr, e.he, e.we);
+      break;
+    default:
+      set_error("unsupported conv epilogue");
+      return BFCNN_ERR_INTERNAL;
   }
   h->launches++;
   BF_CUDA(cudaGetLastError());

@@ -15,8 +15,9 @@ __device__ __forceinline__ float head_activation(float y) {
 // ---- conv_f32.cu
 int launch_base_conv(bfcnn_handle* h, const void* img, bool img_is_u8, float* out, const float* w,
                      const Extent& e, cudaStream_t st);
+enum ConvEpi { CONV_PLAIN = 0, CONV_RELU = 1, CONV_RESIDUAL = 2, CONV_STATS = 3, CONV_MASK = 4 };
 int launch_conv3x3_f32(bfcnn_handle* h, const float* in, float* out, const float* w, const float* bias,
-                       const float* res, double* stats, bool relu, const Extent& e, cudaStream_t st);
+                       const float* res, double* stats, ConvEpi epi, const Extent& e, cudaStream_t st);
 int launch_head(bfcnn_handle* h, const float* feat, void* out, bool out_u8, const float* wh,
                 const Extent& e, cudaStream_t st);
 
