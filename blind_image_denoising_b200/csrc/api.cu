@@ -71,6 +71,12 @@ int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int
     d_out = h->ws_out.p;
   }
   const Extent e = make_extent(h, n, height, width, flags);
+  if (!h->packed_valid) {
+    // a training / optimiser step changed the variables on the device: fold and pack them again
+    BF_CUDA(cudaDeviceSynchronize());
+    BF_CUDA(cudaMemcpy(h->h_vars.data(), h->d_vars.p, h->lay.total * sizeof(float), cudaMemcpyDeviceToHost));
+    BF_CHECK(pack_weights(h));
+  }
 
   BF_CUDA(cudaEventRecord(h->ev0, st));
   if (precision == BFCNN_PREC_FP32) {
@@ -253,6 +259,7 @@ int bfcnn_loss(bfcnn_handle* h, const float* gt, const float* pred, int n, int h
   BF_CHECK(check_images(n, height, width));
   BF_REQUIRE((size_t)n * height * width > 0, "loss of an empty batch is undefined");
   BF_REQUIRE(gt != nullptr && pred != nullptr, "NULL image pointer");
+  BF_REQUIRE(cfg->hinge >= 0.f && cfg->cutoff > 0.f, "hinge must be >= 0 and cutoff > 0");
   BF_CUDA(cudaSetDevice(h->device));
   return run_loss(h, gt, pred, n, height, width, cfg, out4, (cudaStream_t)stream);
 }
@@ -264,6 +271,7 @@ int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, in
   BF_CHECK(check_images(n, height, width));
   BF_REQUIRE((size_t)n * height * width > 0, "train step on an empty batch is undefined");
   BF_REQUIRE(clean != nullptr && noisy != nullptr && flat_grads != nullptr, "NULL pointer");
+  BF_REQUIRE(cfg->hinge >= 0.f && cfg->cutoff > 0.f, "hinge must be >= 0 and cutoff > 0");
   BF_CUDA(cudaSetDevice(h->device));
   return run_train_step(h, clean, noisy, n, height, width, cfg, flat_grads, losses4, update_moving,
                         (cudaStream_t)stream);

@@ -1,0 +1,241 @@
+"""GPU parity tests of the training step (corruption, loss, forward/backward, Adam) against the CPU
+oracles, through the C ABI (ctypes).  Tolerances: noisy tensor bit-identical; loss within
+1e-5 relative; flat gradient cosine >= 0.9999 and max error <= 1e-3 of the gradient's max-abs."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "training_golden.npz")
+
+
+def _trainer(n_layers, loss=None, opt=None, seed=0, **arch_kw):
+    import blind_image_denoising_b200 as bf
+    from blind_image_denoising_b200.training import Trainer
+    arch = bf.Arch(no_layers=n_layers, **arch_kw)
+    v = bf.synthetic_variables(arch, seed)
+    return arch, v, Trainer(arch, v, device=0, loss_config=loss, optimizer_config=opt)
+
+
+def _noise_cfg(**kw):
+    from blind_image_denoising_b200 import _native
+    from oracle import corrupt_oracle as C
+    oc = C.NoiseConfig(**kw)
+    nc = _native.NoiseCfg(oc.additive_min, oc.additive_max, oc.multiplicative_min, oc.multiplicative_max,
+                          int(oc.random_left_right), int(oc.random_up_down), int(oc.subsample), int(oc.round_values))
+    return oc, nc
+
+
+@pytest.mark.parametrize("shape,kw,seed,offset", [
+    ((8, 32, 40, 3), dict(subsample=True), 1, 0),
+    ((5, 17, 23, 3), dict(), 2 ** 40 + 12345, 2 ** 33 + 7),                  # odd sizes, 64-bit seed / offset
+    ((4, 16, 16, 3), dict(round_values=False, random_left_right=False), 3, 9),
+    ((4, 16, 16, 3), dict(additive_max=0.0, additive_min=0.0), 4, 0),        # multiplicative only
+    ((4, 16, 16, 3), dict(multiplicative_max=0.0, multiplicative_min=0.0, random_up_down=False), 5, 0),
+    ((1, 1, 1, 3), dict(subsample=True), 6, 0),
+])
+def test_corrupt_bit_exact(native_lib, shape, kw, seed, offset):
+    import torch
+    from oracle import corrupt_oracle as C
+    _, _, t = _trainer(1)
+    oc, nc = _noise_cfg(**kw)
+    x = np.random.default_rng(seed % 1000).integers(0, 256, size=shape, dtype=np.uint8)
+    clean_ref, noisy_ref = C.corrupt(x, seed, offset, oc)
+    clean, noisy = t.prepare_data(torch.from_numpy(x).cuda(), nc, seed, offset)
+    assert np.array_equal(clean.cpu().numpy(), clean_ref)
+    got = noisy.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), noisy_ref.view(np.uint32)), \
+        f"{(got != noisy_ref).sum()} of {got.size} values differ, max {np.abs(got - noisy_ref).max()}"
+    t.close()
+
+
+def test_corrupt_golden_and_full_size_statistics(native_lib):
+    import torch
+    _, _, t = _trainer(1)
+    z = np.load(GOLDEN)
+    _, nc = _noise_cfg(subsample=True)
+    clean, noisy = t.prepare_data(torch.from_numpy(z["corrupt_x"]).cuda(), nc, int(z["corrupt_seed"]), int(z["corrupt_offset"]))
+    assert np.array_equal(noisy.cpu().numpy(), z["corrupt_noisy"]) and np.array_equal(clean.cpu().numpy(), z["corrupt_clean"])
+    # BASELINE configs[3] size: 32 x 256 x 256 x 3, additive only, flat grey input -> the noise itself
+    from blind_image_denoising_b200 import _native
+    nc2 = _native.NoiseCfg(20.0, 20.0, 0.0, 0.0, 0, 0, 0, 0)
+    x = torch.full((32, 256, 256, 3), 128, dtype=torch.uint8, device="cuda")
+    clean, noisy = t.prepare_data(x, nc2, 77, 0)
+    d = (noisy - clean).reshape(32, -1)
+    on = d.abs().amax(dim=1) > 0
+    assert 6 <= int(on.sum()) <= 26                      # Bernoulli(1/2) over 32 samples
+    dn = d[on]
+    assert float(dn.abs().max()) < 40.0 + 1e-3           # |z| < 2 sigma
+    assert abs(float(dn.mean())) < 0.05 and abs(float(dn.std()) / 20.0 - 0.8796) < 5e-3
+    # empty batch
+    e = torch.empty((0, 8, 8, 3), dtype=torch.uint8, device="cuda")
+    c0, n0 = t.prepare_data(e, nc, 1, 0)
+    assert c0.shape == (0, 8, 8, 3) and n0.shape == (0, 8, 8, 3)
+    t.close()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.0, regularization=0.01, ssim_multiplier=0.0),
+    dict(hinge=0.0, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=1.0, regularization=0.01, ssim_multiplier=0.0),
+    dict(hinge=2.0, cutoff=30.0, mae_multiplier=0.5, mse_multiplier=2.0, regularization=0.01, ssim_multiplier=0.0),
+])
+def test_loss_matches_oracle(native_lib, cfg):
+    import torch
+    from oracle import bfcnn_oracle as O
+    _, _, t = _trainer(1, loss=cfg)
+    rng = np.random.default_rng(0)
+    gt = rng.integers(0, 256, size=(5, 33, 47, 3)).astype(np.float32)
+    pred = np.clip(gt + rng.normal(0, 12, size=gt.shape), 0, 255).astype(np.float32)
+    pred[0, :4] = gt[0, :4]                       # exact zeros of the error
+    pred[1, :4] = gt[1, :4] - 0.5                 # error exactly at the hinge
+    got = t.denoiser_loss(torch.from_numpy(gt).cuda(), torch.from_numpy(pred).cuda())
+    ref = O.denoiser_loss(torch.from_numpy(gt).double(), torch.from_numpy(pred).double(), hinge=cfg["hinge"],
+                          cutoff=cfg["cutoff"], mae_multiplier=cfg["mae_multiplier"], mse_multiplier=cfg["mse_multiplier"])
+    for k in ("total_loss", "mae_loss", "mse_loss"):
+        assert got[k] == pytest.approx(float(ref[k]), rel=1e-5), k
+    with pytest.raises(Exception):
+        t.denoiser_loss(torch.empty((0, 4, 4, 3), device="cuda"), torch.empty((0, 4, 4, 3), device="cuda"))
+    t.close()
+
+
+def _grad_check(got, ref_list, arch):
+    ref = np.concatenate([g.reshape(-1) for g in ref_list]).astype(np.float64)
+    got = got.astype(np.float64)
+    cos = float(got @ ref / (np.linalg.norm(got) * np.linalg.norm(ref)))
+    assert cos >= 0.9999, cos
+    # per variable: max error relative to that variable's gradient scale
+    from blind_image_denoising_b200.weights import trainable_offsets
+    for (_, n, t_off), g in zip(trainable_offsets(arch), ref_list):
+        r = ref[t_off:t_off + n]
+        e = np.abs(got[t_off:t_off + n] - r).max()
+        assert e <= 1e-3 * max(np.abs(r).max(), 1e-6), (t_off, n, e, np.abs(r).max())
+    return cos
+
+
+@pytest.mark.parametrize("n_layers,shape,loss", [
+    (2, (2, 24, 40, 3), dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.0, regularization=0.01)),
+    (6, (3, 36, 28, 3), dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.0, regularization=0.01)),
+    (3, (2, 70, 66, 3), dict(hinge=0.0, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=1.0, regularization=0.1)),
+    (0, (2, 16, 16, 3), dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.0, regularization=0.01)),
+])
+def test_train_step_matches_oracle(native_lib, n_layers, shape, loss):
+    import torch
+    from oracle import bfcnn_oracle as O
+    from oracle import corrupt_oracle as C
+    arch, v, t = _trainer(n_layers, loss=dict(loss, ssim_multiplier=0.0))
+    x = np.random.default_rng(n_layers).integers(0, 256, size=shape, dtype=np.uint8)
+    clean, noisy = C.corrupt(x, 11, 0, C.NoiseConfig())
+    ref = O.train_step(v, clean, noisy, **loss)
+    total, model_loss, dl, grads = t.train_step_single_gpu(torch.from_numpy(clean).cuda(), torch.from_numpy(noisy).cuda())
+    assert total == pytest.approx(ref["total"], rel=1e-5)
+    assert dl["total_loss"] == pytest.approx(ref["denoiser_total"], rel=1e-5)
+    assert dl["mae_loss"] == pytest.approx(ref["mae"], rel=1e-5)
+    assert model_loss["regularization_loss"] == pytest.approx(ref["reg"], rel=1e-5)
+    _grad_check(grads.cpu().numpy(), ref["grads"], arch)
+    # BN moving statistics (momentum 0.995, unbiased variance)
+    new = t.get_weights()
+    for i, (m, var) in enumerate(ref["new_moving"]):
+        assert np.allclose(new[1 + 5 * i + 3], m, rtol=1e-5, atol=1e-6)
+        assert np.allclose(new[1 + 5 * i + 4], var, rtol=1e-5, atol=1e-6)
+    t.close()
+
+
+def test_train_step_golden_and_base_kernel_7(native_lib):
+    import torch
+    from oracle import bfcnn_oracle as O
+    z = np.load(GOLDEN)
+    loss = dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.5, regularization=0.01, ssim_multiplier=0.0)
+    arch, v, t = _trainer(3, loss=loss)
+    total, ml, dl, grads = t.train_step_single_gpu(torch.from_numpy(z["train_clean"]).cuda(), torch.from_numpy(z["train_noisy"]).cuda(),
+                                                   update_moving=False)
+    assert total == pytest.approx(float(z["train_total"]), rel=1e-5)
+    g, r = grads.cpu().numpy().astype(np.float64), z["train_grads"].astype(np.float64)
+    assert float(g @ r / np.linalg.norm(g) / np.linalg.norm(r)) >= 0.9999
+    assert np.abs(g - r).max() <= 1e-3 * np.abs(r).max()
+    assert all(np.array_equal(a, b) for a, b in zip(t.get_weights(), v))     # update_moving=False leaves variables alone
+    t.close()
+    # k0 = 7 (every in-tree resnet config uses 7, SURVEY 8 notation)
+    arch, v, t = _trainer(1, loss=loss, base_kernel=7)
+    clean = np.random.default_rng(1).integers(0, 256, size=(2, 20, 20, 3)).astype(np.float32)
+    noisy = np.rint(clean + np.random.default_rng(2).normal(0, 10, clean.shape)).astype(np.float32)
+    lk = {k: loss[k] for k in ("hinge", "cutoff", "mae_multiplier", "mse_multiplier", "regularization")}
+    ref = O.train_step(v, clean, noisy, **lk)
+    total, _, _, grads = t.train_step_single_gpu(torch.from_numpy(clean).cuda(), torch.from_numpy(noisy).cuda())
+    assert total == pytest.approx(ref["total"], rel=1e-5)
+    _grad_check(grads.cpu().numpy(), ref["grads"], arch)
+    t.close()
+
+
+def test_adam_and_repack(native_lib):
+    """bfcnn_adam_step vs the oracle's Keras-Adam restatement, then inference with the updated weights."""
+    import torch
+    import blind_image_denoising_b200 as bf
+    from blind_image_denoising_b200.weights import gather_trainables, flatten_variables, trainable_offsets
+    from oracle import bfcnn_oracle as O
+    from oracle import corrupt_oracle as C
+    opt = {"schedule": {"type": "exponential_decay", "config": {"learning_rate": 1e-2, "decay_rate": 0.5, "decay_steps": 2}},
+           "gradient_clipping_by_norm": 0.05}
+    arch, v, t = _trainer(2, opt=opt)
+    flat = flatten_variables(arch, v).astype(np.float64)
+    w = gather_trainables(arch, flat)
+    m, vv = np.zeros_like(w), np.zeros_like(w)
+    rng = np.random.default_rng(0)
+    for step in range(1, 4):
+        g = rng.standard_normal(w.size).astype(np.float32) * 0.01
+        lr = t.apply_grads(torch.from_numpy(g).cuda())
+        assert lr == pytest.approx(1e-2 * 0.5 ** ((step - 1) / 2))
+        w, m, vv = C.adam_step(w, g, m, vv, step, learning_rate=lr, global_clipnorm=0.05)
+    got = gather_trainables(arch, flatten_variables(arch, t.get_weights()))
+    assert np.allclose(got, w, rtol=2e-5, atol=2e-7)
+    # the same handle now denoises with the updated variables (fold + pack again)
+    new_vars = t.get_weights()
+    x = np.random.default_rng(1).integers(0, 256, size=(1, 40, 40, 3), dtype=np.uint8)
+    yref, _ = O.denoise(new_vars, x, pad_pow2=True)
+    out = np.empty((1, 40, 40, 3), np.float32)
+    lib = t._lib
+    from blind_image_denoising_b200 import _native
+    _native.check(lib.bfcnn_denoise_f32(t.handle, x.ctypes.data, out.ctypes.data, 1, 40, 40, _native.PREC_FP32, 0, None))
+    assert np.abs(out - yref).max() <= 0.5 and np.abs(out - yref).mean() <= 0.05
+    t.close()
+
+
+def test_training_loop_reduces_loss(native_lib):
+    """corrupt -> train step -> Adam, 30 steps on one batch: the loss must go down (end-to-end sanity of signs)."""
+    import torch
+    from blind_image_denoising_b200 import _native
+    opt = {"schedule": {"type": "exponential_decay", "config": {"learning_rate": 2e-3, "decay_rate": 1.0, "decay_steps": 1}},
+           "gradient_clipping_by_norm": 1.0}
+    arch, v, t = _trainer(2, opt=opt)
+    yy, xx = np.mgrid[0:64, 0:64]
+    img = np.stack([(np.sin(xx / 7.0) * 60 + 128), (np.cos(yy / 5.0) * 60 + 128), ((xx + yy) * 2 % 256)], -1)
+    x = torch.from_numpy(np.repeat(img[None].astype(np.uint8), 8, 0)).cuda()
+    nc = _native.NoiseCfg(20.0, 20.0, 0.0, 0.0, 0, 0, 0, 1)
+    losses = []
+    for step in range(30):
+        clean, noisy = t.prepare_data(x, nc, 3, step * 8)
+        total, _, dl, g = t.train_step_single_gpu(clean, noisy)
+        t.apply_grads(g)
+        losses.append(dl["mae_loss"])
+    assert np.mean(losses[-5:]) < 0.8 * np.mean(losses[:5]), losses
+    t.close()
+
+
+def test_full_size_train_step_properties(native_lib):
+    """BASELINE configs[3]: batch 32 of 256x256x3, 1x6.  Size-independent properties: gradients finite,
+    deterministic run to run (fixed-order reductions), scale with 1/n when the batch is duplicated."""
+    import torch
+    from blind_image_denoising_b200 import _native
+    arch, v, t = _trainer(6)
+    x = torch.from_numpy(np.random.default_rng(0).integers(0, 256, size=(32, 256, 256, 3), dtype=np.uint8)).cuda()
+    nc = _native.NoiseCfg(5.0, 40.0, 0.05, 0.1, 1, 1, 0, 1)
+    clean, noisy = t.prepare_data(x, nc, 0, 0)
+    total1, _, _, g = t.train_step_single_gpu(clean, noisy, update_moving=False)
+    g1 = g.clone()
+    total2, _, _, g = t.train_step_single_gpu(clean, noisy, update_moving=False)
+    assert np.isfinite(total1) and torch.isfinite(g1).all()
+    assert total1 == total2
+    assert float((g - g1).abs().max()) <= 1e-6 * float(g1.abs().max())
+    t.close()
