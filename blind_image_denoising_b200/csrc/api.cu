@@ -50,7 +50,8 @@ int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int
                  int precision, uint32_t flags, void* stream) {
   BF_REQUIRE(h != nullptr, "handle is NULL");
   BF_CHECK(check_images(n, height, width));
-  BF_REQUIRE(precision == BFCNN_PREC_FP32 || precision == BFCNN_PREC_F16 || precision == BFCNN_PREC_F16X3,
+  BF_REQUIRE(precision == BFCNN_PREC_FP32 || precision == BFCNN_PREC_F16 || precision == BFCNN_PREC_F16X3 ||
+                 precision == BFCNN_PREC_F16_MMA_SYNC,
              "unknown precision");
   const size_t npx = (size_t)n * height * width;
   if (npx == 0) return BFCNN_OK;  // empty batch / empty image: nothing to do
@@ -94,8 +95,10 @@ int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int
       BF_CHECK(launch_conv3x3_f32(h, T, X, wb, bb, X, nullptr, CONV_RESIDUAL, e, st));
     }
     BF_CHECK(launch_head(h, X, d_out, out_u8, h->d_head_f32.as<float>(), e, st));
+  } else if (precision == BFCNN_PREC_F16) {
+    BF_CHECK(run_fused_stack_umma(h, d_in, d_out, out_u8, e, st));
   } else {
-    BF_CHECK(run_fused_stack(h, d_in, d_out, out_u8, e, precision, st));
+    BF_CHECK(run_fused_stack(h, d_in, d_out, out_u8, e, precision == BFCNN_PREC_F16_MMA_SYNC ? BFCNN_PREC_F16 : precision, st));
   }
   BF_CUDA(cudaEventRecord(h->ev1, st));
   h->ev_valid = true;
@@ -184,7 +187,7 @@ void bfcnn_destroy(bfcnn_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   h->d_vars.release(); h->d_base_f32.release(); h->d_conv_f32.release(); h->d_bias_f32.release();
-  h->d_head_f32.release(); h->d_conv_frag.release(); h->d_base_frag.release();
+  h->d_head_f32.release(); h->d_conv_frag.release(); h->d_base_frag.release(); h->d_conv_umma.release();
   h->ws_in.release(); h->ws_out.release();
   for (auto& b : h->ws_feat) b.release();
   h->ws_train.release(); h->ws_stats.release(); h->ws_grads.release();

@@ -116,6 +116,20 @@ int pack_weights(bfcnn_handle* h) {
           pack_frag(&conv[((size_t)l * 9 + tap) * C * C], nt,
                     &frag[((((size_t)l * 2 + pl) * 9 + tap) * 2 + nt) * 64], pl == 1);
 
+  // tcgen05 B operands (fused_umma.cu): per conv, per dx, N = 48 rows n = j*16 + cout with j <-> dy = 1 - j
+  // (input row q feeds output rows q-1, q, q+1), K = 16 cin, SWIZZLE_NONE K-major core matrices:
+  // byte offset(n, k) = (k/8)*768 + (n/8)*128 + (n%8)*16 + (k%8)*2
+  std::vector<__half> umma((size_t)2 * N * 3 * 48 * 16);
+  for (int l = 0; l < 2 * N; ++l)
+    for (int dxi = 0; dxi < 3; ++dxi)
+      for (int n = 0; n < 48; ++n)
+        for (int k = 0; k < 16; ++k) {
+          const int j = n / 16, co = n % 16, dy = 1 - j;
+          const int tap = (dy + 1) * 3 + dxi;
+          const size_t off = (size_t)(l * 3 + dxi) * 768 + (k / 8) * 384 + (n / 8) * 64 + (n % 8) * 8 + (k % 8);
+          umma[off] = __float2half_rn(conv[((size_t)l * 9 + tap) * C * C + k * C + co]);
+        }
+
   BF_CUDA(cudaSetDevice(h->device));
   const size_t nbase = (size_t)k0 * k0 * 3 * C;
   BF_CHECK(h->d_vars.reserve(L.total * sizeof(float)));
@@ -124,12 +138,14 @@ int pack_weights(bfcnn_handle* h) {
   BF_CHECK(h->d_bias_f32.reserve(std::max<size_t>(bias.size(), 1) * sizeof(float)));
   BF_CHECK(h->d_head_f32.reserve(head.size() * sizeof(float)));
   BF_CHECK(h->d_conv_frag.reserve(std::max<size_t>(frag.size(), 1) * sizeof(uint32_t)));
+  BF_CHECK(h->d_conv_umma.reserve(std::max<size_t>(umma.size(), 1) * sizeof(__half)));
   BF_CUDA(cudaMemcpy(h->d_vars.p, v, L.total * sizeof(float), cudaMemcpyHostToDevice));
   BF_CUDA(cudaMemcpy(h->d_base_f32.p, v + L.base, nbase * sizeof(float), cudaMemcpyHostToDevice));
   if (N > 0) {
     BF_CUDA(cudaMemcpy(h->d_conv_f32.p, conv.data(), conv.size() * sizeof(float), cudaMemcpyHostToDevice));
     BF_CUDA(cudaMemcpy(h->d_bias_f32.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
     BF_CUDA(cudaMemcpy(h->d_conv_frag.p, frag.data(), frag.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    BF_CUDA(cudaMemcpy(h->d_conv_umma.p, umma.data(), umma.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
   BF_CUDA(cudaMemcpy(h->d_head_f32.p, head.data(), head.size() * sizeof(float), cudaMemcpyHostToDevice));
   h->packed_valid = true;

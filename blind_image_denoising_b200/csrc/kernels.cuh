@@ -25,6 +25,10 @@ int launch_head(bfcnn_handle* h, const float* feat, void* out, bool out_u8, cons
 int run_fused_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                     int precision, cudaStream_t st);
 
+// ---- fused_umma.cu: the fused stack on tcgen05 (UMMA, accumulators in TMEM), F16
+int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
+                         cudaStream_t st);
+
 // ---- train.cu
 int run_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, float* noisy_f32, int n,
                 int height, int width, uint64_t seed, uint64_t sample_offset,
