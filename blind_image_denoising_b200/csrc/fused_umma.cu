@@ -17,9 +17,13 @@
 //   * Accumulators never leave TMEM between the MMA and the epilogue; the epilogue (bias, ReLU / residual add,
 //     border mask, fp16 pack) runs in 16 warps that each own one 32-lane TMEM quarter of a row, writes the next
 //     layer's A operand straight back into the shared-memory planes and re-zeroes the drained TMEM block.
-//   * One elected thread issues every MMA; per-row mbarriers couple it to the epilogue warps
-//     (mma_done[q] via tcgen05.commit, epi_done[r] via mbarrier.arrive), so layer l+1 chases layer l down the
+//   * One elected thread issues every MMA; mbarriers per group of 3 rows couple it to the epilogue warps
+//     (mma_done[g] via tcgen05.commit, epi_done[g] via mbarrier.arrive), so layer l+1 chases layer l down the
 //     region a few rows behind and the tensor pipe never drains at a layer boundary.
+//   * The kernel is persistent (one CTA per SM, regions round-robin).  In the last layer of a region every
+//     epilogue thread, once it has consumed its pixel of X, fetches the same pixel of the NEXT region into the
+//     freed slot with cp.async; to the MMA issuer the next region's first layer is just "one more layer", so
+//     the tensor pipe does not drain between regions either and HBM latency hides behind the last conv.
 //
 // Reference arithmetic: module_denoiser.py:53-73, utilities.py:449-461 (normalise), backbone_resnet.py:258-262
 // (base conv), backbone_blocks.py:167-246 (block), model.py:297-342 (head), utilities.py:435-443 (denormalise).
@@ -30,7 +34,7 @@ namespace umma {
 
 constexpr int RW = 128;                 // region width == UMMA M
 constexpr int SLACK_PX = 8;             // pixels of slack before/after every plane (tap shift -1/+1)
-constexpr int NSETS = 4;                // epilogue warp sets (4 warps each, one per TMEM lane quarter)
+constexpr int NSETS = 4;                // epilogue warp sets (4 warps each, one per TMEM lane quarter); 13 warps -> 128 registers
 constexpr int EPI_WARPS = 4 * NSETS;
 constexpr int NTHREADS = 32 * (EPI_WARPS + 1);   // + the MMA issuer warp
 constexpr int MAX_RH = 30;              // (RH + 2) accumulator blocks of 16 columns <= 512 TMEM columns
@@ -40,19 +44,23 @@ constexpr int MAX_LAYERS = 8;           // conv layers fused per pass
 
 enum Epi { EPI_RELU_TO_T = 0, EPI_RES_TO_X = 1, EPI_RES_TO_GLOBAL = 2, EPI_RES_HEAD = 3 };
 
+constexpr int GROUP = 6;                // region rows per barrier group: the MMA issuer pays ~300 cycles per mbarrier wait
+                                        // (the tensor pipe drains behind it, tools/umma_probe3.cu), so it waits per group, not per row
+constexpr int MAX_GROUPS = (MAX_RH + GROUP - 1) / GROUP;
+
 struct Params {
-  const uint8_t* img;      // [n][h][w][3]
-  const __half* fin;       // [n][he][we][16]
+  const __half* fin;       // [n][he][we][16]  input feature map of this pass (base conv output for pass 0)
   __half* fout;            // [n][he][we][16]
   void* out;               // [n][h][w][3] uint8 or float
-  const float* wbase;      // [k0*k0*3][16]
   const uint8_t* wumma;    // [2N][W_LAYER_BYTES]
   const float* bias;       // [2N][16]
   const float* whead;      // [16][4]
   int n, h, w, he, we;
-  int k0, blk0, nblk;
-  int first, last, out_u8;
-  int rh, tw, th, tiles_x, tiles_y;
+  int blk0, nblk;
+  int last, out_u8;
+  int rh, tw, th, tiles_x, tiles_y, regions;
+  long long* trace;        // debug timeline of CTA `trace_block` (BFCNN_UMMA_TRACE=1), else nullptr
+  int trace_block;
 };
 
 // ---------------------------------------------------------------------------- PTX helpers
@@ -81,6 +89,13 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// one lane of a converged warp; the compiler keeps the tcgen05 operands in uniform registers only on this path
+// (a plain `lane == 0` branch wraps every UTCHMMA in an ELECT/BRA.U.ANY loop: 392 instead of 143 cycles per row)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar) : "memory");
 }
@@ -89,6 +104,9 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t cnt) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t mbar, uint32_t n) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(mbar), "r"(n) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   uint32_t done;
@@ -110,10 +128,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+// issue only; the registers are valid after tmem_ld_wait(v) (which carries them as in/out operands so that no use of
+// v can be scheduled above the wait)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
   const uint32_t z = 0u;
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(taddr), "r"(z)
                : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+      "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
@@ -134,14 +174,17 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// max(x, 0) on a packed pair; rounding to fp16 commutes with ReLU (round-to-nearest keeps the sign)
+__device__ __forceinline__ uint32_t relu_h2(uint32_t v) {
+  const __half2 z = __float2half2_rn(0.f);
+  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&v), z);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 
 // ---------------------------------------------------------------------------- shared-memory map
 struct Smem {
-  uint32_t bars;       // mma_done[32], epi_done[32] (8 B each)
-  uint32_t tmem_slot;  // uint32 written by tcgen05.alloc
-  uint32_t head;       // float [16][4]
-  uint32_t bias;       // float [MAX_LAYERS][16]
+  uint32_t bars;       // mma_done[16], epi_done[16] (8 B each)
   uint32_t wts;        // [nlayers][W_LAYER_BYTES]
   uint32_t X[2], T[2]; // byte address of pixel 0 of each channel-half plane
   uint32_t plane_bytes;
@@ -150,90 +193,181 @@ __host__ __device__ inline uint32_t plane_bytes_of(int rh) { return (uint32_t)(r
 constexpr uint32_t SM_BARS = 0, SM_TMEM = 512, SM_HEAD = 528, SM_BIAS = 784, SM_WTS = 784 + MAX_LAYERS * 64;  // 1296
 __host__ __device__ inline uint32_t planes_offset(int nlayers) { return (SM_WTS + (uint32_t)nlayers * W_LAYER_BYTES + 127u) & ~127u; }
 
+struct Region { int b, oy, ox; };
+__device__ __forceinline__ Region region_of(const Params& p, int it, int halo) {
+  Region r;
+  const int tx = it % p.tiles_x;
+  it /= p.tiles_x;
+  const int ty = it % p.tiles_y;
+  r.b = it / p.tiles_y;
+  r.oy = ty * p.th - halo;
+  r.ox = tx * p.tw - halo;
+  return r;
+}
+
+// 16 consecutive pixels (both channel halves = 32 x 16 B = 512 contiguous bytes of the NHWC16 feature map) -> the X
+// planes, one 16-byte cp.async per lane: lane = 2*pixel + half, so the global side is one fully coalesced 512-byte
+// read and the shared side two contiguous 256-byte runs (a per-pixel mapping with its 32-byte global stride costs
+// 40 shared-memory wavefronts per instruction instead of 8: profiles/r01_umma_ncu.md).  Zero outside the extent
+// ("same" padding).
+__device__ __forceinline__ void fetch_16px(const Params& p, const Smem& S, const Region& g, int r, int c0, int lane) {
+  const int c = c0 + (lane >> 1), hf = lane & 1;
+  const int gy = g.oy + r, gx = g.ox + c;
+  const bool valid = (gy >= 0) && (gy < p.he) && (gx >= 0) && (gx < p.we);
+  const __half* src = p.fin + (valid ? (((((long long)g.b * p.he + gy) * p.we + gx) << 4) + 8 * hf) : 0);
+  cp_async16_zfill(S.X[hf] + (uint32_t)(r * RW + c) * 16u, src, valid);
+}
+
 // ---------------------------------------------------------------------------- epilogue of one row quarter
-template <int EPI>
-__device__ __forceinline__ void epilogue_row(const Params& p, const Smem& S, const float* s_bias_l, const float* s_head,
-                                             uint32_t taddr, int r, int c, int oy, int ox, int b, int halo, bool rezero) {
-  uint32_t v[16];
-  tmem_ld16(taddr, v);
-  if (rezero) tmem_zero16(taddr);
-  const int gy = oy + r, gx = ox + c;
-  const bool inside = (gy >= 0) && (gy < p.he) && (gx >= 0) && (gx < p.we);
-  const uint32_t pix_off = (uint32_t)(r * RW + c) * 16u;
+// conv_a rows: T = ReLU(D); then the accumulator block is PRE-LOADED with the residual X + b' (fp32), so that conv_b
+// accumulates Add([x, previous]) (backbone_blocks.py:240-242; BN folded) inside the tensor core and the
+// X plane is dead one layer earlier (the next region's prefetch starts there).
+// conv_b rows: D already is X + conv_b'(T) + b'; mask, pack, write X / the feature map / the head; re-zero D.
+// Per-thread constants of one region: everything that does not depend on the row is computed once, so that the row
+// loop below is ~60 instructions per conv_a row and ~25 per conv_b row (it was 170: the epilogue warps, not the tensor
+// pipe, set the pace -- profiles/r01_umma_ncu.md).
+struct EpiCtx {
+  uint32_t tq;            // TMEM address of this warp's lane quarter, column 0
+  uint32_t x0, x1, t0, t1;  // shared byte addresses of this thread's pixel column in region row 0
+  int oy, he;             // row r is inside the extent iff (unsigned)(oy + r) < he
+  bool col_ok;            // this thread's column is inside the extent
+  bool col_out;           // ... and inside the tile (output) columns [halo, RW - halo) (and inside the image for the head)
+  __half* fout_col;       // feature-map address of (b, oy, gx); row r adds r * row_halves
+  uint8_t* out_col;       // output address of (b, oy, gx) (uint8 or float)
+  long long row_halves;   // we * 16
+  long long row_out;      // w * 3 elements
+  int h_img;              // rows of the image (head: gy < h)
+  // next region (prefetch): two 16-pixel chunks of this warp's quarter
+  const __half* nsrc[2];
+  bool ncol_ok[2];
+  int noy;
+  uint32_t nx[2];         // shared destination (row 0) of this lane's 16 bytes per chunk
+};
+
+template <int EPI, bool PREFETCH>
+__device__ __forceinline__ void epilogue_layer(const Params& p, const Smem& S, const EpiCtx& E, const float* s_bias_next,
+                                               const float* s_head, int set, int l, uint32_t parity) {
+  const int r_lo = l + 1, r_hi = p.rh - l - 1;
+  float bias[16];
   if (EPI == EPI_RELU_TO_T) {
-    uint4 lo, hi;
-    lo.x = pack_h2(fmaxf(__uint_as_float(v[0]), 0.f), fmaxf(__uint_as_float(v[1]), 0.f));
-    lo.y = pack_h2(fmaxf(__uint_as_float(v[2]), 0.f), fmaxf(__uint_as_float(v[3]), 0.f));
-    lo.z = pack_h2(fmaxf(__uint_as_float(v[4]), 0.f), fmaxf(__uint_as_float(v[5]), 0.f));
-    lo.w = pack_h2(fmaxf(__uint_as_float(v[6]), 0.f), fmaxf(__uint_as_float(v[7]), 0.f));
-    hi.x = pack_h2(fmaxf(__uint_as_float(v[8]), 0.f), fmaxf(__uint_as_float(v[9]), 0.f));
-    hi.y = pack_h2(fmaxf(__uint_as_float(v[10]), 0.f), fmaxf(__uint_as_float(v[11]), 0.f));
-    hi.z = pack_h2(fmaxf(__uint_as_float(v[12]), 0.f), fmaxf(__uint_as_float(v[13]), 0.f));
-    hi.w = pack_h2(fmaxf(__uint_as_float(v[14]), 0.f), fmaxf(__uint_as_float(v[15]), 0.f));
-    if (!inside) { lo = make_uint4(0u, 0u, 0u, 0u); hi = lo; }
-    sts128(S.T[0] + pix_off, lo);
-    sts128(S.T[1] + pix_off, hi);
-    return;
-  }
-  // X + conv_b'(T) + b'   (Add([x, previous]), backbone_blocks.py:240-242; BN folded)
-  float f[16];
-  {
-    const uint4 x0 = lds128(S.X[0] + pix_off), x1 = lds128(S.X[1] + pix_off);
-    const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 xv = unpack_h2(xs[i]);
-      f[2 * i] = (__uint_as_float(v[2 * i]) + s_bias_l[2 * i]) + xv.x;
-      f[2 * i + 1] = (__uint_as_float(v[2 * i + 1]) + s_bias_l[2 * i + 1]) + xv.y;
+    for (int q = 0; q < 4; ++q) {
+      const float4 bq = *reinterpret_cast<const float4*>(s_bias_next + 4 * q);
+      bias[4 * q] = bq.x; bias[4 * q + 1] = bq.y; bias[4 * q + 2] = bq.z; bias[4 * q + 3] = bq.w;
     }
   }
-  if (EPI == EPI_RES_TO_X || EPI == EPI_RES_TO_GLOBAL) {
-    uint4 lo, hi;
-    lo.x = pack_h2(f[0], f[1]); lo.y = pack_h2(f[2], f[3]); lo.z = pack_h2(f[4], f[5]); lo.w = pack_h2(f[6], f[7]);
-    hi.x = pack_h2(f[8], f[9]); hi.y = pack_h2(f[10], f[11]); hi.z = pack_h2(f[12], f[13]); hi.w = pack_h2(f[14], f[15]);
-    if (EPI == EPI_RES_TO_X) {
-      if (!inside) { lo = make_uint4(0u, 0u, 0u, 0u); hi = lo; }
-      sts128(S.X[0] + pix_off, lo);
-      sts128(S.X[1] + pix_off, hi);
-    } else {
-      const bool in_tile = inside && (c >= halo) && (c < RW - halo);
-      if (in_tile) {
-        uint4* o = reinterpret_cast<uint4*>(p.fout + ((((long long)b * p.he + gy) * p.we + gx) << 4));
-        o[0] = lo;
-        o[1] = hi;
-      }
+  int waited = -1;   // highest mma_done index already observed in this layer
+  for (int r = set; r < p.rh; r += NSETS) {
+    const int grp = r / GROUP;
+    const int need = min(r + 1, p.rh - 1) / GROUP;   // row r is complete once input row r+1 has been multiplied
+    if (need > waited) {
+      mbar_wait(S.bars + (uint32_t)need * 8, parity);
+      tc_fence_after();
+      waited = need;
     }
-  } else {  // EPI_RES_HEAD: collapsed 1x1 head + tanh(2y)*0.51 + denormalise (+ round + uint8)
-    const bool in_img = inside && (gy < p.h) && (gx < p.w) && (c >= halo) && (c < RW - halo);
-    if (in_img) {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    const uint32_t taddr = E.tq + (uint32_t)(r + 1) * 16;
+    const uint32_t po = (uint32_t)r * (RW * 16);
+    if (r >= r_lo && r < r_hi) {
+      const bool inside = E.col_ok && ((unsigned)(E.oy + r) < (unsigned)E.he);
+      uint32_t v[16];
+      tmem_ld16_issue(taddr, v);
+      if (EPI == EPI_RELU_TO_T) {
+        // T = ReLU(D); D <- X + b' (the residual the following conv_b accumulates onto)
+        const uint4 xa = lds128(E.x0 + po), xb = lds128(E.x1 + po);
+        tmem_ld_wait(v);
+        {
+          float f[16];
+          const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {
-        const float4 wv = *reinterpret_cast<const float4*>(s_head + ch * 4);
-        s0 = fmaf(f[ch], wv.x, s0); s1 = fmaf(f[ch], wv.y, s1); s2 = fmaf(f[ch], wv.z, s2);
-      }
-      const float r0 = head_activation(s0), r1 = head_activation(s1), r2 = head_activation(s2);
-      const long long o = (((long long)b * p.h + gy) * p.w + gx) * 3;
-      if (p.out_u8) {
-        uint8_t* d = reinterpret_cast<uint8_t*>(p.out) + o;
-        d[0] = (uint8_t)__float2int_rn(r0); d[1] = (uint8_t)__float2int_rn(r1); d[2] = (uint8_t)__float2int_rn(r2);
+          for (int i = 0; i < 8; ++i) {
+            const float2 xv = unpack_h2(xs[i]);
+            f[2 * i] = xv.x + bias[2 * i];
+            f[2 * i + 1] = xv.y + bias[2 * i + 1];
+          }
+          tmem_st16(taddr, f);
+        }
+        const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
+        uint4 lo, hi;
+        lo.x = relu_h2(pack_h2(__uint_as_float(v[0]), __uint_as_float(v[1]))) & m; lo.y = relu_h2(pack_h2(__uint_as_float(v[2]), __uint_as_float(v[3]))) & m;
+        lo.z = relu_h2(pack_h2(__uint_as_float(v[4]), __uint_as_float(v[5]))) & m; lo.w = relu_h2(pack_h2(__uint_as_float(v[6]), __uint_as_float(v[7]))) & m;
+        hi.x = relu_h2(pack_h2(__uint_as_float(v[8]), __uint_as_float(v[9]))) & m; hi.y = relu_h2(pack_h2(__uint_as_float(v[10]), __uint_as_float(v[11]))) & m;
+        hi.z = relu_h2(pack_h2(__uint_as_float(v[12]), __uint_as_float(v[13]))) & m; hi.w = relu_h2(pack_h2(__uint_as_float(v[14]), __uint_as_float(v[15]))) & m;
+        sts128(E.t0 + po, lo);
+        sts128(E.t1 + po, hi);
       } else {
-        float* d = reinterpret_cast<float*>(p.out) + o;
-        d[0] = r0; d[1] = r1; d[2] = r2;
+        tmem_ld_wait(v);
+        tmem_zero16(taddr);
+        if (EPI == EPI_RES_HEAD) {   // collapsed 1x1 head + tanh(2y)*0.51 + denormalise (+ round + uint8)
+          if (E.col_out && inside && (E.oy + r) < E.h_img) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 16; ++ch) {
+              const float4 wv = *reinterpret_cast<const float4*>(s_head + ch * 4);
+              const float fv = __uint_as_float(v[ch]);
+              s0 = fmaf(fv, wv.x, s0); s1 = fmaf(fv, wv.y, s1); s2 = fmaf(fv, wv.z, s2);
+            }
+            const float r0o = head_activation(s0), r1o = head_activation(s1), r2o = head_activation(s2);
+            if (p.out_u8) {
+              uint8_t* d = E.out_col + (long long)r * E.row_out;
+              d[0] = (uint8_t)__float2int_rn(r0o); d[1] = (uint8_t)__float2int_rn(r1o); d[2] = (uint8_t)__float2int_rn(r2o);
+            } else {
+              float* d = reinterpret_cast<float*>(E.out_col) + (long long)r * E.row_out;
+              d[0] = r0o; d[1] = r1o; d[2] = r2o;
+            }
+          }
+        } else {
+          uint4 lo, hi;
+          lo.x = pack_h2(__uint_as_float(v[0]), __uint_as_float(v[1])); lo.y = pack_h2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+          lo.z = pack_h2(__uint_as_float(v[4]), __uint_as_float(v[5])); lo.w = pack_h2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+          hi.x = pack_h2(__uint_as_float(v[8]), __uint_as_float(v[9])); hi.y = pack_h2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+          hi.z = pack_h2(__uint_as_float(v[12]), __uint_as_float(v[13])); hi.w = pack_h2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+          if (EPI == EPI_RES_TO_X) {
+            const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
+            lo.x &= m; lo.y &= m; lo.z &= m; lo.w &= m; hi.x &= m; hi.y &= m; hi.z &= m; hi.w &= m;
+            sts128(E.x0 + po, lo);
+            sts128(E.x1 + po, hi);
+          } else if (E.col_out && inside) {
+            uint4* o = reinterpret_cast<uint4*>(E.fout_col + (long long)r * E.row_halves);
+            o[0] = lo;
+            o[1] = hi;
+          }
+        }
       }
+    } else if (EPI == EPI_RES_HEAD || EPI == EPI_RES_TO_GLOBAL) {
+      tmem_zero16(taddr);   // rows that fell out of the valid range hold stale partial sums: clean for the next region
     }
+    if (PREFETCH) {
+      // X row r is dead for this region: fetch the next region's (this warp's quarter = 2 x 16 pixels); the mbarrier
+      // arrive fires when the copies have landed
+      const bool row_ok = (unsigned)(E.noy + r) < (unsigned)E.he;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const bool ok = row_ok && E.ncol_ok[k];
+        cp_async16_zfill(E.nx[k] + po, ok ? (E.nsrc[k] + (long long)r * E.row_halves) : p.fin, ok);
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(S.bars + (uint32_t)(32 + grp) * 8) : "memory");
+    }
+    tmem_wait_st();
+    fence_async_smem();
+    tc_fence_before();
+    mbar_arrive(S.bars + (uint32_t)(16 + grp) * 8);
   }
 }
 
-// ---------------------------------------------------------------------------- the pass kernel
+// ---------------------------------------------------------------------------- the pass kernel (persistent)
+template <bool LAST_PASS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 umma_pass_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nl = 2 * p.nblk;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: no BSSY/BSYNC around role branches
+  const int nl = 2 * p.nblk, halo = 2 * p.nblk;
+  const int ng = (p.rh + GROUP - 1) / GROUP;
+  const bool tr = (p.trace != nullptr) && ((int)blockIdx.x == p.trace_block);
+  if (tr && tid == 0) p.trace[0] = clock64();
   const uint32_t s0 = smem_u32(smem);
   Smem S;
-  S.bars = s0 + SM_BARS; S.tmem_slot = s0 + SM_TMEM; S.head = s0 + SM_HEAD; S.bias = s0 + SM_BIAS; S.wts = s0 + SM_WTS;
+  S.bars = s0 + SM_BARS; S.wts = s0 + SM_WTS;
   S.plane_bytes = plane_bytes_of(p.rh);
   {
     const uint32_t pl = s0 + planes_offset(nl);
@@ -244,165 +378,192 @@ umma_pass_kernel(const Params p) {
   float* s_head = reinterpret_cast<float*>(smem + SM_HEAD);
   float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
 
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x; t /= p.tiles_x;
-  const int ty = t % p.tiles_y;
-  const int b = t / p.tiles_y;
-  const int halo = 2 * p.nblk;
-  const int oy = ty * p.th - halo, ox = tx * p.tw - halo;
-
-  // ---------------- one-time setup: barriers, TMEM, weights
-  if (tid < 64) mbar_init(S.bars + tid * 8, tid < 32 ? 1u : 128u);   // [0,32) mma_done (commit), [32,64) epi_done (128 threads)
+  // ---------------- one-time setup: barriers, TMEM, weights, the first region
+  // [0,16) mma_done[g] (tcgen05.commit), [16,32) epi_done[g], [32,48) x_ready[g] (next region's X rows): every thread
+  // of the 128-pixel row arrives once per row of the group
+  if (tid < 48) {
+    const int gi = tid & 15;
+    const int rows = max(0, min(GROUP, p.rh - gi * GROUP));
+    mbar_init(S.bars + tid * 8, tid < 16 ? 1u : (uint32_t)max(1, 128 * rows));
+  }
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(S.tmem_slot) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(s0 + SM_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  {
+    const Region g0 = region_of(p, (int)blockIdx.x, halo);
+    for (int i = warp; i < p.rh * (RW / 16); i += NTHREADS / 32) fetch_16px(p, S, g0, i / (RW / 16), (i % (RW / 16)) * 16, lane);
   }
   for (int i = tid; i < nl * (W_LAYER_BYTES / 16); i += NTHREADS)
     reinterpret_cast<uint4*>(smem + SM_WTS)[i] =
         reinterpret_cast<const uint4*>(p.wumma + (size_t)(2 * p.blk0) * W_LAYER_BYTES)[i];
   for (int i = tid; i < nl * C; i += NTHREADS) s_bias[i] = p.bias[(size_t)(2 * p.blk0) * C + i];
   if (tid < C * 4) s_head[tid] = p.whead[tid];
-
-  // ---------------- stage the input region into X
-  if (p.first) {
-    const int k0 = p.k0, r0 = (k0 - 1) >> 1;
-    const int sw = RW + 2 * r0, sh = p.rh + 2 * r0;
-    // the uint8 tile and the base weights alias the T planes (not written before the first epilogue)
-    float* s_wb = reinterpret_cast<float*>(g_planes + 2 * S.plane_bytes);
-    uint8_t* s_img = reinterpret_cast<uint8_t*>(s_wb) + ((k0 * k0 * 3 * C * 4 + 15) & ~15);
-    for (int i = tid; i < k0 * k0 * 3 * C; i += NTHREADS) s_wb[i] = p.wbase[i];
-    const uint8_t* img_b = p.img + (long long)b * p.h * p.w * 3;
-    for (int i = tid; i < sh * sw; i += NTHREADS) {
-      const int ly = i / sw, lx = i - ly * sw;
-      const int gy = oy - r0 + ly, gx = ox - r0 + lx;
-      uint8_t v0 = 0, v1 = 0, v2 = 0;  // raw zeros outside the image (pow2 canvas, utilities.py:749)
-      if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
-        const uint8_t* s = img_b + ((long long)gy * p.w + gx) * 3;
-        v0 = s[0]; v1 = s[1]; v2 = s[2];
-      }
-      s_img[i * 3 + 0] = v0; s_img[i * 3 + 1] = v1; s_img[i * 3 + 2] = v2;
-    }
-    __syncthreads();
-    // base conv (FP32 FFMA), one pixel x 16 cout per thread
-    for (int pix = tid; pix < p.rh * RW; pix += NTHREADS) {
-      const int r = pix / RW, c = pix % RW;
-      const int gy = oy + r, gx = ox + c;
-      float acc[C];
-#pragma unroll
-      for (int k = 0; k < C; ++k) acc[k] = 0.f;
-      if (gy >= 0 && gy < p.he && gx >= 0 && gx < p.we) {
-        for (int dy = 0; dy < k0; ++dy) {
-          const int yy = gy + dy - r0;
-          if (yy < 0 || yy >= p.he) continue;  // zero padding of the NORMALISED tensor
-          for (int dx = 0; dx < k0; ++dx) {
-            const int xx = gx + dx - r0;
-            if (xx < 0 || xx >= p.we) continue;
-            const uint8_t* s = s_img + ((r + dy) * sw + (c + dx)) * 3;
-            const float* wt = s_wb + (dy * k0 + dx) * 3 * C;
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-              const float xn = __fsub_rn(__fdiv_rn((float)s[ci], 255.f), 0.5f);
-#pragma unroll
-              for (int k = 0; k < C; ++k) acc[k] = fmaf(xn, wt[ci * C + k], acc[k]);
-            }
-          }
-        }
-      }
-      uint4 lo, hi;
-      lo.x = pack_h2(acc[0], acc[1]); lo.y = pack_h2(acc[2], acc[3]); lo.z = pack_h2(acc[4], acc[5]); lo.w = pack_h2(acc[6], acc[7]);
-      hi.x = pack_h2(acc[8], acc[9]); hi.y = pack_h2(acc[10], acc[11]); hi.z = pack_h2(acc[12], acc[13]); hi.w = pack_h2(acc[14], acc[15]);
-      sts128(S.X[0] + (uint32_t)pix * 16u, lo);
-      sts128(S.X[1] + (uint32_t)pix * 16u, hi);
-    }
-  } else {
-    for (int i = tid; i < p.rh * RW * 2; i += NTHREADS) {
-      const int hf = i & 1, pix = i >> 1;
-      const int r = pix / RW, c = pix % RW;
-      const int gy = oy + r, gx = ox + c;
-      const bool valid = (gy >= 0) && (gy < p.he) && (gx >= 0) && (gx < p.we);
-      const long long o = valid ? (((((long long)b * p.he + gy) * p.we + gx) << 4) + 8 * hf) : 0;
-      cp_async16_zfill(S.X[hf] + (uint32_t)pix * 16u, p.fin + o, valid);
-    }
-    cp_async_wait_all();
-  }
-  // zero the plane slack (read by the -1/+1 tap shifts of the first / last row); in the first pass the T planes
-  // were scratch for the uint8 tile, so this happens only after every thread finished the base conv
-  if (p.first) __syncthreads();
+  // zero the plane slack (read by the -1/+1 tap shifts of the first / last row)
   if (tid < 4 * 2 * SLACK_PX) {
     const int pl = tid / (2 * SLACK_PX), k = tid % (2 * SLACK_PX);
     const uint32_t off = (uint32_t)pl * S.plane_bytes + (k < SLACK_PX ? (uint32_t)k * 16u : S.plane_bytes - (uint32_t)(2 * SLACK_PX - k) * 16u);
     *reinterpret_cast<uint4*>(g_planes + off) = make_uint4(0u, 0u, 0u, 0u);
   }
+  cp_async_wait_all();
   fence_async_smem();   // generic-proxy writes of X -> visible to the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+  if (tr && tid == 0) p.trace[1] = clock64();
 
   if (warp < EPI_WARPS) {
     // ================= epilogue warps =================
     const int quarter = warp & 3, set = warp >> 2;
-    const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16);
     const int c = quarter * 32 + lane;
+    EpiCtx E;
+    E.tq = tmem + ((uint32_t)(quarter * 32) << 16);
+    E.x0 = S.X[0] + (uint32_t)c * 16u; E.x1 = S.X[1] + (uint32_t)c * 16u;
+    E.t0 = S.T[0] + (uint32_t)c * 16u; E.t1 = S.T[1] + (uint32_t)c * 16u;
+    E.he = p.he; E.h_img = p.h;
+    E.row_halves = (long long)p.we * 16; E.row_out = (long long)p.w * 3;
     // zero this warp's share of the accumulator blocks, then release the MMA issuer
-    for (int blk = set; blk < p.rh + 2; blk += NSETS) tmem_zero16(tq + blk * 16);
+    for (int blk = set; blk < p.rh + 2; blk += NSETS) tmem_zero16(E.tq + blk * 16);
     tmem_wait_st();
     tc_fence_before();
     asm volatile("bar.sync 1, %0;\n" ::"r"(NTHREADS) : "memory");
-    for (int l = 0; l < nl; ++l) {
-      const int r_lo = l + 1, r_hi = p.rh - l - 1;
-      const bool is_b = (l & 1) != 0, last_layer = (l + 1 == nl);
-      const float* s_bias_l = s_bias + l * C;
-      int r = r_lo + ((set - (r_lo % NSETS)) + NSETS) % NSETS;
-      for (; r < r_hi; r += NSETS) {
-        mbar_wait(S.bars + (uint32_t)(r + 1) * 8, (uint32_t)(l & 1));
-        tc_fence_after();
-        const uint32_t taddr = tq + (uint32_t)(r + 1) * 16;
-        if (!is_b) epilogue_row<EPI_RELU_TO_T>(p, S, s_bias_l, s_head, taddr, r, c, oy, ox, b, halo, true);
-        else if (!last_layer) epilogue_row<EPI_RES_TO_X>(p, S, s_bias_l, s_head, taddr, r, c, oy, ox, b, halo, true);
-        else if (p.last) epilogue_row<EPI_RES_HEAD>(p, S, s_bias_l, s_head, taddr, r, c, oy, ox, b, halo, false);
-        else epilogue_row<EPI_RES_TO_GLOBAL>(p, S, s_bias_l, s_head, taddr, r, c, oy, ox, b, halo, false);
-        if (!last_layer) {
-          tmem_wait_st();
-          fence_async_smem();
-          tc_fence_before();
-          mbar_arrive(S.bars + (uint32_t)(32 + r) * 8);
+    uint32_t L = 0;   // global layer counter == mbarrier phase index
+    for (int it = (int)blockIdx.x; it < p.regions; it += (int)gridDim.x) {
+      const Region g = region_of(p, it, halo);
+      const bool has_next = (it + (int)gridDim.x) < p.regions;
+      {
+        const int gx = g.ox + c;
+        E.oy = g.oy;
+        E.col_ok = (gx >= 0) && (gx < p.we);
+        E.col_out = E.col_ok && (c >= halo) && (c < RW - halo) && (!LAST_PASS || gx < p.w);
+        E.fout_col = p.fout + ((((long long)g.b * p.he + g.oy) * p.we + gx) << 4);
+        E.out_col = reinterpret_cast<uint8_t*>(p.out) + ((((long long)g.b * p.h + g.oy) * p.w + gx) * 3) * (p.out_u8 ? 1 : 4);
+        if (has_next) {
+          const Region gn = region_of(p, it + (int)gridDim.x, halo);
+          E.noy = gn.oy;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int cn = quarter * 32 + 16 * k + (lane >> 1), hf = lane & 1;
+            const int gxn = gn.ox + cn;
+            E.ncol_ok[k] = (gxn >= 0) && (gxn < p.we);
+            E.nsrc[k] = p.fin + ((((long long)gn.b * p.he + gn.oy) * p.we + gxn) << 4) + 8 * hf;
+            E.nx[k] = S.X[hf] + (uint32_t)cn * 16u;
+          }
         }
+      }
+      for (int l = 0; l < nl; ++l, ++L) {
+        const float* s_bias_next = s_bias + (l + 1) * C;   // conv_a pre-loads the bias of the conv_b that follows
+        if ((l & 1) == 0) {
+          if (has_next && l == nl - 2) epilogue_layer<EPI_RELU_TO_T, true>(p, S, E, s_bias_next, s_head, set, l, L & 1u);
+          else epilogue_layer<EPI_RELU_TO_T, false>(p, S, E, s_bias_next, s_head, set, l, L & 1u);
+        } else if (l + 1 < nl) {
+          epilogue_layer<EPI_RES_TO_X, false>(p, S, E, s_bias_next, s_head, set, l, L & 1u);
+        } else {
+          epilogue_layer<LAST_PASS ? EPI_RES_HEAD : EPI_RES_TO_GLOBAL, false>(p, S, E, s_bias_next, s_head, set, l, L & 1u);
+        }
+        if (tr && lane == 0 && quarter == 0 && L < 8) p.trace[40 + set * 16 + L] = clock64();
       }
     }
   } else {
     // ================= MMA issuer warp =================
     asm volatile("bar.sync 1, %0;\n" ::"r"(NTHREADS) : "memory");   // accumulators are zero
     tc_fence_after();
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = make_idesc_f16(128, 48);
-      for (int l = 0; l < nl; ++l) {
-        const uint32_t src = (l & 1) ? S.T[0] : S.X[0];
-        const uint32_t wl = S.wts + (uint32_t)l * W_LAYER_BYTES;
-        const int q_lo = l, q_hi = p.rh - l;
-        for (int q = q_lo; q < q_hi; ++q) {
-          if (l > 0) {
-            const uint32_t par = (uint32_t)((l - 1) & 1);
-            if (q == q_lo) mbar_wait(S.bars + (uint32_t)(32 + q) * 8, par);
-            if (q + 1 < q_hi) mbar_wait(S.bars + (uint32_t)(32 + q + 1) * 8, par);
-            tc_fence_after();
+      // descriptors with the start-address field at pixel 0 / layer 0; the per-MMA part is an add of 16-byte units
+      const uint64_t adesc_x = make_desc(S.X[0], S.plane_bytes, 128), adesc_t = make_desc(S.T[0], S.plane_bytes, 128);
+      const uint64_t bdesc0 = make_desc(S.wts, 48 * 16, 128);
+      uint32_t L = 0;
+      int nreg = 0;   // regions finished by this CTA
+      for (int it = (int)blockIdx.x; it < p.regions; it += (int)gridDim.x, ++nreg) {
+        for (int l = 0; l < nl; ++l, ++L) {
+          const uint64_t ad0 = (l & 1) ? adesc_t : adesc_x;
+          const uint64_t bd0 = bdesc0 + (uint64_t)(l * (W_LAYER_BYTES / 16));
+          const int q_lo = l, q_hi = p.rh - l;
+          if (tr && L < 8) p.trace[8 + 2 * L] = clock64();
+          for (int grp = 0; grp < ng; ++grp) {
+            if (L > 0) {
+              const uint32_t par = (L - 1) & 1u;
+              if (grp == 0) mbar_wait(S.bars + (uint32_t)(16 + 0) * 8, par);
+              if (grp + 1 < ng) mbar_wait(S.bars + (uint32_t)(16 + grp + 1) * 8, par);
+              if (l == 0) {   // first layer of a later region: its X rows were fetched (cp.async) during the previous region
+                const uint32_t xpar = (uint32_t)(nreg - 1) & 1u;
+                if (grp == 0) mbar_wait(S.bars + (uint32_t)(32 + 0) * 8, xpar);
+                if (grp + 1 < ng) mbar_wait(S.bars + (uint32_t)(32 + grp + 1) * 8, xpar);
+                fence_async_smem();   // generic-proxy writes observed through the mbarrier -> async-proxy reads of the MMA
+              }
+              tc_fence_after();
+            }
+            const int row_end = min(grp * GROUP + GROUP, q_hi);
+            for (int q = max(grp * GROUP, q_lo); q < row_end; ++q) {
+              const uint64_t ad = ad0 + (uint64_t)(q * RW - 1);
+              const uint32_t d = tmem + (uint32_t)q * 16;
+              mma_f16_ss(d, ad, bd0, idesc, 1u);
+              mma_f16_ss(d, ad + 1, bd0 + (48 * 16 * 2 / 16), idesc, 1u);
+              mma_f16_ss(d, ad + 2, bd0 + 2 * (48 * 16 * 2 / 16), idesc, 1u);
+            }
+            umma_commit(S.bars + (uint32_t)grp * 8);
           }
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const uint64_t ad = make_desc(src + (uint32_t)(q * RW + dx - 1) * 16u, S.plane_bytes, 128);
-            const uint64_t bd = make_desc(wl + (uint32_t)dx * (48 * 16 * 2), 48 * 16, 128);
-            mma_f16_ss(tmem + (uint32_t)q * 16, ad, bd, idesc, 1u);
-          }
-          umma_commit(S.bars + (uint32_t)q * 8);
+          if (tr && L < 8) p.trace[9 + 2 * L] = clock64();
         }
       }
     }
     __syncwarp();
   }
+  if (tr && tid == 0) p.trace[2] = clock64();
   tc_fence_before();
   __syncthreads();
+  if (tr && tid == 0) p.trace[3] = clock64();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+// ---------------------------------------------------------------------------- base conv -> fp16 NHWC16
+// normalise (utilities.py:449-461) + base conv k0 x k0, 3 -> 16 (backbone_resnet.py:258-262) over the work extent;
+// the raw-zero pow2 canvas (utilities.py:749) and the zero padding of the NORMALISED tensor as in conv_f32.cu.
+__global__ void __launch_bounds__(256, 3)
+base_conv_f16_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, const float* __restrict__ w,
+                     int n, int h, int wd, int he, int we, int k0) {
+  extern __shared__ float sw[];  // [k0*k0*3][16]
+  for (int i = threadIdx.x; i < k0 * k0 * 3 * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int r = (k0 - 1) >> 1;
+  const long long total = (long long)n * he * we;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % we);
+    const int y = (int)((idx / we) % he);
+    const int b = (int)(idx / ((long long)we * he));
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int dy = 0; dy < k0; ++dy) {
+      const int yy = y + dy - r;
+      if (yy < 0 || yy >= he) continue;
+      for (int dx = 0; dx < k0; ++dx) {
+        const int xx = x + dx - r;
+        if (xx < 0 || xx >= we) continue;
+        float v[3] = {0.f, 0.f, 0.f};
+        if (yy < h && xx < wd) {
+          const uint8_t* s = img + (((long long)b * h + yy) * wd + xx) * 3;
+          v[0] = (float)s[0]; v[1] = (float)s[1]; v[2] = (float)s[2];
+        }
+        const float* wt = sw + (dy * k0 + dx) * 3 * C;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float xn = __fsub_rn(__fdiv_rn(v[ci], 255.f), 0.5f);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(xn, wt[ci * C + c], acc[c]);
+        }
+      }
+    }
+    uint4 lo, hi;
+    lo.x = pack_h2(acc[0], acc[1]); lo.y = pack_h2(acc[2], acc[3]); lo.z = pack_h2(acc[4], acc[5]); lo.w = pack_h2(acc[6], acc[7]);
+    hi.x = pack_h2(acc[8], acc[9]); hi.y = pack_h2(acc[10], acc[11]); hi.z = pack_h2(acc[12], acc[13]); hi.w = pack_h2(acc[14], acc[15]);
+    uint4* o = reinterpret_cast<uint4*>(out + (idx << 4));
+    o[0] = lo;
+    o[1] = hi;
+  }
 }
 
 }  // namespace umma
@@ -417,60 +578,59 @@ static int env_int_u(const char* name, int dflt) {
 
 int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e, cudaStream_t st) {
   using namespace umma;
-  const int N = h->arch.no_layers, k0 = h->arch.base_kernel, r0 = (k0 - 1) / 2;
+  const int N = h->arch.no_layers, k0 = h->arch.base_kernel;
   if (N < 1) {
     set_error("the fused tensor-core stack needs no_layers >= 1 (use BFCNN_PREC_FP32)");
     return BFCNN_ERR_UNSUPPORTED;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    BF_CUDA(cudaFuncSetAttribute((const void*)umma_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    BF_CUDA(cudaFuncSetAttribute((const void*)umma_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    BF_CUDA(cudaFuncSetAttribute((const void*)umma_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     attr_set = true;
   }
   int kb = env_int_u("BFCNN_KB_UMMA", 2);
   kb = std::max(1, std::min(std::min(kb, N), MAX_LAYERS / 2));
   const int passes = (N + kb - 1) / kb;
   const size_t feat_halves = (size_t)e.n * e.he * e.we * C;
-  if (passes > 1) {
-    BF_CHECK(h->ws_feat[0].reserve(feat_halves * sizeof(__half)));
-    if (passes > 2) BF_CHECK(h->ws_feat[1].reserve(feat_halves * sizeof(__half)));
+  BF_CHECK(h->ws_feat[1].reserve(feat_halves * sizeof(__half)));
+  if (passes > 1) BF_CHECK(h->ws_feat[0].reserve(feat_halves * sizeof(__half)));
+
+  // pass "-1": base conv into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
+  {
+    const long long total = (long long)e.n * e.he * e.we;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+    base_conv_f16_kernel<<<blocks, 256, (size_t)k0 * k0 * 3 * C * sizeof(float), st>>>(
+        d_in, h->ws_feat[1].as<__half>(), h->d_base_f32.as<float>(), e.n, e.h, e.w, e.he, e.we, k0);
+    h->launches++;
+    BF_CUDA(cudaGetLastError());
   }
   for (int ps = 0; ps < passes; ++ps) {
     Params p;
-    p.img = d_in; p.out = d_out;
-    p.fin = (ps > 0) ? h->ws_feat[(ps - 1) & 1].as<__half>() : nullptr;
+    p.out = d_out;
+    p.fin = h->ws_feat[(ps + 1) & 1].as<__half>();
     p.fout = (ps + 1 < passes) ? h->ws_feat[ps & 1].as<__half>() : nullptr;
-    p.wbase = h->d_base_f32.as<float>();
     p.wumma = h->d_conv_umma.as<uint8_t>();
     p.bias = h->d_bias_f32.as<float>();
     p.whead = h->d_head_f32.as<float>();
     p.n = e.n; p.h = e.h; p.w = e.w; p.he = e.he; p.we = e.we;
-    p.k0 = k0;
     p.blk0 = ps * kb;
     p.nblk = std::min(kb, N - p.blk0);
-    p.first = (ps == 0); p.last = (ps + 1 == passes); p.out_u8 = out_u8 ? 1 : 0;
+    p.last = (ps + 1 == passes); p.out_u8 = out_u8 ? 1 : 0;
     const int nl = 2 * p.nblk, halo = 2 * p.nblk;
-    // shared-memory budget -> region rows (<= MAX_RH by TMEM capacity)
+    // shared-memory budget -> region rows (<= MAX_RH by TMEM capacity), a whole number of row groups when possible
     const size_t fixed = planes_offset(nl) + 64;
-    int rh_max = (int)((MAX_SMEM - fixed) / ((size_t)4 * RW * 16)) - 1;   // 4 planes, 2 KB per row each (+ slack)
+    int rh_max = MAX_RH;
     while (rh_max > 0 && fixed + (size_t)4 * plane_bytes_of(rh_max) > (size_t)MAX_SMEM) --rh_max;
-    rh_max = std::min(rh_max, MAX_RH);
-    if (p.first) {
-      // the uint8 tile + base weights alias the two T planes
-      while (rh_max > 2 * halo + 1) {
-        const size_t need = (((size_t)k0 * k0 * 3 * C * 4 + 15) & ~size_t(15)) + (size_t)(rh_max + 2 * r0) * (RW + 2 * r0) * 3;
-        if (need <= (size_t)2 * plane_bytes_of(rh_max)) break;
-        --rh_max;
-      }
-    }
     const int rows_needed = p.last ? e.h : e.he;
     const int cols_needed = p.last ? e.w : e.we;
-    const int th_max = rh_max - 2 * halo;
+    int th_max = rh_max - 2 * halo;
     p.tw = RW - 2 * halo;
     if (th_max < 1 || p.tw < 1) {
       set_error("fused tcgen05 pass does not fit (kb=%d)", kb);
       return BFCNN_ERR_INTERNAL;
     }
+    if (rows_needed > th_max && (rh_max / GROUP) * GROUP - 2 * halo >= 1) th_max = (rh_max / GROUP) * GROUP - 2 * halo;
     p.tiles_y = (rows_needed + th_max - 1) / th_max;
     p.th = (rows_needed + p.tiles_y - 1) / p.tiles_y;   // balance the tile rows
     p.rh = p.th + 2 * halo;
@@ -480,9 +640,31 @@ int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool
       set_error("internal: tcgen05 pass smem %zu rh %d", smem, p.rh);
       return BFCNN_ERR_INTERNAL;
     }
-    const long long grid = (long long)p.tiles_x * p.tiles_y * e.n;
-    BF_REQUIRE(grid < (1ll << 31), "too many tiles");
-    umma_pass_kernel<<<(unsigned)grid, NTHREADS, smem, st>>>(p);
+    const long long regions = (long long)p.tiles_x * p.tiles_y * e.n;
+    BF_REQUIRE(regions < (1ll << 31), "too many tiles");
+    p.regions = (int)regions;
+    const int grid = (int)std::min<long long>(regions, h->sm_count);
+    static const int trace_on = env_int_u("BFCNN_UMMA_TRACE", 0);
+    p.trace = nullptr; p.trace_block = 0;
+    if (trace_on && ps == std::min(1, passes - 1)) {
+      BF_CHECK(h->ws_feat[2].reserve(256 * sizeof(long long)));
+      BF_CUDA(cudaMemsetAsync(h->ws_feat[2].p, 0, 256 * sizeof(long long), st));
+      p.trace = h->ws_feat[2].as<long long>(); p.trace_block = grid / 2;
+    }
+    if (p.last) umma_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p);
+    else umma_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p);
+    if (p.trace) {
+      long long t[256];
+      BF_CUDA(cudaMemcpyAsync(t, p.trace, sizeof(t), cudaMemcpyDeviceToHost, st));
+      BF_CUDA(cudaStreamSynchronize(st));
+      fprintf(stderr, "[umma trace] pass %d rh %d nl %d regions %d grid %d: setup %lld total %lld (%.0f per region)\n", ps, p.rh, nl,
+              p.regions, grid, t[1] - t[0], t[3] - t[0], (double)(t[3] - t[0]) / ((p.regions + grid - 1) / grid));
+      for (int L = 0; L < 8; ++L) {
+        fprintf(stderr, "  layer %d: mma issue [%lld .. %lld] |", L, t[8 + 2 * L] - t[0], t[9 + 2 * L] - t[0]);
+        for (int s = 0; s < NSETS; ++s) fprintf(stderr, " epi%d end %lld", s, t[40 + s * 16 + L] - t[0]);
+        fprintf(stderr, "\n");
+      }
+    }
     h->launches++;
     BF_CUDA(cudaGetLastError());
   }

@@ -96,12 +96,15 @@ struct Params {
   int m_dim;           // throughput: M (64 or 128)
   int n2;              // throughput: if > 0 every other MMA uses N = n2 and a shifted A
   int preload;         // correctness: 1 => preload D with a constant via tcgen05.st and accumulate on top
+  int group;           // throughput: consecutive MMAs sharing one D block (1 = every MMA its own block)
+  int commit_every;    // throughput: tcgen05.commit to a scratch mbarrier every this many MMAs (0 = never)
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* pl0 = smem;
   uint8_t* pl1 = smem + PLANE_BYTES;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
     const int tap = (dy + 1) * 3 + dx;
     reinterpret_cast<__half*>(sB)[i] = p.wts[(tap * 16 + co) * 16 + kc * 8 + k8];
   }
-  if (tid == 0) mbar_init(smem_u32(&s_bar), 1);
+  if (tid == 0) { mbar_init(smem_u32(&s_bar), 1); mbar_init(smem_u32(&s_bar2), 1); }
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(&s_tmem)));
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = s_tmem;
-  const uint32_t a0 = smem_u32(pl0), b0 = smem_u32(sB), bar = smem_u32(&s_bar);
+  const uint32_t a0 = smem_u32(pl0), b0 = smem_u32(sB), bar = smem_u32(&s_bar), bar2 = smem_u32(&s_bar2);
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 
   if (p.mode == 0) {
@@ -188,9 +191,11 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
         for (int i = 0; i < p.mmas; i += 8) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const uint32_t k = (uint32_t)((i + u) & 15);
+            const uint32_t j = (uint32_t)(i + u);
+            const uint32_t k = (p.group > 1 ? j / (uint32_t)p.group : j) & 15;
             if ((u & 1) && p.n2 > 0) mma(tmem + k * 16, ad0 + (uint64_t)(k * sh + 1), bd, idesc2, 1u);
-            else mma(tmem + k * 16, ad0 + (uint64_t)(k * sh), bd, idesc, 1u);
+            else mma(tmem + k * 16, ad0 + (uint64_t)(k * sh + (p.group > 1 ? j % (uint32_t)p.group : 0)), bd, idesc, 1u);
+            if (p.commit_every > 0 && (j % (uint32_t)p.commit_every) == (uint32_t)p.commit_every - 1) commit(bar2);
           }
         }
         commit(bar);
@@ -233,7 +238,7 @@ int main() {
 
   // ---- Q1/Q2 correctness
   for (int preload = 0; preload < 2; ++preload) {
-    Params p{d_act, d_wts, d_out, d_cyc, 0, 48, 0, 0, 0, 128, 0, preload};
+    Params p{d_act, d_wts, d_out, d_cyc, 0, 48, 0, 0, 0, 128, 0, preload, 1, 0};
     CK(cudaMemset(d_out, 0, (size_t)ROWS * 128 * 16 * 4));
     probe_kernel<<<1, 128, SMEM_BYTES>>>(p);
     CK(cudaDeviceSynchronize());
@@ -260,8 +265,8 @@ int main() {
   }
 
   // ---- Q3 throughput
-  auto run = [&](int grid, int M, int N, int n2, int shift) {
-    Params p{d_act, d_wts, d_out, d_cyc, 1, N, 384, 10, shift, M, n2, 0};
+  auto run = [&](int grid, int M, int N, int n2, int shift, int group = 1, int commit_every = 0) {
+    Params p{d_act, d_wts, d_out, d_cyc, 1, N, 384, 10, shift, M, n2, 0, group, commit_every};
     probe_kernel<<<grid, 128, SMEM_BYTES>>>(p);
     CK(cudaDeviceSynchronize());
     std::vector<long long> cyc(grid);
@@ -271,13 +276,21 @@ int main() {
     avg /= grid;
     const double per = avg / (384.0 * 10.0);
     const double macs = n2 > 0 ? 0.5 * M * (N + n2) * 16 : (double)M * N * 16;
-    printf("grid %3d M %3d N %3d n2 %3d shift %3d: %.1f cyc/MMA -> %.0f MAC/clk/SM\n", grid, M, N, n2, shift, per, macs / per);
+    printf("grid %3d M %3d N %3d n2 %3d shift %3d group %d commit %d: %.1f cyc/MMA -> %.0f MAC/clk/SM\n", grid, M, N, n2, shift, group,
+           commit_every, per, macs / per);
   };
   for (int N : {16, 32, 48, 64, 96, 128, 144, 192, 256}) run(148, 128, N, 0, 1);
   for (int N : {16, 32, 48, 64, 96, 128, 256}) run(148, 64, N, 0, 1);
   run(148, 128, 96, 48, 1);
   run(148, 128, 144, 0, 128);
   run(1, 128, 96, 48, 1);
+  // the conv stack's pattern: 3 dx-shifted MMAs per D block, rows 128 px apart, a commit per row
+  run(148, 128, 48, 0, 128, 1, 0);
+  run(148, 128, 48, 0, 128, 3, 0);
+  run(148, 128, 48, 0, 128, 3, 3);
+  run(148, 128, 48, 0, 128, 1, 3);
+  run(148, 128, 48, 0, 128, 1, 1);
+  run(148, 128, 48, 0, 1, 3, 3);
   printf("done\n");
   return 0;
 }
