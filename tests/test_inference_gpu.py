@@ -3,16 +3,17 @@
 Gates (BASELINE.json north_star / SURVEY 8d):
   fp32, f16x3 : max-abs <= 0.5 and mean-abs <= 0.05 on the 0..255 scale (pre-round float);
                 uint8 outputs differ by <= 1 LSB on < 1 % of values
-  f16         : stated looser bound max-abs <= 2.0, mean-abs <= 0.25
+  f16         : stated looser bound max-abs <= 2.0, mean-abs <= 0.25 (the tcgen05 stack; `f16_mma_sync` is the same
+                arithmetic on the legacy mma.sync path, kept as a comparison baseline)
 """
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
-GATES = {"fp32": (0.5, 0.05), "f16x3": (0.5, 0.05), "f16": (2.0, 0.25)}
+GATES = {"fp32": (0.5, 0.05), "f16x3": (0.5, 0.05), "f16": (2.0, 0.25), "f16_mma_sync": (2.0, 0.25)}
 # what the kernels actually achieve (regression guard, tighter than the gate)
-TIGHT = {"fp32": (0.02, 0.002), "f16x3": (0.02, 0.002), "f16": (2.0, 0.25)}
+TIGHT = {"fp32": (0.02, 0.002), "f16x3": (0.02, 0.002), "f16": (2.0, 0.25), "f16_mma_sync": (2.0, 0.25)}
 
 
 def _model(n_layers, **kw):
@@ -34,11 +35,12 @@ def _check(y, yref, u8, u8ref, prec):
     assert mx <= GATES[prec][0] and mean <= GATES[prec][1], (prec, mx, mean)
     assert mx <= TIGHT[prec][0] and mean <= TIGHT[prec][1], ("regression", prec, mx, mean)
     du = np.abs(u8.astype(np.int32) - u8ref.astype(np.int32))
-    assert du.max() <= (1 if prec != "f16" else 2)
-    assert (du > 0).mean() < (0.01 if prec != "f16" else 0.25)
+    f16 = prec.startswith("f16") and prec != "f16x3"
+    assert du.max() <= (2 if f16 else 1)
+    assert (du > 0).mean() < (0.25 if f16 else 0.01)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16", "f16_mma_sync"])
 @pytest.mark.parametrize("n_layers,shape", [
     (1, (1, 32, 32, 3)),
     (6, (2, 64, 64, 3)),
@@ -70,7 +72,7 @@ def test_no_pad_pow2(native_lib, prec):
     assert np.abs(y2 - yref).max() > 1.0
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16", "f16_mma_sync"])
 def test_edge_shapes(native_lib, prec):
     m = _model(6, precision=prec)
     out = m(np.zeros((0, 16, 16, 3), np.uint8))
