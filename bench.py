@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--cpu-crop", type=int, default=768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="skip the secondary precision modes")
+    ap.add_argument("--no-training", action="store_true", help="skip the secondary training-step workload")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -280,6 +281,39 @@ def main():
             modes[prec] = {"value": world * mp_per_step_rank * steps / (rr["ms"] / 1e3), "unit": UNIT,
                            "tflops_algorithmic": alg_flops / (rr["stack_ms"] / 1e3) / 1e12}
 
+    # secondary workload: BASELINE configs[3]/[4] -- training step (corruption + forward/backward + all-reduce + Adam)
+    training = None
+    if not args.no_training:
+        from blind_image_denoising_b200 import synthetic_variables, _native
+        from blind_image_denoising_b200.training import Trainer
+        t_layers = 6 if world == 1 else 18
+        t_arch = Arch(no_layers=t_layers)
+        tr = Trainer(t_arch, synthetic_variables(t_arch, 0), device=local_rank,
+                     optimizer_config={"gradient_clipping_by_norm": 1.0})
+        clean_u8 = torch.from_numpy(np.random.default_rng(1000 + rank).integers(0, 256, size=(32, 256, 256, 3), dtype=np.uint8)).cuda()
+        ncfg = _native.NoiseCfg(5.0, 40.0, 0.05, 0.1, 1, 1, 0, 1)
+        def train_once(step):
+            clean, noisy = tr.prepare_data(clean_u8, ncfg, 0, (step * world + rank) * 32)
+            _, _, _, g = tr.train_step_single_gpu(clean, noisy)
+            tr.apply_grads(g)
+        for i in range(2):
+            train_once(i)
+        barrier()
+        l0 = tr.launch_count()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        tsteps = 3
+        for i in range(tsteps):
+            train_once(2 + i)
+        t1e.record()
+        barrier()
+        tms = max_over_ranks(t0e.elapsed_time(t1e)) / tsteps
+        training = {"workload": f"resnet_color_1x{t_layers} training step: corruption + fwd/bwd (BN batch stats, hinged MAE, L1/L2 reg) + "
+                                f"{'NCCL all-reduce + ' if world > 1 else ''}Adam, batch 32 x 256x256x3 per GPU (BASELINE configs[{3 if world == 1 else 4}])",
+                    "value": world * 32 * 256 * 256 / 1e6 / (tms / 1e3), "unit": UNIT, "ms_per_step": tms, "dtype": "f32",
+                    "gpu_launches_per_step": int((tr.launch_count() - l0) / tsteps)}
+        tr.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         mp_s, med, cores = cpu_reference_mp_s(args.cpu_crop, reps=3)
@@ -307,6 +341,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "modes": modes,
+            "training": training,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
