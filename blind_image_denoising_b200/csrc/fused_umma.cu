@@ -27,6 +27,8 @@
 //
 // Reference arithmetic: module_denoiser.py:53-73, utilities.py:449-461 (normalise), backbone_resnet.py:258-262
 // (base conv), backbone_blocks.py:167-246 (block), model.py:297-342 (head), utilities.py:435-443 (denormalise).
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include "kernels.cuh"
 
 namespace bfcnn {
@@ -170,6 +172,18 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+// TMA: one quarter-row of one channel half (32 pixels x 16 B = 512 contiguous shared bytes) of the NHWC16 feature map,
+// addressed as a 5-D tensor {ch8, half, x, y, n}; out-of-extent coordinates (negative included) are zero-filled by the
+// hardware, which is exactly the "same" padding of the feature map.
+__device__ __forceinline__ void tma_load_q(uint32_t dst, const CUtensorMap* tmap, int hf, int gx, int gy, int b, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(hf), "r"(gx), "r"(gy), "r"(b), "r"(mbar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -205,24 +219,6 @@ __device__ __forceinline__ Region region_of(const Params& p, int it, int halo) {
   return r;
 }
 
-// 16 consecutive pixels (both channel halves = 32 x 16 B = 512 contiguous bytes of the NHWC16 feature map) -> the X
-// planes, one 16-byte cp.async per lane: lane = 2*pixel + half, so the global side is one fully coalesced 512-byte
-// read and the shared side two contiguous 256-byte runs (a per-pixel mapping with its 32-byte global stride costs
-// 40 shared-memory wavefronts per instruction instead of 8: profiles/r01_umma_ncu.md).  Zero outside the extent
-// ("same" padding).
-__device__ __forceinline__ void fetch_16px(const Params& p, const Smem& S, const Region& g, int r, int c0, int lane) {
-  const int c = c0 + (lane >> 1), hf = lane & 1;
-  const int gy = g.oy + r, gx = g.ox + c;
-  const bool valid = (gy >= 0) && (gy < p.he) && (gx >= 0) && (gx < p.we);
-  const __half* src = p.fin + (valid ? (((((long long)g.b * p.he + gy) * p.we + gx) << 4) + 8 * hf) : 0);
-  cp_async16_zfill(S.X[hf] + (uint32_t)(r * RW + c) * 16u, src, valid);
-}
-
-// ---------------------------------------------------------------------------- epilogue of one row quarter
-// conv_a rows: T = ReLU(D); then the accumulator block is PRE-LOADED with the residual X + b' (fp32), so that conv_b
-// accumulates Add([x, previous]) (backbone_blocks.py:240-242; BN folded) inside the tensor core and the
-// X plane is dead one layer earlier (the next region's prefetch starts there).
-// conv_b rows: D already is X + conv_b'(T) + b'; mask, pack, write X / the feature map / the head; re-zero D.
 // Per-thread constants of one region: everything that does not depend on the row is computed once, so that the row
 // loop below is ~60 instructions per conv_a row and ~25 per conv_b row (it was 170: the epilogue warps, not the tensor
 // pipe, set the pace -- profiles/r01_umma_ncu.md).
@@ -237,16 +233,14 @@ struct EpiCtx {
   long long row_halves;   // we * 16
   long long row_out;      // w * 3 elements
   int h_img;              // rows of the image (head: gy < h)
-  // next region (prefetch): two 16-pixel chunks of this warp's quarter
-  const __half* nsrc[2];
-  bool ncol_ok[2];
-  int noy;
-  uint32_t nx[2];         // shared destination (row 0) of this lane's 16 bytes per chunk
+  // next region (prefetch of this warp's quarter-row by TMA)
+  int nb, noy, nox_q;     // image index, first row, first column of the quarter in the next region
+  uint32_t nx0, nx1;      // shared destinations (region row 0) of the quarter in the two channel-half planes
 };
 
 template <int EPI, bool PREFETCH>
-__device__ __forceinline__ void epilogue_layer(const Params& p, const Smem& S, const EpiCtx& E, const float* s_bias_next,
-                                               const float* s_head, int set, int l, uint32_t parity) {
+__device__ __forceinline__ void epilogue_layer(const Params& p, const CUtensorMap* tmap, const Smem& S, const EpiCtx& E,
+                                               const float* s_bias_next, const float* s_head, int set, int l, uint32_t parity) {
   const int r_lo = l + 1, r_hi = p.rh - l - 1;
   float bias[16];
   if (EPI == EPI_RELU_TO_T) {
@@ -336,19 +330,19 @@ __device__ __forceinline__ void epilogue_layer(const Params& p, const Smem& S, c
     } else if (EPI == EPI_RES_HEAD || EPI == EPI_RES_TO_GLOBAL) {
       tmem_zero16(taddr);   // rows that fell out of the valid range hold stale partial sums: clean for the next region
     }
+    fence_async_smem();   // T/X stores of this row -> async proxy (tensor core); X reads of this row -> before the TMA overwrite
     if (PREFETCH) {
-      // X row r is dead for this region: fetch the next region's (this warp's quarter = 2 x 16 pixels); the mbarrier
-      // arrive fires when the copies have landed
-      const bool row_ok = (unsigned)(E.noy + r) < (unsigned)E.he;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const bool ok = row_ok && E.ncol_ok[k];
-        cp_async16_zfill(E.nx[k] + po, ok ? (E.nsrc[k] + (long long)r * E.row_halves) : p.fin, ok);
+      // X row r is dead for this region: one lane fetches the next region's quarter-row (2 halves x 512 B) by TMA; the
+      // x_ready barrier of the row group completes when the bytes have landed
+      __syncwarp();
+      if (elect_one_sync()) {
+        const uint32_t bar = S.bars + (uint32_t)(32 + grp) * 8;
+        mbar_arrive_expect_tx(bar, 1024u);
+        tma_load_q(E.nx0 + po, tmap, 0, E.nox_q, E.noy + r, E.nb, bar);
+        tma_load_q(E.nx1 + po, tmap, 1, E.nox_q, E.noy + r, E.nb, bar);
       }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(S.bars + (uint32_t)(32 + grp) * 8) : "memory");
     }
     tmem_wait_st();
-    fence_async_smem();
     tc_fence_before();
     mbar_arrive(S.bars + (uint32_t)(16 + grp) * 8);
   }
@@ -357,7 +351,7 @@ __device__ __forceinline__ void epilogue_layer(const Params& p, const Smem& S, c
 // ---------------------------------------------------------------------------- the pass kernel (persistent)
 template <bool LAST_PASS>
 __global__ void __launch_bounds__(NTHREADS, 1)
-umma_pass_kernel(const Params p) {
+umma_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: no BSSY/BSYNC around role branches
@@ -379,21 +373,19 @@ umma_pass_kernel(const Params p) {
   float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
 
   // ---------------- one-time setup: barriers, TMEM, weights, the first region
-  // [0,16) mma_done[g] (tcgen05.commit), [16,32) epi_done[g], [32,48) x_ready[g] (next region's X rows): every thread
-  // of the 128-pixel row arrives once per row of the group
-  if (tid < 48) {
+  // [0,16) mma_done[g] (tcgen05.commit); [16,32) epi_done[g]: every thread of the 128-pixel row arrives once per row of
+  // the group; [32,48) x_ready[g] (next region's X rows): one arrive.expect_tx per warp per row + the TMA bytes;
+  // [48] the first region's staging (one arrive.expect_tx per warp)
+  if (tid < 49) {
     const int gi = tid & 15;
     const int rows = max(0, min(GROUP, p.rh - gi * GROUP));
-    mbar_init(S.bars + tid * 8, tid < 16 ? 1u : (uint32_t)max(1, 128 * rows));
+    const uint32_t cnt = tid < 16 ? 1u : (tid < 32 ? (uint32_t)max(1, 128 * rows) : (tid < 48 ? (uint32_t)max(1, 4 * rows) : (uint32_t)(NTHREADS / 32)));
+    mbar_init(S.bars + tid * 8, cnt);
   }
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(s0 + SM_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
-  {
-    const Region g0 = region_of(p, (int)blockIdx.x, halo);
-    for (int i = warp; i < p.rh * (RW / 16); i += NTHREADS / 32) fetch_16px(p, S, g0, i / (RW / 16), (i % (RW / 16)) * 16, lane);
   }
   for (int i = tid; i < nl * (W_LAYER_BYTES / 16); i += NTHREADS)
     reinterpret_cast<uint4*>(smem + SM_WTS)[i] =
@@ -406,8 +398,24 @@ umma_pass_kernel(const Params p) {
     const uint32_t off = (uint32_t)pl * S.plane_bytes + (k < SLACK_PX ? (uint32_t)k * 16u : S.plane_bytes - (uint32_t)(2 * SLACK_PX - k) * 16u);
     *reinterpret_cast<uint4*>(g_planes + off) = make_uint4(0u, 0u, 0u, 0u);
   }
-  cp_async_wait_all();
-  fence_async_smem();   // generic-proxy writes of X -> visible to the tensor core (async proxy)
+  fence_async_smem();   // barrier inits + slack zeros -> async proxy
+  __syncthreads();
+  {
+    // the first region: quarter-row boxes by TMA, spread over the warps' elected lanes, one barrier
+    const Region g0 = region_of(p, (int)blockIdx.x, halo);
+    const int nbox = p.rh * 8;   // rows x 4 quarters x 2 halves
+    const uint32_t bar = S.bars + 48 * 8;
+    if (elect_one_sync()) {
+      int mine = 0;
+      for (int i = warp; i < nbox; i += NTHREADS / 32) ++mine;
+      mbar_arrive_expect_tx(bar, (uint32_t)mine * 512u);
+      for (int i = warp; i < nbox; i += NTHREADS / 32) {
+        const int hf = i & 1, q = (i >> 1) & 3, r = i >> 3;
+        tma_load_q(S.X[hf] + (uint32_t)(r * RW + q * 32) * 16u, &tmap, hf, g0.ox + q * 32, g0.oy + r, g0.b, bar);
+      }
+    }
+    mbar_wait(bar, 0);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -422,6 +430,7 @@ umma_pass_kernel(const Params p) {
     E.tq = tmem + ((uint32_t)(quarter * 32) << 16);
     E.x0 = S.X[0] + (uint32_t)c * 16u; E.x1 = S.X[1] + (uint32_t)c * 16u;
     E.t0 = S.T[0] + (uint32_t)c * 16u; E.t1 = S.T[1] + (uint32_t)c * 16u;
+    E.nx0 = S.X[0] + (uint32_t)(quarter * 32) * 16u; E.nx1 = S.X[1] + (uint32_t)(quarter * 32) * 16u;
     E.he = p.he; E.h_img = p.h;
     E.row_halves = (long long)p.we * 16; E.row_out = (long long)p.w * 3;
     // zero this warp's share of the accumulator blocks, then release the MMA issuer
@@ -442,26 +451,18 @@ umma_pass_kernel(const Params p) {
         E.out_col = reinterpret_cast<uint8_t*>(p.out) + ((((long long)g.b * p.h + g.oy) * p.w + gx) * 3) * (p.out_u8 ? 1 : 4);
         if (has_next) {
           const Region gn = region_of(p, it + (int)gridDim.x, halo);
-          E.noy = gn.oy;
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int cn = quarter * 32 + 16 * k + (lane >> 1), hf = lane & 1;
-            const int gxn = gn.ox + cn;
-            E.ncol_ok[k] = (gxn >= 0) && (gxn < p.we);
-            E.nsrc[k] = p.fin + ((((long long)gn.b * p.he + gn.oy) * p.we + gxn) << 4) + 8 * hf;
-            E.nx[k] = S.X[hf] + (uint32_t)cn * 16u;
-          }
+          E.nb = gn.b; E.noy = gn.oy; E.nox_q = gn.ox + quarter * 32;
         }
       }
       for (int l = 0; l < nl; ++l, ++L) {
         const float* s_bias_next = s_bias + (l + 1) * C;   // conv_a pre-loads the bias of the conv_b that follows
         if ((l & 1) == 0) {
-          if (has_next && l == nl - 2) epilogue_layer<EPI_RELU_TO_T, true>(p, S, E, s_bias_next, s_head, set, l, L & 1u);
-          else epilogue_layer<EPI_RELU_TO_T, false>(p, S, E, s_bias_next, s_head, set, l, L & 1u);
+          if (has_next && l == nl - 2) epilogue_layer<EPI_RELU_TO_T, true>(p, &tmap, S, E, s_bias_next, s_head, set, l, L & 1u);
+          else epilogue_layer<EPI_RELU_TO_T, false>(p, &tmap, S, E, s_bias_next, s_head, set, l, L & 1u);
         } else if (l + 1 < nl) {
-          epilogue_layer<EPI_RES_TO_X, false>(p, S, E, s_bias_next, s_head, set, l, L & 1u);
+          epilogue_layer<EPI_RES_TO_X, false>(p, &tmap, S, E, s_bias_next, s_head, set, l, L & 1u);
         } else {
-          epilogue_layer<LAST_PASS ? EPI_RES_HEAD : EPI_RES_TO_GLOBAL, false>(p, S, E, s_bias_next, s_head, set, l, L & 1u);
+          epilogue_layer<LAST_PASS ? EPI_RES_HEAD : EPI_RES_TO_GLOBAL, false>(p, &tmap, S, E, s_bias_next, s_head, set, l, L & 1u);
         }
         if (tr && lane == 0 && quarter == 0 && L < 8) p.trace[40 + set * 16 + L] = clock64();
       }
@@ -520,47 +521,76 @@ umma_pass_kernel(const Params p) {
 }
 
 // ---------------------------------------------------------------------------- base conv -> fp16 NHWC16
-// normalise (utilities.py:449-461) + base conv k0 x k0, 3 -> 16 (backbone_resnet.py:258-262) over the work extent;
-// the raw-zero pow2 canvas (utilities.py:749) and the zero padding of the NORMALISED tensor as in conv_f32.cu.
-__global__ void __launch_bounds__(256, 3)
+// normalise (utilities.py:449-461) + base conv k0 x k0, 3 -> 16 (backbone_resnet.py:258-262) over the work extent.
+// CTA tile 64 x 16 pixels; the uint8 halo tile goes to shared memory already normalised (exactly the reference's
+// x/255 - 0.5 in fp32): 0 outside the work extent (zero padding of the NORMALISED tensor), -0.5 on the raw-zero pow2
+// canvas (utilities.py:749).  Each thread owns 4 consecutive pixels x 16 cout.
+constexpr int BC_W = 64, BC_H = 16;
+__global__ void __launch_bounds__(256, 2)
 base_conv_f16_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, const float* __restrict__ w,
-                     int n, int h, int wd, int he, int we, int k0) {
-  extern __shared__ float sw[];  // [k0*k0*3][16]
-  for (int i = threadIdx.x; i < k0 * k0 * 3 * C; i += blockDim.x) sw[i] = w[i];
+                     int h, int wd, int he, int we, int k0) {
+  extern __shared__ __align__(16) float bsm[];
+  const int r0 = (k0 - 1) >> 1;
+  const int tw = BC_W + 2 * r0, th = BC_H + 2 * r0;
+  float* s_w = bsm;                              // [k0*k0*3][16]
+  float* s_in = bsm + k0 * k0 * 3 * C;           // [th][tw][3]
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * BC_W, y0 = blockIdx.y * BC_H, b = blockIdx.z;
+  for (int i = tid; i < k0 * k0 * 3 * C; i += 256) s_w[i] = w[i];
+  const uint8_t* img_b = img + (long long)b * h * wd * 3;
+  for (int i = tid; i < th * tw; i += 256) {
+    const int ly = i / tw, lx = i - ly * tw;
+    const int gy = y0 + ly - r0, gx = x0 + lx - r0;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (gy >= 0 && gy < he && gx >= 0 && gx < we) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      if (gy < h && gx < wd) {
+        const uint8_t* sp = img_b + ((long long)gy * wd + gx) * 3;
+        a0 = (float)sp[0]; a1 = (float)sp[1]; a2 = (float)sp[2];
+      }
+      v0 = __fsub_rn(__fdiv_rn(a0, 255.f), 0.5f);
+      v1 = __fsub_rn(__fdiv_rn(a1, 255.f), 0.5f);
+      v2 = __fsub_rn(__fdiv_rn(a2, 255.f), 0.5f);
+    }
+    s_in[i * 3 + 0] = v0; s_in[i * 3 + 1] = v1; s_in[i * 3 + 2] = v2;
+  }
   __syncthreads();
-  const int r = (k0 - 1) >> 1;
-  const long long total = (long long)n * he * we;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % we);
-    const int y = (int)((idx / we) % he);
-    const int b = (int)(idx / ((long long)we * he));
-    float acc[C];
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 0.f;
-    for (int dy = 0; dy < k0; ++dy) {
-      const int yy = y + dy - r;
-      if (yy < 0 || yy >= he) continue;
-      for (int dx = 0; dx < k0; ++dx) {
-        const int xx = x + dx - r;
-        if (xx < 0 || xx >= we) continue;
-        float v[3] = {0.f, 0.f, 0.f};
-        if (yy < h && xx < wd) {
-          const uint8_t* s = img + (((long long)b * h + yy) * wd + xx) * 3;
-          v[0] = (float)s[0]; v[1] = (float)s[1]; v[2] = (float)s[2];
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[p][c] = 0.f;
+  for (int dy = 0; dy < k0; ++dy)
+    for (int dx = 0; dx < k0; ++dx) {
+      const float* ip = s_in + ((ty + dy) * tw + 4 * tx + dx) * 3;
+      const float* wp = s_w + (dy * k0 + dx) * 3 * C;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        float wv[C];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(wp + ci * C + 4 * q);
+          wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
         }
-        const float* wt = sw + (dy * k0 + dx) * 3 * C;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          const float xn = __fsub_rn(__fdiv_rn(v[ci], 255.f), 0.5f);
+        for (int p = 0; p < 4; ++p) {
+          const float xv = ip[p * 3 + ci];
 #pragma unroll
-          for (int c = 0; c < C; ++c) acc[c] = fmaf(xn, wt[ci * C + c], acc[c]);
+          for (int c = 0; c < C; ++c) acc[p][c] = fmaf(xv, wv[c], acc[p][c]);
         }
       }
     }
+  const int gy = y0 + ty;
+  if (gy >= he) return;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int gx = x0 + 4 * tx + p;
+    if (gx >= we) continue;
     uint4 lo, hi;
-    lo.x = pack_h2(acc[0], acc[1]); lo.y = pack_h2(acc[2], acc[3]); lo.z = pack_h2(acc[4], acc[5]); lo.w = pack_h2(acc[6], acc[7]);
-    hi.x = pack_h2(acc[8], acc[9]); hi.y = pack_h2(acc[10], acc[11]); hi.z = pack_h2(acc[12], acc[13]); hi.w = pack_h2(acc[14], acc[15]);
-    uint4* o = reinterpret_cast<uint4*>(out + (idx << 4));
+    lo.x = pack_h2(acc[p][0], acc[p][1]); lo.y = pack_h2(acc[p][2], acc[p][3]); lo.z = pack_h2(acc[p][4], acc[p][5]); lo.w = pack_h2(acc[p][6], acc[p][7]);
+    hi.x = pack_h2(acc[p][8], acc[p][9]); hi.y = pack_h2(acc[p][10], acc[p][11]); hi.z = pack_h2(acc[p][12], acc[p][13]); hi.w = pack_h2(acc[p][14], acc[p][15]);
+    uint4* o = reinterpret_cast<uint4*>(out + ((((long long)b * he + gy) * we + gx) << 4));
     o[0] = lo;
     o[1] = hi;
   }
@@ -571,6 +601,37 @@ base_conv_f16_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, 
 // ------------------------------------------------------------------------------------
 // host: pass planning
 // ------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e) {
+  static tmap_encode_fn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    BF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return BFCNN_ERR_CUDA;
+    }
+    enc = reinterpret_cast<tmap_encode_fn>(fn);
+  }
+  // fp16 NHWC16 viewed as {ch8, half, x, y, n}
+  const cuuint64_t dims[5] = {8, 2, (cuuint64_t)e.we, (cuuint64_t)e.he, (cuuint64_t)e.n};
+  const cuuint64_t strides[4] = {16, 32, (cuuint64_t)e.we * 32, (cuuint64_t)e.he * e.we * 32};
+  const cuuint32_t box[5] = {8, 1, 32, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (extent %d x %d x %d)", (int)r, e.n, e.he, e.we);
+    return BFCNN_ERR_CUDA;
+  }
+  return BFCNN_OK;
+}
+
 static int env_int_u(const char* name, int dflt) {
   const char* s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
@@ -598,10 +659,11 @@ int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool
 
   // pass "-1": base conv into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
   {
-    const long long total = (long long)e.n * e.he * e.we;
-    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
-    base_conv_f16_kernel<<<blocks, 256, (size_t)k0 * k0 * 3 * C * sizeof(float), st>>>(
-        d_in, h->ws_feat[1].as<__half>(), h->d_base_f32.as<float>(), e.n, e.h, e.w, e.he, e.we, k0);
+    const int r0 = (k0 - 1) / 2;
+    const size_t bsm = (size_t)(k0 * k0 * 3 * C + (BC_H + 2 * r0) * (BC_W + 2 * r0) * 3) * sizeof(float);
+    dim3 grid((e.we + BC_W - 1) / BC_W, (e.he + BC_H - 1) / BC_H, e.n);
+    BF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "image too large for the base conv grid");
+    base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, h->ws_feat[1].as<__half>(), h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, k0);
     h->launches++;
     BF_CUDA(cudaGetLastError());
   }
@@ -651,8 +713,10 @@ int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool
       BF_CUDA(cudaMemsetAsync(h->ws_feat[2].p, 0, 256 * sizeof(long long), st));
       p.trace = h->ws_feat[2].as<long long>(); p.trace_block = grid / 2;
     }
-    if (p.last) umma_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p);
-    else umma_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p);
+    CUtensorMap tmap;
+    BF_CHECK(make_feature_tmap(&tmap, p.fin, e));
+    if (p.last) umma_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
+    else umma_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     if (p.trace) {
       long long t[256];
       BF_CUDA(cudaMemcpyAsync(t, p.trace, sizeof(t), cudaMemcpyDeviceToHost, st));
