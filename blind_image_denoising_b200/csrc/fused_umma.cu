@@ -486,6 +486,7 @@ umma_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
           if (tr && L < 8) p.trace[8 + 2 * L] = clock64();
           for (int grp = 0; grp < ng; ++grp) {
             if (L > 0) {
+              const long long w0 = tr ? clock64() : 0;
               const uint32_t par = (L - 1) & 1u;
               if (grp == 0) mbar_wait(S.bars + (uint32_t)(16 + 0) * 8, par);
               if (grp + 1 < ng) mbar_wait(S.bars + (uint32_t)(16 + grp + 1) * 8, par);
@@ -496,6 +497,7 @@ umma_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 fence_async_smem();   // generic-proxy writes observed through the mbarrier -> async-proxy reads of the MMA
               }
               tc_fence_after();
+              if (tr && L < 8) p.trace[24 + L] += clock64() - w0;
             }
             const int row_end = min(grp * GROUP + GROUP, q_hi);
             for (int q = max(grp * GROUP, q_lo); q < row_end; ++q) {
@@ -724,7 +726,7 @@ int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool
       fprintf(stderr, "[umma trace] pass %d rh %d nl %d regions %d grid %d: setup %lld total %lld (%.0f per region)\n", ps, p.rh, nl,
               p.regions, grid, t[1] - t[0], t[3] - t[0], (double)(t[3] - t[0]) / ((p.regions + grid - 1) / grid));
       for (int L = 0; L < 8; ++L) {
-        fprintf(stderr, "  layer %d: mma issue [%lld .. %lld] |", L, t[8 + 2 * L] - t[0], t[9 + 2 * L] - t[0]);
+        fprintf(stderr, "  layer %d: mma issue [%lld .. %lld] waited %lld |", L, t[8 + 2 * L] - t[0], t[9 + 2 * L] - t[0], t[24 + L]);
         for (int s = 0; s < NSETS; ++s) fprintf(stderr, " epi%d end %lld", s, t[40 + s * 16 + L] - t[0]);
         fprintf(stderr, "\n");
       }
