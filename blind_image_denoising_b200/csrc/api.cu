@@ -46,40 +46,8 @@ int check_images(int n, int height, int width) {
   return BFCNN_OK;
 }
 
-int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int n, int height, int width,
-                 int precision, uint32_t flags, void* stream) {
-  BF_REQUIRE(h != nullptr, "handle is NULL");
-  BF_CHECK(check_images(n, height, width));
-  BF_REQUIRE(precision == BFCNN_PREC_FP32 || precision == BFCNN_PREC_F16 || precision == BFCNN_PREC_F16X3 ||
-                 precision == BFCNN_PREC_F16_MMA_SYNC,
-             "unknown precision");
-  const size_t npx = (size_t)n * height * width;
-  if (npx == 0) return BFCNN_OK;  // empty batch / empty image: nothing to do
-  BF_REQUIRE(in != nullptr && out != nullptr, "in/out is NULL");
-  BF_CUDA(cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t in_bytes = npx * 3, out_bytes = npx * 3 * (out_u8 ? 1 : sizeof(float));
-
-  const uint8_t* d_in = in;
-  if (!(flags & BFCNN_FLAG_IN_DEVICE)) {
-    BF_CHECK(h->ws_in.reserve(in_bytes));
-    BF_CUDA(cudaMemcpyAsync(h->ws_in.p, in, in_bytes, cudaMemcpyHostToDevice, st));
-    d_in = h->ws_in.as<uint8_t>();
-  }
-  void* d_out = out;
-  if (!(flags & BFCNN_FLAG_OUT_DEVICE)) {
-    BF_CHECK(h->ws_out.reserve(out_bytes));
-    d_out = h->ws_out.p;
-  }
-  const Extent e = make_extent(h, n, height, width, flags);
-  if (!h->packed_valid) {
-    // a training / optimiser step changed the variables on the device: fold and pack them again
-    BF_CUDA(cudaDeviceSynchronize());
-    BF_CUDA(cudaMemcpy(h->h_vars.data(), h->d_vars.p, h->lay.total * sizeof(float), cudaMemcpyDeviceToHost));
-    BF_CHECK(pack_weights(h));
-  }
-
-  BF_CUDA(cudaEventRecord(h->ev0, st));
+// the conv stack of one batch (device pointers)
+int run_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e, int precision, cudaStream_t st) {
   if (precision == BFCNN_PREC_FP32) {
     const size_t feat = (size_t)e.n * e.he * e.we * C * sizeof(float);
     BF_CHECK(h->ws_feat[0].reserve(feat));
@@ -94,17 +62,83 @@ int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int
       BF_CHECK(launch_conv3x3_f32(h, X, T, wa, nullptr, nullptr, nullptr, CONV_RELU, e, st));
       BF_CHECK(launch_conv3x3_f32(h, T, X, wb, bb, X, nullptr, CONV_RESIDUAL, e, st));
     }
-    BF_CHECK(launch_head(h, X, d_out, out_u8, h->d_head_f32.as<float>(), e, st));
-  } else if (precision == BFCNN_PREC_F16) {
-    BF_CHECK(run_fused_stack_umma(h, d_in, d_out, out_u8, e, st));
-  } else {
-    BF_CHECK(run_fused_stack(h, d_in, d_out, out_u8, e, precision == BFCNN_PREC_F16_MMA_SYNC ? BFCNN_PREC_F16 : precision, st));
+    return launch_head(h, X, d_out, out_u8, h->d_head_f32.as<float>(), e, st);
+  }
+  if (precision == BFCNN_PREC_F16) return run_fused_stack_umma(h, d_in, d_out, out_u8, e, st);
+  return run_fused_stack(h, d_in, d_out, out_u8, e, precision == BFCNN_PREC_F16_MMA_SYNC ? BFCNN_PREC_F16 : precision, st);
+}
+
+int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int n, int height, int width,
+                 int precision, uint32_t flags, void* stream) {
+  BF_REQUIRE(h != nullptr, "handle is NULL");
+  BF_CHECK(check_images(n, height, width));
+  BF_REQUIRE(precision == BFCNN_PREC_FP32 || precision == BFCNN_PREC_F16 || precision == BFCNN_PREC_F16X3 ||
+                 precision == BFCNN_PREC_F16_MMA_SYNC,
+             "unknown precision");
+  const size_t npx = (size_t)n * height * width;
+  if (npx == 0) return BFCNN_OK;  // empty batch / empty image: nothing to do
+  BF_REQUIRE(in != nullptr && out != nullptr, "in/out is NULL");
+  BF_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t px_img = (size_t)height * width;
+  const size_t in_bytes = npx * 3, osz = out_u8 ? 1 : sizeof(float), out_bytes = npx * 3 * osz;
+  if (!h->packed_valid) {
+    // a training / optimiser step changed the variables on the device: fold and pack them again
+    BF_CUDA(cudaDeviceSynchronize());
+    BF_CUDA(cudaMemcpy(h->h_vars.data(), h->d_vars.p, h->lay.total * sizeof(float), cudaMemcpyDeviceToHost));
+    BF_CHECK(pack_weights(h));
+  }
+  const bool in_host = !(flags & BFCNN_FLAG_IN_DEVICE), out_host = !(flags & BFCNN_FLAG_OUT_DEVICE);
+  if (in_host) BF_CHECK(h->ws_in.reserve(in_bytes));
+  if (out_host) BF_CHECK(h->ws_out.reserve(out_bytes));
+  const uint8_t* d_in = in_host ? h->ws_in.as<uint8_t>() : in;
+  uint8_t* d_out = out_host ? h->ws_out.as<uint8_t>() : reinterpret_cast<uint8_t*>(out);
+
+  // Host buffers: split the batch into chunks of >= ~4 MP and pipeline H2D(i+1) | conv stack(i) | D2H(i-1) on three
+  // streams (pinned host memory makes the copies truly asynchronous).  Device buffers: one chunk on the caller's stream.
+  int per_chunk = n;
+  if ((in_host || out_host) && n > 1) per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (4u << 20) / std::max<size_t>(px_img, 1)));
+  const int chunks = (n + per_chunk - 1) / per_chunk;
+  if (chunks > 1) {
+    if (!h->s_h2d) BF_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    if (!h->s_d2h) BF_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    while ((int)h->ev_pool.size() < 2 * chunks + 1) {
+      cudaEvent_t e;
+      BF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->ev_pool.push_back(e);
+    }
+    // the copy streams start after whatever the caller queued on `st`
+    BF_CUDA(cudaEventRecord(h->ev_pool[2 * chunks], st));
+    BF_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_pool[2 * chunks], 0));
+  }
+  BF_CUDA(cudaEventRecord(h->ev0, st));
+  for (int c = 0; c < chunks; ++c) {
+    const int i0 = c * per_chunk, nc = std::min(per_chunk, n - i0);
+    const size_t off_in = (size_t)i0 * px_img * 3, off_out = off_in * osz;
+    const size_t cin = (size_t)nc * px_img * 3, cout = cin * osz;
+    if (in_host) {
+      cudaStream_t sc = chunks > 1 ? h->s_h2d : st;
+      BF_CUDA(cudaMemcpyAsync(h->ws_in.as<uint8_t>() + off_in, in + off_in, cin, cudaMemcpyHostToDevice, sc));
+      if (chunks > 1) {
+        BF_CUDA(cudaEventRecord(h->ev_pool[2 * c], sc));
+        BF_CUDA(cudaStreamWaitEvent(st, h->ev_pool[2 * c], 0));
+      }
+    }
+    const Extent e = make_extent(h, nc, height, width, flags);
+    BF_CHECK(run_stack(h, d_in + off_in, d_out + off_out, out_u8, e, precision, st));
+    if (out_host) {
+      cudaStream_t sc = chunks > 1 ? h->s_d2h : st;
+      if (chunks > 1) {
+        BF_CUDA(cudaEventRecord(h->ev_pool[2 * c + 1], st));
+        BF_CUDA(cudaStreamWaitEvent(sc, h->ev_pool[2 * c + 1], 0));
+      }
+      BF_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + off_out, h->ws_out.as<uint8_t>() + off_out, cout, cudaMemcpyDeviceToHost, sc));
+    }
   }
   BF_CUDA(cudaEventRecord(h->ev1, st));
   h->ev_valid = true;
-
-  if (!(flags & BFCNN_FLAG_OUT_DEVICE)) {
-    BF_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  if (out_host) {
+    if (chunks > 1) BF_CUDA(cudaStreamSynchronize(h->s_d2h));
     BF_CUDA(cudaStreamSynchronize(st));
   }
   return BFCNN_OK;
@@ -192,6 +226,9 @@ void bfcnn_destroy(bfcnn_handle* h) {
   for (auto& b : h->ws_feat) b.release();
   h->ws_train.release(); h->ws_stats.release(); h->ws_grads.release();
   h->adam_m.release(); h->adam_v.release();
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+  if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;

@@ -158,3 +158,19 @@ def test_row_strips_reassemble_bit_exact(native_lib, pad_pow2):
         assert [p[0] for p in parts][1:] == [p[1] for p in parts][:-1]
         assert np.array_equal(np.concatenate([p[2] for p in parts], axis=1), whole)
     m.close()
+
+
+def test_host_pipeline_chunks_match_device_path(native_lib):
+    """Host buffers are pipelined H2D | conv stack | D2H in chunks of >= ~4 MP (api.cu); the result must be the
+    same bits as the single-shot device-buffer path, for uint8 and float outputs."""
+    import torch
+    m = _model(6, precision="f16", pad_pow2=False)
+    x = np.random.default_rng(9).integers(0, 256, size=(5, 1100, 1300, 3), dtype=np.uint8)   # 1.43 MP each -> 3 chunks
+    xd = torch.from_numpy(x).cuda()
+    assert np.array_equal(m(x), m(xd).cpu().numpy())
+    assert np.array_equal(m(x, return_float=True), m(xd, return_float=True).cpu().numpy())
+    xp = torch.from_numpy(x).pin_memory()
+    out = torch.empty_like(xp).pin_memory()
+    m(xp, out=out)
+    assert np.array_equal(out.numpy(), m(xd).cpu().numpy())
+    m.close()
