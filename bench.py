@@ -33,6 +33,7 @@ N_LAYERS = 18
 FRAME_H, FRAME_W = 2160, 3840
 METRIC = "megapixels/sec denoised"
 UNIT = "MP/s"
+WORKLOAD = f"{MODEL_NAME} inference on synthetic 3840x2160x3 uint8 frames (BASELINE configs[2])"
 
 
 def load_peaks():
@@ -98,6 +99,7 @@ def cpu_reference_mp_s(crop: int, reps: int, frames_seed: int = 0):
     """Oracle torch-CPU fp32 restatement on a crop x crop sample of frame 0 (kind 'port')."""
     import numpy as np
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)
     from blind_image_denoising_b200 import Arch, synthetic_variables
     from oracle import bfcnn_oracle as O
     v = synthetic_variables(Arch(no_layers=N_LAYERS), 0)
@@ -121,6 +123,7 @@ def run_reference(args):
     crop = args.cpu_crop
     import numpy as np
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     from blind_image_denoising_b200 import Arch, synthetic_variables
     from oracle import bfcnn_oracle as O
     v = synthetic_variables(Arch(no_layers=N_LAYERS), 0)
@@ -138,14 +141,24 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": mp_s, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{MODEL_NAME} inference, 3840x2160x3 uint8 frames", "no_layers": N_LAYERS,
+        "config": {"workload": WORKLOAD, "no_layers": N_LAYERS,
                    "note": "reference TF path is not installable (tensorflow==2.13.1, no wheel for py3.12, no network); "
                            "this is the oracle's CPU restatement of it"},
         "cpu_baseline": {"value": mp_s, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": mp_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
+
+
+def _emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else a library prints to fd 1 (e.g. NCCL's version
+    banner) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -329,7 +342,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms"] / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"{MODEL_NAME} inference on synthetic 3840x2160x3 uint8 frames (BASELINE configs[2])",
+            "config": {"workload": WORKLOAD,
                        "frames_per_gpu_per_step": F, "no_layers": N_LAYERS, "weights": "synthetic seed 0 (reference ships none, SURVEY F2)",
                        "parity": parity[args.precision], "pad_pow2": False,
                        "l2": f"working set {F * 24.9 * 2 + F * 8.29 * 32 * 2:.0f} MB per step > 126 MB L2 (no flush needed)",
@@ -343,7 +356,7 @@ def main():
             "modes": modes,
             "training": training,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
