@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "bfcnn_abi_version", "bfcnn_last_error", "bfcnn_device_count", "bfcnn_num_weights",
     "bfcnn_num_trainable", "bfcnn_create", "bfcnn_destroy", "bfcnn_set_weights",
     "bfcnn_get_weights", "bfcnn_denoise_u8", "bfcnn_denoise_f32", "bfcnn_launch_count",
-    "bfcnn_last_stack_ms", "bfcnn_corrupt", "bfcnn_loss", "bfcnn_train_step", "bfcnn_adam_step",
+    "bfcnn_last_stack_ms", "bfcnn_corrupt", "bfcnn_loss", "bfcnn_train_step", "bfcnn_adam_step", "bfcnn_conv3x3", "bfcnn_set_train_engine",
 ]
 
 
@@ -100,6 +100,10 @@ def load_library() -> ctypes.CDLL:
     lib.bfcnn_train_step.argtypes = [H, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(LossCfg),
                                      c_void_p, POINTER(c_float), c_int, c_void_p]
     lib.bfcnn_train_step.restype = c_int
+    lib.bfcnn_set_train_engine.argtypes = [H, c_int]
+    lib.bfcnn_set_train_engine.restype = c_int
+    lib.bfcnn_conv3x3.argtypes = [H, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.bfcnn_conv3x3.restype = c_int
     lib.bfcnn_adam_step.argtypes = [H, c_void_p, c_float, POINTER(AdamCfg), c_int64, c_void_p]
     lib.bfcnn_adam_step.restype = c_int
     if lib.bfcnn_abi_version() != 1:

@@ -317,6 +317,28 @@ int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, in
                         (cudaStream_t)stream);
 }
 
+int bfcnn_set_train_engine(bfcnn_handle* h, int engine) {
+  BF_REQUIRE(h != nullptr, "handle is NULL");
+  BF_REQUIRE(engine == 0 || engine == 1, "engine must be 0 (FP32 FFMA) or 1 (tensor cores, fp16 hi/lo split)");
+  h->train_engine = engine;
+  return BFCNN_OK;
+}
+
+int bfcnn_conv3x3(bfcnn_handle* h, const float* in, const float* weights, float* out, int n, int height, int width,
+                  int engine, int relu, void* stream) {
+  BF_REQUIRE(h != nullptr && in != nullptr && weights != nullptr && out != nullptr, "NULL argument");
+  BF_CHECK(check_images(n, height, width));
+  if ((size_t)n * height * width == 0) return BFCNN_OK;
+  BF_CUDA(cudaSetDevice(h->device));
+  const Extent e{n, height, width, height, width};
+  cudaStream_t st = (cudaStream_t)stream;
+  const ConvEpi epi = relu ? CONV_RELU : CONV_PLAIN;
+  if (engine == 0) return launch_conv3x3_f32(h, in, out, weights, nullptr, nullptr, nullptr, epi, e, st);
+  if (engine == 1) return launch_conv3x3_x3(h, in, out, weights, nullptr, nullptr, epi, e, 64.0f, st);
+  set_error("invalid argument: engine must be 0 (FP32 FFMA) or 1 (tensor cores, fp16 hi/lo split)");
+  return BFCNN_ERR_INVALID_ARGUMENT;
+}
+
 int bfcnn_adam_step(bfcnn_handle* h, const float* flat_grads, float grad_scale, const bfcnn_adam_cfg* cfg,
                     int64_t step, void* stream) {
   BF_REQUIRE(h != nullptr && cfg != nullptr && flat_grads != nullptr, "NULL argument");

@@ -1,0 +1,221 @@
+// conv_x3.cu -- the training-step 3x3 16->16 convolutions on tensor cores at FP32-grade accuracy.
+//
+// Same contract as conv3x3_c16_kernel (conv_f32.cu): fp32 NHWC16 in, fp32 NHWC16 out, zero "same" padding, fused
+// epilogue (ReLU / residual add / per-channel batch statistics / ReLU-mask for the backward pass).  The arithmetic is
+// the F16X3 scheme of fused_f16.cu: activations and weights are split into fp16 hi + lo parts on the fly and every tap
+// issues hi*hi + lo*hi + hi*lo on mma.sync.m16n8k16 with fp32 accumulation -- error ~2^-21 relative, i.e. FP32-grade,
+// which is what the gradient parity gate (cosine >= 0.9999, max error <= 1e-3 of the gradient scale) needs.
+// Used for the forward convs (backbone_blocks.py:167-246 in training mode) and for the dgrad convs of
+// train_loop.py:302-304 (a correlation of dOut with the flipped, transposed kernel).
+#include "kernels.cuh"
+
+namespace bfcnn {
+namespace x3 {
+
+constexpr int RW = 64;           // region width in pixels == shared-memory row pitch (62 output columns + halo)
+constexpr int NT = 256;          // 8 warps: 4 column strips x 2 row bands
+constexpr int SLACK_PX = 8;
+constexpr int PX_BYTES = 32;     // 16 channels fp16
+constexpr float W_SCALE = 256.f;  // weights ~0.1: the low part of the split would be an fp16 subnormal without it
+constexpr int TH_MAX = 25;       // rows per tile: 2 CTAs per SM (107 KB each) overlap each other's load and math
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint2 b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+// the two 16-byte halves of a pixel are XOR-swizzled by bit 2 of the pixel index (conflict-free ldmatrix rows)
+__device__ __forceinline__ int px_off(int pix, int half) { return pix * PX_BYTES + ((half ^ ((pix >> 2) & 1)) << 4); }
+
+__device__ __forceinline__ void split_store(uint32_t hi_addr, uint32_t lo_addr, const float4& a, const float4& b) {
+  uint4 hi, lo;
+  hi.x = pack_h2(a.x, a.y); hi.y = pack_h2(a.z, a.w); hi.z = pack_h2(b.x, b.y); hi.w = pack_h2(b.z, b.w);
+  float2 f;
+  f = unpack_h2(hi.x); lo.x = pack_h2(a.x - f.x, a.y - f.y);
+  f = unpack_h2(hi.y); lo.y = pack_h2(a.z - f.x, a.w - f.y);
+  f = unpack_h2(hi.z); lo.z = pack_h2(b.x - f.x, b.y - f.y);
+  f = unpack_h2(hi.w); lo.w = pack_h2(b.z - f.x, b.w - f.y);
+  sts128(hi_addr, hi);
+  sts128(lo_addr, lo);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NT, 2)
+conv3x3_x3_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w /*[9][16 cin][16 cout]*/,
+                  const float* __restrict__ res, double* __restrict__ stats, int h, int wd, int th, int tiles_x, int tiles_y,
+                  float in_scale, float out_scale) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float s_stat[2 * C];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rh = th + 2;
+  const int plane_bytes = (rh * RW + 2 * SLACK_PX) * PX_BYTES;
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t sH = s0 + SLACK_PX * PX_BYTES, sL = s0 + plane_bytes + SLACK_PX * PX_BYTES;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int oy = ty * th - 1, ox = tx * (RW - 2) - 1;
+  if (EPI == CONV_STATS && tid < 2 * C) s_stat[tid] = 0.f;
+
+  // ---- stage the region: fp32 -> fp16 hi + lo planes, zero outside the image ("same" padding)
+  const float* in_b = in + (long long)b * h * wd * C;
+  for (int i = tid; i < rh * RW * 2; i += NT) {
+    const int hf = i & 1, pix = i >> 1;
+    const int r = pix / RW, c = pix % RW;
+    const int gy = oy + r, gx = ox + c;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a;
+    if (gy >= 0 && gy < h && gx >= 0 && gx < wd) {
+      const float4* s = reinterpret_cast<const float4*>(in_b + ((long long)gy * wd + gx) * C + 8 * hf);
+      a = s[0]; bq = s[1];
+      // power-of-two pre-scale (exact): keeps the LOW part of the split out of the fp16 subnormal range (activations ~0.1
+      // have low parts ~2e-5 < 6.1e-5; back-propagated gradients are ~1e-6 to begin with)
+      a.x *= in_scale; a.y *= in_scale; a.z *= in_scale; a.w *= in_scale;
+      bq.x *= in_scale; bq.y *= in_scale; bq.z *= in_scale; bq.w *= in_scale;
+    }
+    split_store(sH + px_off(pix, hf), sL + px_off(pix, hf), a, bq);
+  }
+  // ---- B fragments (weights) hi / lo: lane holds B[k][n], k = 2q, 2q+1, 2q+8, 2q+9, n = 8*nt + g
+  uint2 Bh[9][2], Bl[9][2];
+  {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float* wp = w + tap * C * C + nt * 8 + g;
+        const float w0 = __ldg(wp + (2 * q) * C) * W_SCALE, w1 = __ldg(wp + (2 * q + 1) * C) * W_SCALE;
+        const float w2 = __ldg(wp + (2 * q + 8) * C) * W_SCALE, w3 = __ldg(wp + (2 * q + 9) * C) * W_SCALE;
+        const uint32_t h01 = pack_h2(w0, w1), h23 = pack_h2(w2, w3);
+        const float2 f01 = unpack_h2(h01), f23 = unpack_h2(h23);
+        Bh[tap][nt] = make_uint2(h01, h23);
+        Bl[tap][nt] = make_uint2(pack_h2(w0 - f01.x, w1 - f01.y), pack_h2(w2 - f23.x, w3 - f23.y));
+      }
+  }
+  __syncthreads();
+
+  const int strip = warp & 3, band = warp >> 2;
+  const int x0 = strip * 16;
+  const int r_begin = 1 + (th * band) / 2, r_end = 1 + (th * (band + 1)) / 2;
+  int aoff[3];
+  {
+    const int i = (lane & 7) + ((lane >> 3) & 1) * 8, hf = lane >> 4;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) aoff[dx] = px_off(x0 + dx - 1 + i, hf);
+  }
+  const int q = lane & 3;
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = r_begin; r < r_end; ++r) {
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int rowb = (r + dy - 1) * (RW * PX_BYTES);
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        uint32_t ah[4], al[4];
+        ldsm4(ah, sH + rowb + aoff[dx]);
+        ldsm4(al, sL + rowb + aoff[dx]);
+        const int tap = dy * 3 + dx;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          mma16816(acc[nt], al, Bh[tap][nt]);
+          mma16816(acc[nt], ah, Bl[tap][nt]);
+          mma16816(acc[nt], ah, Bh[tap][nt]);
+        }
+      }
+    }
+    // ---- epilogue: acc[nt][0..1] -> pixel x0 + lane/4, acc[nt][2..3] -> pixel x0 + lane/4 + 8; channels 8*nt + 2q, +1
+    const int gy = oy + r;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = x0 + (lane >> 2) + 8 * j;
+      const int gx = ox + c;
+      if (c < 1 || c >= RW - 1 || gx >= wd || gy >= h) continue;
+      const long long o = (((long long)b * h + gy) * wd + gx) * C;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        float2 v = make_float2(acc[nt][2 * j] * out_scale, acc[nt][2 * j + 1] * out_scale);
+        const long long oc = o + nt * 8 + 2 * q;
+        if (EPI == CONV_STATS) {
+          ssum[2 * nt] += v.x; ssum[2 * nt + 1] += v.y;
+          ssq[2 * nt] += v.x * v.x; ssq[2 * nt + 1] += v.y * v.y;
+        }
+        if (EPI == CONV_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+        if (EPI == CONV_RESIDUAL) {
+          const float2 rv = *reinterpret_cast<const float2*>(res + oc);
+          v.x += rv.x; v.y += rv.y;
+        }
+        if (EPI == CONV_MASK) {   // ReLU backward: pass the gradient where the saved activation is > 0
+          const float2 mv = *reinterpret_cast<const float2*>(res + oc);
+          v.x = mv.x > 0.f ? v.x : 0.f; v.y = mv.y > 0.f ? v.y : 0.f;
+        }
+        *reinterpret_cast<float2*>(out + oc) = v;
+      }
+    }
+  }
+  if (EPI == CONV_STATS) {
+    // lanes that share q own the same 4 channels (2q, 2q+1, 8+2q, 8+2q+1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a = ssum[k], s2 = ssq[k];
+#pragma unroll
+      for (int s = 4; s < 32; s <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, s); s2 += __shfl_xor_sync(0xffffffffu, s2, s); }
+      if (lane < 4) {
+        const int ch = (k >> 1) * 8 + 2 * q + (k & 1);
+        atomicAdd(&s_stat[ch], a);
+        atomicAdd(&s_stat[C + ch], s2);
+      }
+    }
+    __syncthreads();
+    if (tid < 2 * C) atomicAdd(&stats[tid], (double)s_stat[tid]);
+  }
+}
+
+}  // namespace x3
+
+int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
+                      ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st) {
+  using namespace x3;
+  const int tiles_y = (e.he + TH_MAX - 1) / TH_MAX;
+  const int th = (e.he + tiles_y - 1) / tiles_y;
+  const int tiles_x = (e.we + (RW - 2) - 1) / (RW - 2);
+  const size_t smem = (size_t)2 * ((th + 2) * RW + 2 * SLACK_PX) * PX_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int mx = 2 * ((TH_MAX + 2) * RW + 2 * SLACK_PX) * PX_BYTES;
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_x3_kernel<CONV_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_x3_kernel<CONV_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_x3_kernel<CONV_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_x3_kernel<CONV_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_x3_kernel<CONV_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    attr_set = true;
+  }
+  const long long grid = (long long)tiles_x * tiles_y * e.n;
+  BF_REQUIRE(grid < (1ll << 31), "too many tiles");
+  BF_REQUIRE(in_scale > 0.f, "in_scale must be a positive power of two");
+  const unsigned g = (unsigned)grid;
+  switch (epi) {
+    case CONV_PLAIN: conv3x3_x3_kernel<CONV_PLAIN><<<g, NT, smem, st>>>(in, out, w, res, stats, e.he, e.we, th, tiles_x, tiles_y, in_scale, 1.0f / (in_scale * W_SCALE)); break;
+    case CONV_RELU: conv3x3_x3_kernel<CONV_RELU><<<g, NT, smem, st>>>(in, out, w, res, stats, e.he, e.we, th, tiles_x, tiles_y, in_scale, 1.0f / (in_scale * W_SCALE)); break;
+    case CONV_RESIDUAL: conv3x3_x3_kernel<CONV_RESIDUAL><<<g, NT, smem, st>>>(in, out, w, res, stats, e.he, e.we, th, tiles_x, tiles_y, in_scale, 1.0f / (in_scale * W_SCALE)); break;
+    case CONV_STATS: conv3x3_x3_kernel<CONV_STATS><<<g, NT, smem, st>>>(in, out, w, res, stats, e.he, e.we, th, tiles_x, tiles_y, in_scale, 1.0f / (in_scale * W_SCALE)); break;
+    case CONV_MASK: conv3x3_x3_kernel<CONV_MASK><<<g, NT, smem, st>>>(in, out, w, res, stats, e.he, e.we, th, tiles_x, tiles_y, in_scale, 1.0f / (in_scale * W_SCALE)); break;
+    default: set_error("unsupported conv epilogue"); return BFCNN_ERR_INTERNAL;
+  }
+  h->launches++;
+  BF_CUDA(cudaGetLastError());
+  return BFCNN_OK;
+}
+
+}  // namespace bfcnn

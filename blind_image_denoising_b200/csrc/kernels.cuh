@@ -21,6 +21,10 @@ int launch_conv3x3_f32(bfcnn_handle* h, const float* in, float* out, const float
 int launch_head(bfcnn_handle* h, const float* feat, void* out, bool out_u8, const float* wh,
                 const Extent& e, cudaStream_t st);
 
+// ---- conv_x3.cu: the same layer contract on tensor cores, fp16 hi/lo split (FP32-grade); training fwd + dgrad
+int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
+                      ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st);
+
 // ---- fused_f16.cu: the fused tensor-core stack (F16 / F16X3)
 int run_fused_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                     int precision, cudaStream_t st);

@@ -829,11 +829,22 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   const int ew_blocks = (int)std::min<long long>((n4 + 255) / 256, (long long)h->sm_count * 8);
   const int ew_blocks4 = std::max(4, ew_blocks & ~3);  // multiple of 4 blocks*256 keeps (i & 3) fixed per thread
 
+  // conv engine: tensor cores with the fp16 hi/lo split (FP32-grade, conv_x3.cu) unless BFCNN_TRAIN_CONV=fp32
+  // conv engine: tensor cores with the fp16 hi/lo split (conv_x3.cu; default) or FP32 FFMA (bfcnn_set_train_engine)
+  const int x3_mode = h->train_engine == 1 ? 3 : 0;
+  // back-propagated gradients are ~255/(n*h*w*3) in magnitude: a power-of-two pre-scale brings them to O(1) for the split
+  const float gscale = exp2f(floorf(log2f(fmaxf((float)(npx * 3) / 256.f, 1.f))));
+  auto conv = [&](const float* in, float* out, const float* wts, const float* res, double* stats, ConvEpi epi) {
+    const bool backward = (epi == CONV_MASK || epi == CONV_RESIDUAL);
+    const bool use_x3 = (x3_mode & (backward ? 2 : 1)) != 0;
+    return use_x3 ? launch_conv3x3_x3(h, in, out, wts, res, stats, epi, e, backward ? gscale * 64.0f : 64.0f, st)
+                  : launch_conv3x3_f32(h, in, out, wts, nullptr, res, stats, epi, e, st);
+  };
   // ---- forward (training mode)
   BF_CHECK(launch_base_conv(h, noisy, false, Xm(0), vars + L.base, e, st));
   for (int i = 0; i < N; ++i) {
-    BF_CHECK(launch_conv3x3_f32(h, Xm(i), Tm(i), vars + L.wa[i], nullptr, nullptr, nullptr, CONV_RELU, e, st));
-    BF_CHECK(launch_conv3x3_f32(h, Tm(i), Um(i), vars + L.wb[i], nullptr, nullptr, bn_stats + (size_t)i * 2 * C, CONV_STATS, e, st));
+    BF_CHECK(conv(Xm(i), Tm(i), vars + L.wa[i], nullptr, nullptr, CONV_RELU));
+    BF_CHECK(conv(Tm(i), Um(i), vars + L.wb[i], nullptr, bn_stats + (size_t)i * 2 * C, CONV_STATS));
     bn_finalize_kernel<<<1, 32, 0, st>>>(bn_stats + (size_t)i * 2 * C, cnt, h->arch.bn_epsilon, h->arch.bn_momentum, vars,
                                          (long long)L.gamma[i], (long long)L.mean[i], (long long)L.var[i],
                                          bn_params + (size_t)i * 4 * C, update_moving);
@@ -865,11 +876,11 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
     bn_bwd_apply_kernel<<<ew_blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dX), reinterpret_cast<const float4*>(Um(i)), bnp, bs, cnt,
                                                    reinterpret_cast<float4*>(dU), flat_grads + L.t_gamma[i], n4);
     // conv_b: dT = dgrad(dU) masked by ReLU ; dWb = T (x) dU
-    BF_CHECK(launch_conv3x3_f32(h, dU, dT, dgrad_w + (size_t)(2 * i + 1) * 9 * C * C, nullptr, Tm(i), nullptr, CONV_MASK, e, st));
+    BF_CHECK(conv(dU, dT, dgrad_w + (size_t)(2 * i + 1) * 9 * C * C, Tm(i), nullptr, CONV_MASK));
     wgrad3x3_kernel<<<wg_blocks, 256, WG_SMEM, st>>>(Tm(i), dU, partial, n, height, width, tiles_x, tiles_y);
     wgrad_reduce_kernel<<<9, 256, 0, st>>>(partial, wg_blocks, 2304, vars + L.wb[i], reg1, flat_grads + L.t_wb[i]);
     // conv_a: dX_i = dgrad(dT) + dX_{i+1} ; dWa = X_i (x) dT
-    BF_CHECK(launch_conv3x3_f32(h, dT, dXn, dgrad_w + (size_t)(2 * i) * 9 * C * C, nullptr, dX, nullptr, CONV_RESIDUAL, e, st));
+    BF_CHECK(conv(dT, dXn, dgrad_w + (size_t)(2 * i) * 9 * C * C, dX, nullptr, CONV_RESIDUAL));
     wgrad3x3_kernel<<<wg_blocks, 256, WG_SMEM, st>>>(Xm(i), dT, partial, n, height, width, tiles_x, tiles_y);
     wgrad_reduce_kernel<<<9, 256, 0, st>>>(partial, wg_blocks, 2304, vars + L.wa[i], reg1, flat_grads + L.t_wa[i]);
     h->launches += 6;

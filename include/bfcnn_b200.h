@@ -154,6 +154,18 @@ int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, in
                      int width, const bfcnn_loss_cfg* cfg, float* flat_grads, float* losses4,
                      int update_moving, void* stream);
 
+/* Engine of the 3x3 convs inside bfcnn_train_step: 1 (default) = tensor cores with the fp16 hi/lo split (3 MMAs per
+ * product, conv error ~4e-6 on O(1) data, i.e. FP32-grade), 0 = FP32 FFMA (conv error ~1e-6).  The two differ only in
+ * rounding; on tiny batches a single ReLU whose pre-activation is ~1e-6 can switch and move one pixel's worth of
+ * gradient (tests/test_training_gpu.py states the gates per engine). */
+int bfcnn_set_train_engine(bfcnn_handle* h, int engine);
+
+/* One 3x3 16->16 "same" convolution layer (keras Conv2D of utilities.py:195-196, no bias), device float32 NHWC16
+ * in/out, weights [3,3,16,16] HWIO on the device.  engine 0 = FP32 FFMA, 1 = tensor cores with the fp16 hi/lo split
+ * (the engines of the training step); exposed so that the layer kernels can be tested in isolation. */
+int bfcnn_conv3x3(bfcnn_handle* h, const float* in, const float* weights, float* out, int n, int height, int width,
+                  int engine, int relu, void* stream);
+
 /* replaces: optimizer.apply_gradients with keras Adam + global_clipnorm
  * (bfcnn/optimizer.py:145-224, bfcnn/train_loop.py:314-321, 421-434).  flat_grads is
  * the (all-reduced, averaged) device gradient; step counts from 1. */
