@@ -182,6 +182,132 @@ conv3x3_x3_kernel(const float* __restrict__ in, float* __restrict__ out, const f
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// wgrad on tensor cores: dW[tap][ci][co] = sum_p A[p + tap][ci] * G[p][co]  (zero padding), fp16 hi/lo split (3 MMAs).
+// Per tap this is a [16 ci x 16 co] GEMM whose K dimension runs over pixels: A^T and G come straight from the NHWC16
+// tiles with ldmatrix.trans (rows = pixels), 16 pixels of one image row per K step.  Every warp keeps the full
+// [9][16][16] partial in registers (72 accumulators per lane) over all the tiles its CTA visits (persistent grid); the
+// warps are summed in fixed order through shared memory and the per-CTA partials by wgrad_reduce_kernel: deterministic.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int WG_TH = 12;        // tile rows (two 108 KB CTAs per SM)
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+__global__ void __launch_bounds__(NT, 2)
+wgrad3x3_x3_kernel(const float* __restrict__ A, const float* __restrict__ G, float* __restrict__ partial, int n, int h, int wd,
+                   int tiles_x, int tiles_y, float g_scale, float out_scale) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int RH = WG_TH + 2;
+  constexpr int A_PLANE = (RH * RW + 2 * SLACK_PX) * PX_BYTES, G_PLANE = (WG_TH * RW + 2 * SLACK_PX) * PX_BYTES;
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t aH = s0 + SLACK_PX * PX_BYTES, aL = aH + A_PLANE;
+  const uint32_t gH = s0 + 2 * A_PLANE + SLACK_PX * PX_BYTES, gL = gH + G_PLANE;
+  float acc[9][2][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[t][nt][k] = 0.f;
+  // ldmatrix.trans row addresses: lanes 0-7 / 8-15 / 16-23 / 24-31 give the rows of the four 8x8 matrices
+  //   (pixels 0-7, ch 0-7), (pixels 0-7, ch 8-15), (pixels 8-15, ch 0-7), (pixels 8-15, ch 8-15)
+  const int lp = (lane & 7) + ((lane >> 4) & 1) * 8, lh = (lane >> 3) & 1;
+  // for the B operand (G) the x4 order is (px 0-7, co 0-7), (px 8-15, co 0-7), (px 0-7, co 8-15), (px 8-15, co 8-15)
+  const int gp = (lane & 7) + ((lane >> 3) & 1) * 8, gh = (lane >> 4) & 1;
+
+  // the tap shifts read one pixel before / after the activation planes: those products meet a zero gradient, but
+  // 0 * (NaN bit pattern left in shared memory) would still poison the sum, so the slack is zeroed once
+  if (tid < 2 * 2 * SLACK_PX * 2) {
+    const int pl = tid / (4 * SLACK_PX), k = tid % (4 * SLACK_PX);   // 16-byte chunks: 2 per pixel
+    const uint32_t base = s0 + pl * A_PLANE;
+    const uint32_t off = k < 2 * SLACK_PX ? (uint32_t)k * 16u : (uint32_t)(A_PLANE - (4 * SLACK_PX - k) * 16);
+    sts128(base + off, make_uint4(0u, 0u, 0u, 0u));
+  }
+  const int ntiles = tiles_x * tiles_y * n;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const int oy = ty * WG_TH - 1, ox = tx * (RW - 2) - 1;
+    const float* a_b = A + (long long)b * h * wd * C;
+    const float* g_b = G + (long long)b * h * wd * C;
+    __syncthreads();
+    for (int i = tid; i < RH * RW * 2; i += NT) {      // activations with the one-pixel halo
+      const int hf = i & 1, pix = i >> 1;
+      const int r = pix / RW, c = pix % RW;
+      const int gy = oy + r, gx = ox + c;
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+      if (gy >= 0 && gy < h && gx >= 0 && gx < wd) {
+        const float4* s = reinterpret_cast<const float4*>(a_b + ((long long)gy * wd + gx) * C + 8 * hf);
+        u = s[0]; v = s[1];
+        u.x *= 64.f; u.y *= 64.f; u.z *= 64.f; u.w *= 64.f; v.x *= 64.f; v.y *= 64.f; v.z *= 64.f; v.w *= 64.f;
+      }
+      split_store(aH + px_off(pix, hf), aL + px_off(pix, hf), u, v);
+    }
+    for (int i = tid; i < WG_TH * RW * 2; i += NT) {   // output gradients: zero on the halo columns and outside the image
+      const int hf = i & 1, pix = i >> 1;
+      const int r = pix / RW, c = pix % RW;
+      const int gy = oy + 1 + r, gx = ox + c;
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+      if (c >= 1 && c < RW - 1 && gy < h && gx < wd) {
+        const float4* s = reinterpret_cast<const float4*>(g_b + ((long long)gy * wd + gx) * C + 8 * hf);
+        u = s[0]; v = s[1];
+        u.x *= g_scale; u.y *= g_scale; u.z *= g_scale; u.w *= g_scale; v.x *= g_scale; v.y *= g_scale; v.z *= g_scale; v.w *= g_scale;
+      }
+      split_store(gH + px_off(pix, hf), gL + px_off(pix, hf), u, v);
+    }
+    __syncthreads();
+    for (int r = warp; r < WG_TH; r += NT / 32) {
+#pragma unroll 1
+      for (int ks = 0; ks < RW / 16; ++ks) {
+        uint32_t bh[4], bl[4];
+        const int gpix = r * RW + ks * 16 + gp;
+        ldsm4t(bh, gH + px_off(gpix, gh));
+        ldsm4t(bl, gL + px_off(gpix, gh));
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            uint32_t ah[4], al[4];
+            const int apix = (r + dy) * RW + ks * 16 + dx - 1 + lp;
+            ldsm4t(ah, aH + px_off(apix, lh));
+            ldsm4t(al, aL + px_off(apix, lh));
+            const int t = dy * 3 + dx;
+            // A fragment order of mma (a0: m 0-7 k 0-7, a1: m 8-15 k 0-7, a2: m 0-7 k 8-15, a3: m 8-15 k 8-15) == load order
+            mma16816(acc[t][0], al, make_uint2(bh[0], bh[1]));
+            mma16816(acc[t][0], ah, make_uint2(bl[0], bl[1]));
+            mma16816(acc[t][0], ah, make_uint2(bh[0], bh[1]));
+            mma16816(acc[t][1], al, make_uint2(bh[2], bh[3]));
+            mma16816(acc[t][1], ah, make_uint2(bl[2], bl[3]));
+            mma16816(acc[t][1], ah, make_uint2(bh[2], bh[3]));
+          }
+      }
+    }
+  }
+  // ---- the 8 warps in fixed order through shared memory, then one partial per CTA
+  __syncthreads();
+  float* s_red = reinterpret_cast<float*>(smem);   // [8][2304]
+  {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        float* d = s_red + warp * 2304 + t * C * C + nt * 8 + 2 * q;
+        d[g * C] = acc[t][nt][0]; d[g * C + 1] = acc[t][nt][1];
+        d[(g + 8) * C] = acc[t][nt][2]; d[(g + 8) * C + 1] = acc[t][nt][3];
+      }
+  }
+  __syncthreads();
+  float* dst = partial + (size_t)blockIdx.x * 2304;
+  for (int i = tid; i < 2304; i += NT) {
+    float a = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < NT / 32; ++w8) a += s_red[w8 * 2304 + i];
+    dst[i] = a * out_scale;
+  }
+}
+
 }  // namespace x3
 
 int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
@@ -215,6 +341,30 @@ int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float*
   }
   h->launches++;
   BF_CUDA(cudaGetLastError());
+  return BFCNN_OK;
+}
+
+// dW partials of one 3x3 conv: `partial` receives [returned grid][2304]; g_scale (a power of two) lifts the gradients
+int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, float* partial, int max_parts, const Extent& e,
+                       float g_scale, int* parts_out, cudaStream_t st) {
+  using namespace x3;
+  constexpr int RH = WG_TH + 2;
+  const size_t smem = (size_t)2 * (RH * RW + 2 * SLACK_PX) * PX_BYTES + (size_t)2 * (WG_TH * RW + 2 * SLACK_PX) * PX_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BF_CUDA(cudaFuncSetAttribute((const void*)wgrad3x3_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  static_assert((size_t)8 * 2304 * 4 <= (size_t)2 * ((WG_TH + 2) * RW + 2 * SLACK_PX) * PX_BYTES + (size_t)2 * (WG_TH * RW + 2 * SLACK_PX) * PX_BYTES,
+                "cross-warp reduction buffer does not fit");
+  const int tiles_x = (e.we + (RW - 2) - 1) / (RW - 2), tiles_y = (e.he + WG_TH - 1) / WG_TH;
+  const long long ntiles = (long long)tiles_x * tiles_y * e.n;
+  BF_REQUIRE(ntiles < (1ll << 31), "too many tiles");
+  const int grid = (int)std::min<long long>(ntiles, std::min(max_parts, 2 * h->sm_count));
+  wgrad3x3_x3_kernel<<<grid, NT, smem, st>>>(act, grad, partial, e.n, e.he, e.we, tiles_x, tiles_y, g_scale, 1.0f / (64.f * g_scale));
+  h->launches++;
+  BF_CUDA(cudaGetLastError());
+  *parts_out = grid;
   return BFCNN_OK;
 }
 

@@ -25,6 +25,9 @@ int launch_head(bfcnn_handle* h, const float* feat, void* out, bool out_u8, cons
 int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
                       ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st);
 
+int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, float* partial, int max_parts, const Extent& e,
+                       float g_scale, int* parts_out, cudaStream_t st);
+
 // ---- fused_f16.cu: the fused tensor-core stack (F16 / F16X3)
 int run_fused_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                     int precision, cudaStream_t st);

@@ -868,6 +868,19 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   // ---- backward: residual blocks
   const int tiles_x = (width + WG_W - 1) / WG_W, tiles_y = (height + WG_H - 1) / WG_H;
   const int wg_blocks = std::min(wg_grid, tiles_x * tiles_y * n);
+  // dW = act (x) grad + L1 sub-gradient, engine as for the convs
+  auto wgrad = [&](const float* act, const float* grad, const float* wts, float* out) -> int {
+    int parts = wg_blocks;
+    if (x3_mode) {
+      BF_CHECK(launch_wgrad3x3_x3(h, act, grad, partial, wg_grid, e, gscale * 64.0f, &parts, st));
+    } else {
+      wgrad3x3_kernel<<<wg_blocks, 256, WG_SMEM, st>>>(act, grad, partial, n, height, width, tiles_x, tiles_y);
+      h->launches++;
+    }
+    wgrad_reduce_kernel<<<9, 256, 0, st>>>(partial, parts, 2304, wts, reg1, out);
+    h->launches++;
+    return BFCNN_OK;
+  };
   float* dX = dXa; float* dXn = dXb;
   for (int i = N - 1; i >= 0; --i) {
     const float* bnp = bn_params + (size_t)i * 4 * C;
@@ -877,13 +890,11 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
                                                    reinterpret_cast<float4*>(dU), flat_grads + L.t_gamma[i], n4);
     // conv_b: dT = dgrad(dU) masked by ReLU ; dWb = T (x) dU
     BF_CHECK(conv(dU, dT, dgrad_w + (size_t)(2 * i + 1) * 9 * C * C, Tm(i), nullptr, CONV_MASK));
-    wgrad3x3_kernel<<<wg_blocks, 256, WG_SMEM, st>>>(Tm(i), dU, partial, n, height, width, tiles_x, tiles_y);
-    wgrad_reduce_kernel<<<9, 256, 0, st>>>(partial, wg_blocks, 2304, vars + L.wb[i], reg1, flat_grads + L.t_wb[i]);
+    BF_CHECK(wgrad(Tm(i), dU, vars + L.wb[i], flat_grads + L.t_wb[i]));
     // conv_a: dX_i = dgrad(dT) + dX_{i+1} ; dWa = X_i (x) dT
     BF_CHECK(conv(dT, dXn, dgrad_w + (size_t)(2 * i) * 9 * C * C, dX, nullptr, CONV_RESIDUAL));
-    wgrad3x3_kernel<<<wg_blocks, 256, WG_SMEM, st>>>(Xm(i), dT, partial, n, height, width, tiles_x, tiles_y);
-    wgrad_reduce_kernel<<<9, 256, 0, st>>>(partial, wg_blocks, 2304, vars + L.wa[i], reg1, flat_grads + L.t_wa[i]);
-    h->launches += 6;
+    BF_CHECK(wgrad(Xm(i), dT, vars + L.wa[i], flat_grads + L.t_wa[i]));
+    h->launches += 2;
     std::swap(dX, dXn);
   }
   // ---- backward: base conv (weights only; no gradient into the image)
