@@ -37,7 +37,7 @@ class NoiseCfg(ctypes.Structure):
 
 class LossCfg(ctypes.Structure):
     _fields_ = [("hinge", c_float), ("cutoff", c_float), ("mae_multiplier", c_float),
-                ("mse_multiplier", c_float), ("regularization", c_float)]
+                ("mse_multiplier", c_float), ("regularization", c_float), ("ssim_multiplier", c_float)]
 
 
 class AdamCfg(ctypes.Structure):
@@ -106,7 +106,7 @@ def load_library() -> ctypes.CDLL:
     lib.bfcnn_conv3x3.restype = c_int
     lib.bfcnn_adam_step.argtypes = [H, c_void_p, c_float, POINTER(AdamCfg), c_int64, c_void_p]
     lib.bfcnn_adam_step.restype = c_int
-    if lib.bfcnn_abi_version() != 1:
+    if lib.bfcnn_abi_version() != 2:
         raise ImportError("libbfcnn_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -242,9 +242,9 @@ loss_reduce_kernel(const float* __restrict__ gt, const float* __restrict__ pred,
   block_accumulate<4>(acc, sums + 4 * s, s_red);
 }
 
-// scalars[0..3] = total, mae, rmse, hinged-mae ; coef[0] = c_mae ; coef[1+s] = c_mse[s]
-__global__ void loss_finalize_kernel(const double* __restrict__ sums, int n, int per_sample, bfcnn_loss_cfg cfg,
-                                     float* __restrict__ scalars, float* __restrict__ coef) {
+// scalars[0..4] = total, mae, rmse, hinged-mae, ssim loss ; coef[0] = c_mae ; coef[1+s] = c_mse[s]
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, const double* __restrict__ ssim_sums, double ssim_cnt, int n,
+                                     int per_sample, bfcnn_loss_cfg cfg, float* __restrict__ scalars, float* __restrict__ coef) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double cnt = (double)per_sample;
   double mae = 0, hm = 0, rm = 0, rmh = 0;
@@ -257,10 +257,16 @@ __global__ void loss_finalize_kernel(const double* __restrict__ sums, int n, int
     if (coef) coef[1 + s] = (cfg.mse_multiplier > 0.f) ? (float)((double)cfg.mse_multiplier / ((double)n * cnt * r)) : 0.f;
   }
   mae /= n; hm /= n; rm /= n; rmh /= n;
-  double total = 0;
+  double total = 0, ssim_loss = 0;
   if (cfg.mae_multiplier > 0.f) total += hm * (double)cfg.mae_multiplier;
+  if (cfg.ssim_multiplier > 0.f && ssim_sums) {     // 1 - mean over images of (mean over windows and channels)
+    double m = 0;
+    for (int s = 0; s < n; ++s) m += ssim_sums[s] / ssim_cnt;
+    ssim_loss = 1.0 - m / n;
+    total += ssim_loss * (double)cfg.ssim_multiplier;
+  }
   if (cfg.mse_multiplier > 0.f) total += rmh * (double)cfg.mse_multiplier;
-  scalars[0] = (float)total; scalars[1] = (float)mae; scalars[2] = (float)rm; scalars[3] = (float)hm;
+  scalars[0] = (float)total; scalars[1] = (float)mae; scalars[2] = (float)rm; scalars[3] = (float)hm; scalars[4] = (float)ssim_loss;
   if (coef) coef[0] = (cfg.mae_multiplier > 0.f) ? (float)((double)cfg.mae_multiplier / ((double)n * cnt)) : 0.f;
 }
 
@@ -269,21 +275,164 @@ static int loss_grid_x(const bfcnn_handle* h, int per_sample, int n) {
   return std::max(1, std::min(want, (8 * h->sm_count + n - 1) / n));
 }
 
+// (run_loss is defined after the SSIM kernels)
+// =====================================================================================
+// SSIM term (row N3): tf.image.ssim(gt, pred, filter_size=7, max_val=255) as called by loss.py:217-225
+// (TF 2.13 image_ops_impl._ssim_helper: 7x7 Gaussian (sigma 1.5, softmax-normalised), VALID windows, per channel
+//  luminance * contrast-structure, mean over windows and channels, then loss = 1 - mean over the batch)
+// =====================================================================================
+constexpr int SS_F = 7;                       // filter size
+constexpr int SS_TW = 32, SS_TH = 8;          // windows (forward) / pixels (backward) per CTA
+__constant__ float c_gauss[SS_F * SS_F];
+constexpr float SS_C1 = (0.01f * 255.f) * (0.01f * 255.f), SS_C2 = (0.03f * 255.f) * (0.03f * 255.f);
+
+static int ssim_upload_filter() {
+  static bool done = false;
+  if (done) return BFCNN_OK;
+  double g1[SS_F], sum = 0;
+  for (int i = 0; i < SS_F; ++i) { const double c = i - (SS_F - 1) / 2.0; g1[i] = exp(-0.5 * c * c / (1.5 * 1.5)); sum += g1[i]; }
+  float g2[SS_F * SS_F];
+  for (int i = 0; i < SS_F; ++i)
+    for (int j = 0; j < SS_F; ++j) g2[i * SS_F + j] = (float)((g1[i] / sum) * (g1[j] / sum));   // softmax of the sum of exponents
+  BF_CUDA(cudaMemcpyToSymbol(c_gauss, g2, sizeof(g2)));
+  done = true;
+  return BFCNN_OK;
+}
+
+// per window and channel: S = l*cs and its partial derivatives w.r.t. (mean_y, E[xy], E[x^2+y^2]) -> maps [n][hv][wv][3][3];
+// per-image sum of S -> ssum[n]
+__global__ void __launch_bounds__(SS_TW * SS_TH)
+ssim_forward_kernel(const float* __restrict__ gt, const float* __restrict__ pred, float* __restrict__ maps,
+                    double* __restrict__ ssum, int h, int w, int hv, int wv) {
+  __shared__ float s_x[(SS_TH + SS_F - 1) * (SS_TW + SS_F - 1) * 3];
+  __shared__ float s_y[(SS_TH + SS_F - 1) * (SS_TW + SS_F - 1) * 3];
+  __shared__ float s_red[1];
+  constexpr int PW = SS_TW + SS_F - 1, PH = SS_TH + SS_F - 1;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * SS_TW, y0 = blockIdx.y * SS_TH, b = blockIdx.z;
+  const float* gb = gt + (size_t)b * h * w * 3;
+  const float* pb = pred + (size_t)b * h * w * 3;
+  for (int i = tid; i < PH * PW * 3; i += SS_TW * SS_TH) {
+    const int c = i % 3, p = i / 3;
+    const int lx = p % PW, ly = p / PW;
+    const int gx = x0 + lx, gy = y0 + ly;
+    float xv = 0.f, yv = 0.f;
+    if (gx < w && gy < h) { xv = gb[((size_t)gy * w + gx) * 3 + c]; yv = pb[((size_t)gy * w + gx) * 3 + c]; }
+    s_x[i] = xv; s_y[i] = yv;
+  }
+  __syncthreads();
+  const int lx = tid % SS_TW, ly = tid / SS_TW;
+  const int wx = x0 + lx, wy = y0 + ly;
+  float acc = 0.f;
+  if (wx < wv && wy < hv) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float mx = 0.f, my = 0.f, exy = 0.f, e2 = 0.f;
+      for (int dy = 0; dy < SS_F; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < SS_F; ++dx) {
+          const float g = c_gauss[dy * SS_F + dx];
+          const int o = ((ly + dy) * PW + lx + dx) * 3 + c;
+          const float xv = s_x[o], yv = s_y[o];
+          mx = fmaf(g, xv, mx); my = fmaf(g, yv, my);
+          exy = fmaf(g, xv * yv, exy); e2 = fmaf(g, xv * xv + yv * yv, e2);
+        }
+      const float num0 = 2.f * mx * my, den0 = mx * mx + my * my;
+      const float lden = den0 + SS_C1, l = (num0 + SS_C1) / lden;
+      const float Nn = 2.f * exy - num0 + SS_C2, D = e2 - den0 + SS_C2;
+      const float cs = Nn / D;
+      acc += l * cs;
+      const float dl_dmy = (2.f * mx * lden - (num0 + SS_C1) * 2.f * my) / (lden * lden);
+      const float dcs_dmy = (-2.f * mx * D + 2.f * my * Nn) / (D * D);
+      float* m = maps + ((((size_t)b * hv + wy) * wv + wx) * 3 + c) * 3;
+      m[0] = cs * dl_dmy + l * dcs_dmy;     // dS/d mean_y
+      m[1] = l * 2.f / D;                   // dS/d E[xy]
+      m[2] = -l * Nn / (D * D);             // dS/d E[x^2 + y^2]
+    }
+  }
+  if (tid == 0) s_red[0] = 0.f;
+  __syncthreads();
+  const float wsum = warp_sum(acc);
+  if ((tid & 31) == 0) atomicAdd(&s_red[0], wsum);
+  __syncthreads();
+  if (tid == 0) atomicAdd(&ssum[b], (double)s_red[0]);
+}
+
+// dpred[p][c] = coef * sum_{windows containing p} g * (dS/dmy + dS/dExy * x_p + dS/dE2 * 2 y_p)
+__global__ void __launch_bounds__(SS_TW * SS_TH)
+ssim_backward_kernel(const float* __restrict__ gt, const float* __restrict__ pred, const float* __restrict__ maps,
+                     float* __restrict__ dpred, int h, int w, int hv, int wv, float coef) {
+  __shared__ float s_m[(SS_TH + SS_F - 1) * (SS_TW + SS_F - 1) * 9];
+  constexpr int PW = SS_TW + SS_F - 1, PH = SS_TH + SS_F - 1;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * SS_TW, y0 = blockIdx.y * SS_TH, b = blockIdx.z;
+  // windows (wy, wx) with wy in [y - 6, y], wx in [x - 6, x]: tile origin (y0 - 6, x0 - 6)
+  for (int i = tid; i < PH * PW * 9; i += SS_TW * SS_TH) {
+    const int k = i % 9, p = i / 9;
+    const int lx = p % PW, ly = p / PW;
+    const int wx = x0 + lx - (SS_F - 1), wy = y0 + ly - (SS_F - 1);
+    float v = 0.f;
+    if (wx >= 0 && wx < wv && wy >= 0 && wy < hv) v = maps[(((size_t)b * hv + wy) * wv + wx) * 9 + k];
+    s_m[i] = v;
+  }
+  __syncthreads();
+  const int lx = tid % SS_TW, ly = tid / SS_TW;
+  const int gx = x0 + lx, gy = y0 + ly;
+  if (gx >= w || gy >= h) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float sa = 0.f, sb = 0.f, sc = 0.f;
+    for (int dy = 0; dy < SS_F; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < SS_F; ++dx) {
+        // pixel p sits at offset (dy, dx) inside window (gy - dy, gx - dx)
+        const float g = c_gauss[dy * SS_F + dx];
+        const float* m = s_m + (((ly + (SS_F - 1) - dy) * PW + lx + (SS_F - 1) - dx) * 3 + c) * 3;
+        sa = fmaf(g, m[0], sa); sb = fmaf(g, m[1], sb); sc = fmaf(g, m[2], sc);
+      }
+    const size_t o = (((size_t)b * h + gy) * w + gx) * 3 + c;
+    dpred[o] = coef * (sa + sb * gt[o] + sc * 2.f * pred[o]);
+  }
+}
+
+// SSIM forward: per-window derivative maps + per-image sums (ssim_sums[n] must be zeroed by the caller)
+static int run_ssim(bfcnn_handle* h, const float* gt, const float* pred, int n, int height, int width, float* maps,
+                    double* ssim_sums, cudaStream_t st) {
+  BF_REQUIRE(height >= SS_F && width >= SS_F, "SSIM needs height and width >= 7 (tf.image.ssim, filter_size=7)");
+  BF_CHECK(ssim_upload_filter());
+  const int hv = height - SS_F + 1, wv = width - SS_F + 1;
+  dim3 grid((wv + SS_TW - 1) / SS_TW, (hv + SS_TH - 1) / SS_TH, n);
+  BF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "image too large for the SSIM grid");
+  ssim_forward_kernel<<<grid, SS_TW * SS_TH, 0, st>>>(gt, pred, maps, ssim_sums, height, width, hv, wv);
+  h->launches++;
+  BF_CUDA(cudaGetLastError());
+  return BFCNN_OK;
+}
+
 int run_loss(bfcnn_handle* h, const float* gt, const float* pred, int n, int height, int width,
-             const bfcnn_loss_cfg* cfg, float* out4, cudaStream_t st) {
+             const bfcnn_loss_cfg* cfg, float* out5, cudaStream_t st) {
   BF_REQUIRE(n <= 65535, "batch too large");
   BF_REQUIRE((long long)height * width * 3 < (1ll << 31), "image too large");
   const int per_sample = height * width * 3;
-  BF_CHECK(h->ws_stats.reserve((size_t)(4 * n) * sizeof(double) + 64));
+  const bool use_ssim = cfg->ssim_multiplier > 0.f;
+  BF_CHECK(h->ws_stats.reserve((size_t)(5 * n) * sizeof(double) + 64));
   double* sums = h->ws_stats.as<double>();
-  float* scal = reinterpret_cast<float*>(sums + 4 * n);
-  BF_CUDA(cudaMemsetAsync(sums, 0, (size_t)4 * n * sizeof(double), st));
+  double* ssim_sums = sums + 4 * n;
+  float* scal = reinterpret_cast<float*>(sums + 5 * n);
+  BF_CUDA(cudaMemsetAsync(sums, 0, (size_t)5 * n * sizeof(double), st));
   dim3 grid((unsigned)loss_grid_x(h, per_sample, n), (unsigned)n);
   loss_reduce_kernel<<<grid, 256, 0, st>>>(gt, pred, sums, per_sample, cfg->hinge, cfg->cutoff);
-  loss_finalize_kernel<<<1, 32, 0, st>>>(sums, n, per_sample, *cfg, scal, nullptr);
+  double ssim_cnt = 1;
+  if (use_ssim) {
+    const size_t nwin = (size_t)n * (height - SS_F + 1 > 0 ? height - SS_F + 1 : 0) * (width - SS_F + 1 > 0 ? width - SS_F + 1 : 0);
+    BF_CHECK(h->ws_grads.reserve(std::max<size_t>(nwin, 1) * 9 * sizeof(float)));
+    BF_CHECK(run_ssim(h, gt, pred, n, height, width, h->ws_grads.as<float>(), ssim_sums, st));
+    ssim_cnt = 3.0 * (height - SS_F + 1) * (width - SS_F + 1);
+  }
+  loss_finalize_kernel<<<1, 32, 0, st>>>(sums, use_ssim ? ssim_sums : nullptr, ssim_cnt, n, per_sample, *cfg, scal, nullptr);
   h->launches += 2;
   BF_CUDA(cudaGetLastError());
-  BF_CUDA(cudaMemcpyAsync(out4, scal, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaMemcpyAsync(out5, scal, 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaStreamSynchronize(st));
   return BFCNN_OK;
 }
@@ -382,7 +531,8 @@ __device__ __forceinline__ void load_px16(const float* __restrict__ p, float (&x
 // forward head + per-sample loss sums in one pass over the last feature map
 __global__ void __launch_bounds__(256)
 head_loss_kernel(const float* __restrict__ feat, const float* __restrict__ gt, const float* __restrict__ wc,
-                 double* __restrict__ sums, int px_per_sample, float hinge, float cutoff) {
+                 double* __restrict__ sums, float* __restrict__ pred_out /* [n,h,w,3] or nullptr (SSIM needs the tensor) */,
+                 int px_per_sample, float hinge, float cutoff) {
   __shared__ float s_wc[C * 4];
   __shared__ float s_red[4];
   if (threadIdx.x < C * 4) s_wc[threadIdx.x] = wc[threadIdx.x];
@@ -398,6 +548,7 @@ head_loss_kernel(const float* __restrict__ feat, const float* __restrict__ gt, c
     for (int o = 0; o < 3; ++o) {
       const LossTerms t = loss_terms(gt[p * 3 + o] - pr[o], hinge, cutoff);
       acc[0] += t.abs_e; acc[1] += t.hinged; acc[2] += t.sq; acc[3] += t.sqh;
+      if (pred_out) pred_out[p * 3 + o] = pr[o];
     }
   }
   block_accumulate<4>(acc, sums + 4 * s, s_red);
@@ -406,8 +557,8 @@ head_loss_kernel(const float* __restrict__ feat, const float* __restrict__ gt, c
 // backward of loss + head: dX = Wc * dy ; G[ci][o] += x[ci]*dy[o]
 __global__ void __launch_bounds__(256)
 head_backward_kernel(const float* __restrict__ feat, const float* __restrict__ gt, const float* __restrict__ wc,
-                     const float* __restrict__ coef, float* __restrict__ dfeat, double* __restrict__ G /*[16][3]*/,
-                     int px_per_sample, float hinge, float cutoff) {
+                     const float* __restrict__ coef, const float* __restrict__ dpred_extra /* SSIM term or nullptr */,
+                     float* __restrict__ dfeat, double* __restrict__ G /*[16][3]*/, int px_per_sample, float hinge, float cutoff) {
   __shared__ float s_wc[C * 4];
   __shared__ float s_red[C * 3];
   if (threadIdx.x < C * 4) s_wc[threadIdx.x] = wc[threadIdx.x];
@@ -429,7 +580,7 @@ head_backward_kernel(const float* __restrict__ feat, const float* __restrict__ g
       const float sgn = (e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f);
       float de = c_mae * sgn * keras_relu_grad(ae, hinge, cutoff);
       de += c_mse * keras_relu(e, hinge, cutoff * cutoff) * keras_relu_grad(e, hinge, cutoff * cutoff);
-      const float dpred = -de;
+      const float dpred = -de + (dpred_extra ? dpred_extra[p * 3 + o] : 0.f);
       const float t = th[o] * 0.51f;
       const float pass = (t >= -0.5f && t <= 0.5f) ? 1.f : 0.f;   // clip_by_value gradient
       dy[o] = dpred * 255.0f * pass * 0.51f * 2.0f * (1.0f - th[o] * th[o]);
@@ -715,14 +866,15 @@ reg_loss_kernel(const float* __restrict__ vars, const long long* __restrict__ se
   if (threadIdx.x == 0) atomicAdd(out, s_red[0] * 0.01);
 }
 
-// losses4 = total, denoiser total, mae, regularisation
+// losses5 = total, denoiser total, mae, regularisation, ssim loss
 __global__ void step_scalars_kernel(const float* __restrict__ loss_scal, const double* __restrict__ reg, float lambda,
-                                    float* __restrict__ out4) {
+                                    float* __restrict__ out5) {
   if (threadIdx.x != 0) return;
-  out4[0] = (float)((double)loss_scal[0] + reg[0] * (double)lambda);
-  out4[1] = loss_scal[0];
-  out4[2] = loss_scal[1];
-  out4[3] = (float)reg[0];
+  out5[0] = (float)((double)loss_scal[0] + reg[0] * (double)lambda);
+  out5[1] = loss_scal[0];
+  out5[2] = loss_scal[1];
+  out5[3] = (float)reg[0];
+  out5[4] = loss_scal[4];
 }
 
 // =====================================================================================
@@ -730,7 +882,7 @@ __global__ void step_scalars_kernel(const float* __restrict__ loss_scal, const d
 // =====================================================================================
 struct TrainWs {
   // offsets into ws_stats (bytes)
-  size_t bn_stats, bn_params, bwd_sums, loss_sums, loss_scal, loss_coef, G, reg, tables, out4, end;
+  size_t bn_stats, bn_params, bwd_sums, loss_sums, ssim_sums, loss_scal, loss_coef, G, reg, tables, out4, end;
 };
 
 static TrainWs plan_stats(int N, int n) {
@@ -740,12 +892,13 @@ static TrainWs plan_stats(int N, int n) {
   w.bn_stats = take((size_t)std::max(N, 1) * 2 * C * sizeof(double));
   w.bwd_sums = take((size_t)std::max(N, 1) * 2 * C * sizeof(double));
   w.loss_sums = take((size_t)4 * n * sizeof(double));
+  w.ssim_sums = take((size_t)n * sizeof(double));
   w.G = take((size_t)C * 3 * sizeof(double));
   w.reg = take(sizeof(double));
   w.bn_params = take((size_t)std::max(N, 1) * 4 * C * sizeof(float));
-  w.loss_scal = take(4 * sizeof(float));
+  w.loss_scal = take(8 * sizeof(float));
   w.loss_coef = take((size_t)(1 + n) * sizeof(float));
-  w.out4 = take(4 * sizeof(float));
+  w.out4 = take(8 * sizeof(float));
   w.tables = take((size_t)(2 * N + 8) * (sizeof(long long) + 2 * sizeof(int)) + 64);
   w.end = o;
   return w;
@@ -773,7 +926,9 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   // ---- workspaces
   const int n_saved = 3 * N + 1;                       // X_0..X_N, T_i, U_i
   BF_CHECK(h->ws_train.reserve((size_t)n_saved * map_floats * sizeof(float)));
-  BF_CHECK(h->ws_grads.reserve((size_t)4 * map_floats * sizeof(float)));
+  const bool use_ssim = cfg->ssim_multiplier > 0.f;
+  // SSIM scratch behind the 4 gradient maps: pred [npx*3], dpred [npx*3], derivative maps [<= npx*9]
+  BF_CHECK(h->ws_grads.reserve(((size_t)4 * map_floats + (use_ssim ? npx * 15 : 0)) * sizeof(float)));
   const int wg_grid = 2 * h->sm_count;
   const size_t nbase = (size_t)k0 * k0 * 3 * C;
   const size_t part_floats = (size_t)wg_grid * std::max<size_t>(2304, nbase);
@@ -784,6 +939,7 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   double* bn_stats = reinterpret_cast<double*>(sb + W.bn_stats);
   double* bwd_sums = reinterpret_cast<double*>(sb + W.bwd_sums);
   double* loss_sums = reinterpret_cast<double*>(sb + W.loss_sums);
+  double* ssim_sums = reinterpret_cast<double*>(sb + W.ssim_sums);
   double* Gd = reinterpret_cast<double*>(sb + W.G);
   double* regd = reinterpret_cast<double*>(sb + W.reg);
   float* bn_params = reinterpret_cast<float*>(sb + W.bn_params);
@@ -801,6 +957,7 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   auto Um = [&](int i) { return saved + (size_t)(2 * N + 1 + i) * map_floats; }; // U_0..U_{N-1}
   float* gbuf = h->ws_grads.as<float>();
   float* dXa = gbuf; float* dXb = gbuf + map_floats; float* dU = gbuf + 2 * map_floats; float* dT = gbuf + 3 * map_floats;
+  float* ss_pred = gbuf + 4 * map_floats; float* ss_dpred = ss_pred + npx * 3; float* ss_maps = ss_dpred + npx * 3;
   float* partial = h->ws_feat[2].as<float>();
   float* dgrad_w = partial + part_floats;                       // [2N][9][16][16]
   float* head_c = dgrad_w + (size_t)2 * std::max(N, 1) * 9 * C * C;  // [16][4]
@@ -855,11 +1012,25 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   // ---- loss
   const int px_per_sample = height * width;
   dim3 lgrid((unsigned)loss_grid_x(h, px_per_sample, n), (unsigned)n);
-  head_loss_kernel<<<lgrid, 256, 0, st>>>(Xm(N), clean, head_c, loss_sums, px_per_sample, cfg->hinge, cfg->cutoff);
-  loss_finalize_kernel<<<1, 32, 0, st>>>(loss_sums, n, px_per_sample * 3, *cfg, loss_scal, loss_coef);
+  head_loss_kernel<<<lgrid, 256, 0, st>>>(Xm(N), clean, head_c, loss_sums, use_ssim ? ss_pred : nullptr, px_per_sample, cfg->hinge,
+                                          cfg->cutoff);
+  double ssim_cnt = 1;
+  if (use_ssim) {
+    BF_CHECK(run_ssim(h, clean, ss_pred, n, height, width, ss_maps, ssim_sums, st));
+    const int hv = height - SS_F + 1, wv = width - SS_F + 1;
+    ssim_cnt = 3.0 * hv * wv;
+    // d(total)/d(pred) of  m * (1 - mean_b mean_{c,w} S)
+    const float coef = -cfg->ssim_multiplier / (float)((double)n * ssim_cnt);
+    dim3 bgrid((width + SS_TW - 1) / SS_TW, (height + SS_TH - 1) / SS_TH, n);
+    ssim_backward_kernel<<<bgrid, SS_TW * SS_TH, 0, st>>>(clean, ss_pred, ss_maps, ss_dpred, height, width, hv, wv, coef);
+    h->launches++;
+  }
+  loss_finalize_kernel<<<1, 32, 0, st>>>(loss_sums, use_ssim ? ssim_sums : nullptr, ssim_cnt, n, px_per_sample * 3, *cfg, loss_scal,
+                                         loss_coef);
   step_scalars_kernel<<<1, 32, 0, st>>>(loss_scal, regd, cfg->regularization, out4_d);
   // ---- backward: head
-  head_backward_kernel<<<lgrid, 256, 0, st>>>(Xm(N), clean, head_c, loss_coef, dXa, Gd, px_per_sample, cfg->hinge, cfg->cutoff);
+  head_backward_kernel<<<lgrid, 256, 0, st>>>(Xm(N), clean, head_c, loss_coef, use_ssim ? ss_dpred : nullptr, dXa, Gd, px_per_sample,
+                                              cfg->hinge, cfg->cutoff);
   const float reg1 = cfg->regularization * 0.01f;          // d/dw lambda*0.01*|w|
   const float reg2 = cfg->regularization * 0.01f * 2.0f;   // d/dw lambda*0.01*w^2
   head_grad_finalize_kernel<<<1, 256, 0, st>>>(Gd, vars, (long long)L.h0, (long long)L.h1, F, reg2, flat_grads + L.t_h0,
@@ -909,7 +1080,7 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
     h->launches += 2;
   }
   BF_CUDA(cudaGetLastError());
-  BF_CUDA(cudaMemcpyAsync(losses4, out4_d, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BF_CUDA(cudaMemcpyAsync(losses4, out4_d, 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaStreamSynchronize(st));
   return BFCNN_OK;
 }

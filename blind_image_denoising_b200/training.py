@@ -74,13 +74,10 @@ def noise_cfg_from_config(config: Dict) -> _native.NoiseCfg:
 
 
 def loss_cfg_from_config(config: Dict) -> _native.LossCfg:
-    """bfcnn/loss.py:164-181 defaults; SSIM (default multiplier 1.0 there) is row N3 and must be 0 here."""
-    ssim = float(config.get("ssim_multiplier", 1.0))
-    if ssim > 0.0:
-        raise ValueError("ssim_multiplier > 0 is not on the hot path (the _l1_ recipes set it to 0; SURVEY N3)")
+    """bfcnn/loss.py:164-181, same keys and defaults (note: the reference's default ssim_multiplier is 1.0)."""
     return _native.LossCfg(float(config.get("hinge", 0.0)), float(config.get("cutoff", 255.0)),
                            float(config.get("mae_multiplier", 1.0)), float(config.get("mse_multiplier", 0.0)),
-                           float(config.get("regularization", 1.0)))
+                           float(config.get("regularization", 1.0)), float(config.get("ssim_multiplier", 1.0)))
 
 
 def schedule_builder(config: Dict) -> Callable[[int], float]:
@@ -230,10 +227,10 @@ class Trainer:
         if gt.shape != pr.shape:
             raise ValueError("gt_batch and predicted_batch differ in shape")
         n, h, w, _ = gt.shape
-        out = (ctypes.c_float * 4)()
+        out = (ctypes.c_float * 5)()
         _native.check(self._lib.bfcnn_loss(self._h, gt.data_ptr(), pr.data_ptr(), n, h, w, ctypes.byref(self.loss_cfg),
                                            out, _stream_ptr(self.device)))
-        return {TOTAL_LOSS_STR: out[0], MAE_LOSS_STR: out[1], MSE_LOSS_STR: out[2], SSIM_LOSS_STR: 0.0,
+        return {TOTAL_LOSS_STR: out[0], MAE_LOSS_STR: out[1], MSE_LOSS_STR: out[2], SSIM_LOSS_STR: out[4],
                 "hinged_mae": out[3]}
 
     # ------------------------------------------------------------------ train_loop.py:263-312
@@ -246,12 +243,12 @@ class Trainer:
         if clean.shape != noisy.shape:
             raise ValueError("clean and noisy batches differ in shape")
         n, h, w, _ = clean.shape
-        out = (ctypes.c_float * 4)()
+        out = (ctypes.c_float * 5)()
         _native.check(self._lib.bfcnn_train_step(self._h, clean.data_ptr(), noisy.data_ptr(), n, h, w,
                                                  ctypes.byref(self.loss_cfg), self.flat_grads.data_ptr(), out,
                                                  int(bool(update_moving)), _stream_ptr(self.device)))
         model_loss = {REGULARIZATION_LOSS_STR: out[3], TOTAL_LOSS_STR: out[3] * self.loss_cfg.regularization}
-        denoiser = {TOTAL_LOSS_STR: out[1], MAE_LOSS_STR: out[2]}
+        denoiser = {TOTAL_LOSS_STR: out[1], MAE_LOSS_STR: out[2], SSIM_LOSS_STR: out[4]}
         return out[0], model_loss, denoiser, self.flat_grads
 
     # ------------------------------------------------------------------ train_loop.py:314-321,418-434

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BFCNN_ABI_VERSION 1
+#define BFCNN_ABI_VERSION 2
 
 typedef enum bfcnn_status {
   BFCNN_OK = 0,
@@ -78,13 +78,14 @@ typedef struct bfcnn_noise_cfg {
   int32_t round_values;                         /* dataset.py:228                           */
 } bfcnn_noise_cfg;
 
-/* loss.py:152-187 configuration (ssim_multiplier must be 0 on this path). */
+/* loss.py:152-187 configuration. */
 typedef struct bfcnn_loss_cfg {
-  float hinge;           /* loss.py:165 */
-  float cutoff;          /* loss.py:166 */
-  float mae_multiplier;  /* loss.py:169 */
-  float mse_multiplier;  /* loss.py:177 */
-  float regularization;  /* loss.py:181 */
+  float hinge;            /* loss.py:165 */
+  float cutoff;           /* loss.py:166 */
+  float mae_multiplier;   /* loss.py:169 */
+  float mse_multiplier;   /* loss.py:177 */
+  float regularization;   /* loss.py:181 */
+  float ssim_multiplier;  /* loss.py:171-173: (1 - mean tf.image.ssim(gt, pred, filter_size=7, max_val=255)) * m; row N3 */
 } bfcnn_loss_cfg;
 
 /* fused Adam of optimizer.py:145-224 (row N1). */
@@ -139,19 +140,20 @@ int bfcnn_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, fl
                   int n, int height, int width, uint64_t seed, uint64_t sample_offset,
                   const bfcnn_noise_cfg* cfg, void* stream);
 
-/* replaces: loss_function_builder(...)["denoiser"] (bfcnn/loss.py:190-247), ssim off.
- * gt, pred: device float32 [n,h,w,3]; out4 (host): total, mae, rmse, hinged-mae. */
+/* replaces: loss_function_builder(...)["denoiser"] (bfcnn/loss.py:190-247).
+ * gt, pred: device float32 [n,h,w,3]; out5 (host): total, mae, rmse, hinged-mae, ssim loss (1 - mean SSIM; 0 when
+ * ssim_multiplier == 0).  SSIM needs height, width >= 7. */
 int bfcnn_loss(bfcnn_handle* h, const float* gt, const float* pred, int n, int height, int width,
-               const bfcnn_loss_cfg* cfg, float* out4, void* stream);
+               const bfcnn_loss_cfg* cfg, float* out5, void* stream);
 
 /* replaces: train_step_single_gpu (bfcnn/train_loop.py:263-312): forward with BN batch
  * statistics, hinged-MAE (+RMSE) loss, L1/L2 weight regularisation, backward.
  * clean, noisy: device float32 [n,h,w,3] (0..255).  flat_grads: device float32
  * [bfcnn_num_trainable] in Keras trainable_variables order (the buffer a data-parallel
- * caller all-reduces).  losses4 (host): total, denoiser total, mae, regularisation.
+ * caller all-reduces).  losses5 (host): total, denoiser total, mae, regularisation, ssim loss.
  * update_moving != 0 applies the BN moving-statistics update (momentum 0.995). */
 int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int n, int height,
-                     int width, const bfcnn_loss_cfg* cfg, float* flat_grads, float* losses4,
+                     int width, const bfcnn_loss_cfg* cfg, float* flat_grads, float* losses5,
                      int update_moving, void* stream);
 
 /* Engine of the 3x3 convs inside bfcnn_train_step: 1 (default) = tensor cores with the fp16 hi/lo split (3 MMAs per

@@ -183,18 +183,48 @@ def rmse_diff(error: torch.Tensor, hinge: float = 0.0, cutoff: float = 255.0 * 2
     return d.mean()
 
 
+def ssim_tf(img1: torch.Tensor, img2: torch.Tensor, max_val: float = 255.0, filter_size: int = 7,
+            filter_sigma: float = 1.5, k1: float = 0.01, k2: float = 0.03) -> torch.Tensor:
+    """tf.image.ssim (TF 2.13 image_ops_impl: _fspecial_gauss, _ssim_helper, _ssim_per_channel) on NHWC tensors, as
+    called by loss.py:217-224 (filter_size=7, max_val=255).  Returns one value per image:
+    mean over channels of the spatial mean (VALID windows) of luminance * contrast-structure."""
+    dtype = img1.dtype
+    coords = torch.arange(filter_size, dtype=dtype) - (filter_size - 1.0) / 2.0
+    g = -0.5 * coords * coords / (filter_sigma * filter_sigma)
+    g2 = torch.softmax((g.view(1, -1) + g.view(-1, 1)).reshape(-1), dim=0).view(1, 1, filter_size, filter_size)
+    c = img1.shape[-1]
+    k = g2.repeat(c, 1, 1, 1)
+
+    def reducer(t):   # depthwise_conv2d, strides 1, padding VALID
+        return F.conv2d(t.permute(0, 3, 1, 2), k, groups=c)
+
+    c1, c2 = (k1 * max_val) ** 2, (k2 * max_val) ** 2
+    mean0, mean1 = reducer(img1), reducer(img2)
+    num0 = mean0 * mean1 * 2.0
+    den0 = mean0 * mean0 + mean1 * mean1
+    luminance = (num0 + c1) / (den0 + c1)
+    num1 = reducer(img1 * img2) * 2.0
+    den1 = reducer(img1 * img1 + img2 * img2)
+    cs = (num1 - num0 + c2) / (den1 - den0 + c2)
+    return (luminance * cs).mean(dim=(2, 3)).mean(dim=1)
+
+
 def denoiser_loss(gt: torch.Tensor, pred: torch.Tensor, *, hinge=0.0, cutoff=255.0,
-                  mae_multiplier=1.0, mse_multiplier=0.0) -> Dict[str, torch.Tensor]:
-    """loss.py:190-247 with ssim_multiplier = 0 (the _l1_ recipes; SSIM is row N3)."""
+                  mae_multiplier=1.0, mse_multiplier=0.0, ssim_multiplier=0.0) -> Dict[str, torch.Tensor]:
+    """loss.py:190-247 (the reference's default ssim_multiplier is 1.0, loss.py:171; the _l1_ recipes use 0)."""
     e = gt - pred
     mae_actual = mae_diff(e, 0.0, 255.0)
     mse_actual = rmse_diff(e, 0.0, 255.0)
     total = torch.zeros((), dtype=gt.dtype)
     if mae_multiplier > 0.0:
         total = total + mae_diff(e, hinge, cutoff) * mae_multiplier
+    ssim_loss = torch.zeros((), dtype=gt.dtype)
+    if ssim_multiplier > 0.0:                                    # loss.py:217-225
+        ssim_loss = 1.0 - ssim_tf(gt, pred, max_val=255.0, filter_size=7).mean()
+        total = total + ssim_loss * ssim_multiplier
     if mse_multiplier > 0.0:
         total = total + rmse_diff(e, hinge, cutoff * cutoff) * mse_multiplier
-    return {"total_loss": total, "mae_loss": mae_actual, "mse_loss": mse_actual}
+    return {"total_loss": total, "mae_loss": mae_actual, "mse_loss": mse_actual, "ssim_loss": ssim_loss}
 
 
 # ----------------------------------------------------------------------------
@@ -202,7 +232,7 @@ def denoiser_loss(gt: torch.Tensor, pred: torch.Tensor, *, hinge=0.0, cutoff=255
 # ----------------------------------------------------------------------------
 def train_step(variables: Sequence[np.ndarray], clean_nhwc: np.ndarray, noisy_nhwc: np.ndarray, *,
                hinge: float = 0.5, cutoff: float = 255.0, mae_multiplier: float = 1.0,
-               mse_multiplier: float = 0.0, regularization: float = 0.01,
+               mse_multiplier: float = 0.0, regularization: float = 0.01, ssim_multiplier: float = 0.0,
                dtype=torch.float64, head_literal: bool = False):
     """One tape step: hydra(noisy, training=True) -> denoiser loss (+ L1/L2 weight
     regularisation * lambda) -> gradients w.r.t. trainable variables.
@@ -252,12 +282,13 @@ def train_step(variables: Sequence[np.ndarray], clean_nhwc: np.ndarray, noisy_nh
     pred = y.permute(0, 2, 3, 1)
     gt = _t(clean_nhwc, dtype)
     dl = denoiser_loss(gt, pred, hinge=hinge, cutoff=cutoff, mae_multiplier=mae_multiplier,
-                       mse_multiplier=mse_multiplier)
+                       mse_multiplier=mse_multiplier, ssim_multiplier=ssim_multiplier)
     total = dl["total_loss"] + reg * regularization            # train_loop.py:297-301
     grads = torch.autograd.grad(total, [params[k] for k in order])
     return {
         "total": float(total), "denoiser_total": float(dl["total_loss"]),
         "mae": float(dl["mae_loss"]), "mse": float(dl["mse_loss"]), "reg": float(reg),
+        "ssim": float(dl["ssim_loss"]),
         "grads": [g.numpy() for g in grads],
         "prediction": pred.detach().numpy(), "new_moving": new_moving,
     }

@@ -107,3 +107,27 @@ def test_train_step_bn_moving_update():
     assert m.shape == (16,) and var.shape == (16,)
     # momentum 0.995: the moving stats move by at most 0.5 % of the gap per step
     assert np.all(np.abs(m - v[4] * 0.995) < 1.0) and np.all(var > 0)
+
+
+def test_ssim_matches_independent_formula():
+    """oracle.ssim_tf (tf.image.ssim restated) against the textbook SSIM with a separable Gaussian from scipy:
+    ((2 mx my + c1)(2 sxy + c2)) / ((mx^2 + my^2 + c1)(sx^2 + sy^2 + c2)), VALID windows, mean over windows, channels."""
+    import torch
+    from scipy.ndimage import correlate1d
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 256, size=(2, 19, 23, 3)).astype(np.float64)
+    y = np.clip(x + rng.normal(0, 25, size=x.shape), 0, 255)
+    got = O.ssim_tf(torch.tensor(x), torch.tensor(y), max_val=255.0, filter_size=7).numpy()
+    c = np.arange(7) - 3.0
+    g = np.exp(-0.5 * c * c / 1.5 ** 2); g /= g.sum()
+
+    def filt(a):   # VALID 7x7 separable correlation over H, W
+        a = correlate1d(a, g, axis=1, mode="constant")[:, 3:-3]
+        return correlate1d(a, g, axis=2, mode="constant")[:, :, 3:-3]
+    mx, my = filt(x), filt(y)
+    sxx, syy, sxy = filt(x * x) - mx * mx, filt(y * y) - my * my, filt(x * y) - mx * my
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    ssim = ((2 * mx * my + c1) * (2 * sxy + c2)) / ((mx * mx + my * my + c1) * (sxx + syy + c2))
+    want = ssim.mean(axis=(1, 2)).mean(axis=1)
+    assert np.allclose(got, want, rtol=1e-10)
+    assert np.allclose(O.ssim_tf(torch.tensor(x), torch.tensor(x)).numpy(), 1.0)

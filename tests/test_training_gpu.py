@@ -81,6 +81,8 @@ def test_corrupt_golden_and_full_size_statistics(native_lib):
     dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.0, regularization=0.01, ssim_multiplier=0.0),
     dict(hinge=0.0, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=1.0, regularization=0.01, ssim_multiplier=0.0),
     dict(hinge=2.0, cutoff=30.0, mae_multiplier=0.5, mse_multiplier=2.0, regularization=0.01, ssim_multiplier=0.0),
+    dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.0, regularization=0.01, ssim_multiplier=1.0),  # reference default
+    dict(hinge=0.0, cutoff=255.0, mae_multiplier=0.0, mse_multiplier=0.5, regularization=0.01, ssim_multiplier=3.0),
 ])
 def test_loss_matches_oracle(native_lib, cfg):
     import torch
@@ -93,11 +95,15 @@ def test_loss_matches_oracle(native_lib, cfg):
     pred[1, :4] = gt[1, :4] - 0.5                 # error exactly at the hinge
     got = t.denoiser_loss(torch.from_numpy(gt).cuda(), torch.from_numpy(pred).cuda())
     ref = O.denoiser_loss(torch.from_numpy(gt).double(), torch.from_numpy(pred).double(), hinge=cfg["hinge"],
-                          cutoff=cfg["cutoff"], mae_multiplier=cfg["mae_multiplier"], mse_multiplier=cfg["mse_multiplier"])
-    for k in ("total_loss", "mae_loss", "mse_loss"):
-        assert got[k] == pytest.approx(float(ref[k]), rel=1e-5), k
+                          cutoff=cfg["cutoff"], mae_multiplier=cfg["mae_multiplier"], mse_multiplier=cfg["mse_multiplier"],
+                          ssim_multiplier=cfg["ssim_multiplier"])
+    for k in ("total_loss", "mae_loss", "mse_loss", "ssim_loss"):
+        assert got[k] == pytest.approx(float(ref[k]), rel=1e-5, abs=1e-7), k
     with pytest.raises(Exception):
         t.denoiser_loss(torch.empty((0, 4, 4, 3), device="cuda"), torch.empty((0, 4, 4, 3), device="cuda"))
+    if cfg["ssim_multiplier"] > 0:   # tf.image.ssim needs at least one 7x7 window
+        with pytest.raises(Exception):
+            t.denoiser_loss(torch.zeros((1, 6, 20, 3), device="cuda"), torch.zeros((1, 6, 20, 3), device="cuda"))
     t.close()
 
 
@@ -135,12 +141,15 @@ def _grad_check(got, ref_list, arch, engine="fp32"):
     (6, (3, 36, 28, 3), dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.0, regularization=0.01)),
     (3, (2, 70, 66, 3), dict(hinge=0.0, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=1.0, regularization=0.1)),
     (0, (2, 16, 16, 3), dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.0, regularization=0.01)),
+    # the reference's default loss: MAE + (1 - SSIM)   (loss.py:169-173)
+    (2, (2, 30, 41, 3), dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.0, regularization=0.01, ssim_multiplier=1.0)),
+    (1, (3, 7, 9, 3), dict(hinge=0.0, cutoff=255.0, mae_multiplier=0.0, mse_multiplier=0.0, regularization=0.01, ssim_multiplier=100.0)),
 ])
 def test_train_step_matches_oracle(native_lib, n_layers, shape, loss, engine):
     import torch
     from oracle import bfcnn_oracle as O
     from oracle import corrupt_oracle as C
-    arch, v, t = _trainer(n_layers, loss=dict(loss, ssim_multiplier=0.0), engine=engine)
+    arch, v, t = _trainer(n_layers, loss=dict({"ssim_multiplier": 0.0}, **loss), engine=engine)
     x = np.random.default_rng(n_layers).integers(0, 256, size=shape, dtype=np.uint8)
     clean, noisy = C.corrupt(x, 11, 0, C.NoiseConfig())
     ref = O.train_step(v, clean, noisy, **loss)
@@ -149,6 +158,7 @@ def test_train_step_matches_oracle(native_lib, n_layers, shape, loss, engine):
     assert dl["total_loss"] == pytest.approx(ref["denoiser_total"], rel=1e-5)
     assert dl["mae_loss"] == pytest.approx(ref["mae"], rel=1e-5)
     assert model_loss["regularization_loss"] == pytest.approx(ref["reg"], rel=1e-5)
+    assert dl["ssim_loss"] == pytest.approx(ref["ssim"], rel=1e-5, abs=1e-7)
     _grad_check(grads.cpu().numpy(), ref["grads"], arch, engine)
     # BN moving statistics (momentum 0.995, unbiased variance)
     new = t.get_weights()
