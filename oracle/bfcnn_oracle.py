@@ -286,9 +286,9 @@ def train_step(variables: Sequence[np.ndarray], clean_nhwc: np.ndarray, noisy_nh
     total = dl["total_loss"] + reg * regularization            # train_loop.py:297-301
     grads = torch.autograd.grad(total, [params[k] for k in order])
     return {
-        "total": float(total), "denoiser_total": float(dl["total_loss"]),
-        "mae": float(dl["mae_loss"]), "mse": float(dl["mse_loss"]), "reg": float(reg),
-        "ssim": float(dl["ssim_loss"]),
+        "total": float(total.detach()), "denoiser_total": float(dl["total_loss"].detach()),
+        "mae": float(dl["mae_loss"].detach()), "mse": float(dl["mse_loss"].detach()), "reg": float(reg.detach()),
+        "ssim": float(dl["ssim_loss"].detach()),
         "grads": [g.numpy() for g in grads],
         "prediction": pred.detach().numpy(), "new_moving": new_moving,
     }

@@ -174,3 +174,18 @@ def test_host_pipeline_chunks_match_device_path(native_lib):
     m(xp, out=out)
     assert np.array_equal(out.numpy(), m(xd).cpu().numpy())
     m.close()
+
+
+@pytest.mark.parametrize("k0", [1, 5, 7])
+def test_base_kernel_sizes(native_lib, k0):
+    """k0 is a load-time parameter (every in-tree resnet config uses 7, SURVEY 8 notation): all engines, odd shape."""
+    import blind_image_denoising_b200 as bf
+    from oracle import bfcnn_oracle as O
+    arch = bf.Arch(no_layers=3, base_kernel=k0)
+    v = bf.synthetic_variables(arch, 1)
+    x = np.random.default_rng(k0).integers(0, 256, size=(2, 45, 70, 3), dtype=np.uint8)
+    yref, u8ref = O.denoise(v, x, pad_pow2=True)
+    for prec in ("fp32", "f16x3", "f16", "f16_mma_sync"):
+        m = bf.Denoiser(arch, v, precision=prec)
+        _check(m(x, return_float=True), yref, m(x), u8ref, prec)
+        m.close()
