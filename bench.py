@@ -48,7 +48,8 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms; only the samples that fall inside the timed region
+    (host timestamps around the CUDA-event bracket) are reported."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -58,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -67,19 +68,23 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [ln for (ts, ln) in self.lines if t0 <= ts <= t1 + 0.03]
+        if not inside:   # region shorter than a sampling period: the closest samples
+            inside = [ln for (ts, ln) in sorted(self.lines, key=lambda p: min(abs(p[0] - t0), abs(p[0] - t1)))[:2]]
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -221,20 +226,22 @@ def main():
 
     def measure(precision: str, steps: int, warmup: int):
         model = bfcnn.load_model(MODEL_NAME, device=local_rank, precision=precision, pad_pow2=False)
+        sampler = ClockSampler(local_rank)
+        sampler.start()            # nvidia-smi needs ~100 ms to start: it runs through the warm-up
         for _ in range(warmup):
             model(d_in, out=d_out)
         barrier()
         l0 = model.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stack_ms = 0.0
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        t_host0 = time.time()
         e0.record()
         for _ in range(steps):
             model(d_in, out=d_out)
         e1.record()
         barrier()
-        clocks = sampler.stop()
+        t_host1 = time.time()
+        clocks = sampler.stop(t_host0, t_host1)
         ms = max_over_ranks(e0.elapsed_time(e1))
         launches = model.launch_count() - l0
         # kernel-only time of the fused stack (events inside the library, same stream)
