@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=4, help="4K frames per GPU per step")
-    ap.add_argument("--precision", default="f16", choices=["f16", "f16_mma_sync", "f16x3", "fp32"])
+    ap.add_argument("--precision", default="f16", choices=["f16", "f16_mma_sync", "f16x3", "f16x3_mma_sync", "fp32"])
     ap.add_argument("--cpu-crop", type=int, default=768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="skip the secondary precision modes")
@@ -270,14 +270,16 @@ def main():
     # roofline of the dominant kernel (the fused conv-stack pass / FP32 conv layer)
     alg_flops = arch.flops_per_pixel() * mp_per_step_rank * 1e6
     passes = {"f16": (N_LAYERS + 1) // 2, "f16_mma_sync": (N_LAYERS + 1) // 2, "f16x3": N_LAYERS,
-              "fp32": 2 * N_LAYERS + 2}[args.precision]
+              "f16x3_mma_sync": N_LAYERS, "fp32": 2 * N_LAYERS + 2}[args.precision]
     achieved = alg_flops / (r["stack_ms"] / 1e3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
         "kernel": {"f16": "umma_pass_kernel (tcgen05; + one base_conv_f16_kernel launch inside the timed stack)",
-                   "f16_mma_sync": "fused_pass_kernel<1>", "f16x3": "fused_pass_kernel<2>",
+                   "f16_mma_sync": "fused_pass_kernel<1>",
+                   "f16x3": "umma3::umma_pass_kernel<P=2> (tcgen05, fp16 hi/lo operand parts)",
+                   "f16x3_mma_sync": "fused_pass_kernel<2>",
                    "fp32": "conv3x3_c16_kernel"}[args.precision],
         "launches_per_step": passes, "avg_launch_ms": r["stack_ms"] / passes,
         "algorithmic_flops_per_launch": alg_flops / passes,
@@ -293,7 +295,7 @@ def main():
 
     modes = {}
     if not args.no_modes:   # every rank takes part (the barriers are collective)
-        for prec in ("f16", "f16_mma_sync", "f16x3", "fp32"):
+        for prec in ("f16", "f16_mma_sync", "f16x3", "f16x3_mma_sync", "fp32"):
             if prec == args.precision:
                 continue
             steps = 2 if prec == "fp32" else max(2, args.steps // 2)
@@ -343,7 +345,8 @@ def main():
     if rank == 0:
         parity = {"f16": "fp16 operands / fp32 accumulate (tcgen05): max-abs <= 2.0, mean-abs <= 0.25 (0-255) vs fp64 oracle (stated bf16-class bound)",
                   "f16_mma_sync": "fp16 operands / fp32 accumulate (mma.sync baseline): max-abs <= 2.0, mean-abs <= 0.25",
-                  "f16x3": "fp16 hi/lo split, 3 MMAs: max-abs <= 0.5, mean-abs <= 0.05 (the fp32 gate)",
+                  "f16x3": "fp16 hi/lo split, 3 tcgen05 MMAs per product: max-abs <= 0.5, mean-abs <= 0.05 (the fp32 gate)",
+                  "f16x3_mma_sync": "fp16 hi/lo split, 3 mma.sync per product: max-abs <= 0.5, mean-abs <= 0.05",
                   "fp32": "FP32 FFMA: max-abs <= 0.5, mean-abs <= 0.05"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

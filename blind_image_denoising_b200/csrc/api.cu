@@ -65,7 +65,8 @@ int run_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, co
     return launch_head(h, X, d_out, out_u8, h->d_head_f32.as<float>(), e, st);
   }
   if (precision == BFCNN_PREC_F16) return run_fused_stack_umma(h, d_in, d_out, out_u8, e, st);
-  return run_fused_stack(h, d_in, d_out, out_u8, e, precision == BFCNN_PREC_F16_MMA_SYNC ? BFCNN_PREC_F16 : precision, st);
+  if (precision == BFCNN_PREC_F16X3) return run_fused_stack_umma_x3(h, d_in, d_out, out_u8, e, st);
+  return run_fused_stack(h, d_in, d_out, out_u8, e, precision == BFCNN_PREC_F16_MMA_SYNC ? BFCNN_PREC_F16 : BFCNN_PREC_F16X3, st);
 }
 
 int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int n, int height, int width,
@@ -73,7 +74,7 @@ int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int
   BF_REQUIRE(h != nullptr, "handle is NULL");
   BF_CHECK(check_images(n, height, width));
   BF_REQUIRE(precision == BFCNN_PREC_FP32 || precision == BFCNN_PREC_F16 || precision == BFCNN_PREC_F16X3 ||
-                 precision == BFCNN_PREC_F16_MMA_SYNC,
+                 precision == BFCNN_PREC_F16_MMA_SYNC || precision == BFCNN_PREC_F16X3_MMA_SYNC,
              "unknown precision");
   const size_t npx = (size_t)n * height * width;
   if (npx == 0) return BFCNN_OK;  // empty batch / empty image: nothing to do
@@ -221,7 +222,7 @@ void bfcnn_destroy(bfcnn_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   h->d_vars.release(); h->d_base_f32.release(); h->d_conv_f32.release(); h->d_bias_f32.release();
-  h->d_head_f32.release(); h->d_conv_frag.release(); h->d_base_frag.release(); h->d_conv_umma.release();
+  h->d_head_f32.release(); h->d_conv_frag.release(); h->d_base_frag.release(); h->d_conv_umma.release(); h->d_conv_umma_x3.release();
   h->ws_in.release(); h->ws_out.release();
   for (auto& b : h->ws_feat) b.release();
   h->ws_train.release(); h->ws_stats.release(); h->ws_grads.release();

@@ -87,6 +87,7 @@ struct bfcnn_handle {
   bfcnn::DevBuf d_head_f32;   // [16][4] collapsed head (4th column zero)
   bfcnn::DevBuf d_conv_frag;  // HMMA B fragments: [2N][hi/lo][9][2][32] uint2
   bfcnn::DevBuf d_base_frag;  // HMMA B fragments of the base conv (K padded to 32)
+  bfcnn::DevBuf d_conv_umma_x3; // the same with a lo part: [2N][hi/lo][dx 3][N 48][K 16] fp16
   bfcnn::DevBuf d_conv_umma;  // tcgen05 B operands: [2N][dx 3][N 48 = (dy, cout)][K 16] fp16, K-major core matrices
   bool packed_valid = false;
 

@@ -1,0 +1,850 @@
+// fused_umma_x3.cu -- the tcgen05 fused stack of fused_umma.cu in the F16X3 arithmetic (FP32-grade results).
+//
+// This is the same kernel design, templated on the number of operand parts P: activations and weights are split into
+// fp16 hi + lo planes and every product is issued as hi*hi + lo*hi + hi*lo (9 MMAs per region row instead of 3), the
+// residual pre-load adds hi + lo in fp32, and the feature map between passes carries both planes.  It is kept in its
+// own translation unit because instantiating the template for P = 1 costs the F16 kernel 3 % (ptxas moves part of the
+// MMA-issue arithmetic off the uniform datapath); fused_umma.cu stays the tuned single-plane version.
+//
+// (original header of the design follows)
+// the fused conv-BN-ReLU residual stack on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// Same contract as fused_f16.cu (one CTA owns a spatial region with a halo of 2*nblk pixels, runs nblk residual
+// blocks on it without leaving the SM, per-layer zero padding by masking), different engine:
+//
+//   * The region is 128 pixels wide: one region row == the M = 128 rows of one tcgen05.mma.
+//   * Activations live in shared memory as two channel-half planes (8 channels = 16 B per pixel per plane).
+//     That is exactly the SWIZZLE_NONE K-major canonical layout (core matrix = 8 pixels x 16 B, SBO = 128 B,
+//     LBO = plane stride), and because it is affine in the pixel index a 3x3 tap shift is just
+//     "descriptor start address += shift * 16 B" -- no im2col, no data movement (tools/umma_probe.cu, Q1).
+//   * A 16-cout GEMM (N = 16) would be shared-memory bound on the A operand (4 KB per MMA for 8 math cycles).
+//     So every MMA computes the contributions of one input row q to the THREE output rows q-1, q, q+1 at once:
+//     B = [16 cin x (3 dy x 16 cout)] = N 48, and the accumulator of output row r sits in TMEM columns
+//     [16(r+1), 16(r+1)+16), so the three dy partial sums are accumulated by the tensor core itself
+//     (D columns 16q .. 16q+47 of MMA(q)).  dx is handled by three MMAs with the A start shifted by -1/0/+1 pixel.
+//     3 MMAs (M128 N48 K16) per 128-pixel row per conv; the epilogue reads 16 columns per pixel.
+//   * Accumulators never leave TMEM between the MMA and the epilogue; the epilogue (bias, ReLU / residual add,
+//     border mask, fp16 pack) runs in 16 warps that each own one 32-lane TMEM quarter of a row, writes the next
+//     layer's A operand straight back into the shared-memory planes and re-zeroes the drained TMEM block.
+//   * One elected thread issues every MMA; mbarriers per group of 3 rows couple it to the epilogue warps
+//     (mma_done[g] via tcgen05.commit, epi_done[g] via mbarrier.arrive), so layer l+1 chases layer l down the
+//     region a few rows behind and the tensor pipe never drains at a layer boundary.
+//   * The kernel is persistent (one CTA per SM, regions round-robin).  In the last layer of a region every
+//     epilogue thread, once it has consumed its pixel of X, fetches the same pixel of the NEXT region into the
+//     freed slot with cp.async; to the MMA issuer the next region's first layer is just "one more layer", so
+//     the tensor pipe does not drain between regions either and HBM latency hides behind the last conv.
+//
+// Reference arithmetic: module_denoiser.py:53-73, utilities.py:449-461 (normalise), backbone_resnet.py:258-262
+// (base conv), backbone_blocks.py:167-246 (block), model.py:297-342 (head), utilities.py:435-443 (denormalise).
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
+
+#include "kernels.cuh"
+
+namespace bfcnn {
+namespace umma3 {
+
+constexpr int RW = 128;                 // region width == UMMA M
+constexpr int SLACK_PX = 8;             // pixels of slack before/after every plane (tap shift -1/+1)
+constexpr int NSETS = 4;                // epilogue warp sets (4 warps each, one per TMEM lane quarter); 13 warps -> 128 registers
+constexpr int EPI_WARPS = 4 * NSETS;
+constexpr int NTHREADS = 32 * (EPI_WARPS + 1);   // + the MMA issuer warp
+constexpr int MAX_RH = 30;              // (RH + 2) accumulator blocks of 16 columns <= 512 TMEM columns
+constexpr int W_LAYER_BYTES = 3 * 48 * 16 * 2;   // B operand of one conv: [dx 3][N 48][K 16] fp16
+constexpr int MAX_SMEM = 232448;
+constexpr int MAX_LAYERS = 8;           // conv layers fused per pass
+
+enum Epi { EPI_RELU_TO_T = 0, EPI_RES_TO_X = 1, EPI_RES_TO_GLOBAL = 2, EPI_RES_HEAD = 3 };
+
+constexpr int GROUP_F16 = 6;            // region rows per barrier group: the MMA issuer pays ~300 cycles per mbarrier wait
+                                        // (the tensor pipe drains behind it, tools/umma_probe3.cu), so it waits per group, not per row
+constexpr int GROUP_X3 = 3;             // F16X3: 9 MMAs per row and 12-row regions: finer groups keep the layers overlapped
+constexpr int MAX_GROUPS = 16;          // barrier slots per kind
+
+struct Params {
+  const __half* fin;       // [P][n][he][we][16]  input feature map of this pass (base conv output for pass 0); P = 1 (fp16)
+                           //                      or 2 (fp16 hi + lo planes, the F16X3 arithmetic)
+  __half* fout;            // [P][n][he][we][16]
+  long long plane_halves;  // n*he*we*16: distance between the hi and the lo plane of fin / fout
+  void* out;               // [n][h][w][3] uint8 or float
+  const uint8_t* wumma;    // [2N][P][W_LAYER_BYTES]  (hi, then lo)
+  const float* bias;       // [2N][16]
+  const float* whead;      // [16][4]
+  int n, h, w, he, we;
+  int blk0, nblk;
+  int last, out_u8;
+  int rh, tw, th, tiles_x, tiles_y, regions;
+  int grp;                 // rows per barrier group (rh <= 16 * grp)
+  long long* trace;        // debug timeline of CTA `trace_block` (BFCNN_UMMA_TRACE=1), else nullptr
+  int trace_block;
+};
+
+// ---------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version 1 (sm_100); layout type 0 = SWIZZLE_NONE
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                    // D = F32
+  d |= 0u << 7;                    // A = F16
+  d |= 0u << 10;                   // B = F16   (both K-major: bits 15, 16 = 0)
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// one lane of a converged warp; the compiler keeps the tcgen05 operands in uniform registers only on this path
+// (a plain `lane == 0` branch wraps every UTCHMMA in an ELECT/BRA.U.ANY loop: 392 instead of 143 cycles per row)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t mbar, uint32_t n) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(mbar), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+// issue only; the registers are valid after tmem_ld_wait(v) (which carries them as in/out operands so that no use of
+// v can be scheduled above the wait)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(taddr), "r"(z)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+      "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+// TMA: one quarter-row of one channel half (32 pixels x 16 B = 512 contiguous shared bytes) of the NHWC16 feature map,
+// addressed as a 5-D tensor {ch8, half, x, y, n}; out-of-extent coordinates (negative included) are zero-filled by the
+// hardware, which is exactly the "same" padding of the feature map.
+__device__ __forceinline__ void tma_load_q(uint32_t dst, const CUtensorMap* tmap, int hf, int gx, int gy, int b, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(hf), "r"(gx), "r"(gy), "r"(b), "r"(mbar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// max(x, 0) on a packed pair; rounding to fp16 commutes with ReLU (round-to-nearest keeps the sign)
+__device__ __forceinline__ uint32_t relu_h2(uint32_t v) {
+  const __half2 z = __float2half2_rn(0.f);
+  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&v), z);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+
+// ---------------------------------------------------------------------------- shared-memory map
+struct Smem {
+  uint32_t bars;       // mma_done[16], epi_done[16] (8 B each)
+  uint32_t wts;        // [nlayers][W_LAYER_BYTES]
+  uint32_t X[2], T[2]; // byte address of pixel 0 of each channel-half plane
+  uint32_t plane_bytes;
+  uint32_t lo_off;     // byte distance from a hi plane to its lo counterpart (4 planes)
+};
+__host__ __device__ inline uint32_t plane_bytes_of(int rh) { return (uint32_t)(rh * RW + 2 * SLACK_PX) * 16u; }
+constexpr uint32_t SM_BARS = 0, SM_TMEM = 512, SM_HEAD = 528, SM_BIAS = 784, SM_WTS = 784 + MAX_LAYERS * 64;  // 1296
+__host__ __device__ inline uint32_t planes_offset(int nlayers, int parts) { return (SM_WTS + (uint32_t)(nlayers * parts) * W_LAYER_BYTES + 127u) & ~127u; }
+// plane order: [X half0, X half1, T half0, T half1] of the hi part, then the same four of the lo part
+
+struct Region { int b, oy, ox; };
+__device__ __forceinline__ Region region_of(const Params& p, int it, int halo) {
+  Region r;
+  const int tx = it % p.tiles_x;
+  it /= p.tiles_x;
+  const int ty = it % p.tiles_y;
+  r.b = it / p.tiles_y;
+  r.oy = ty * p.th - halo;
+  r.ox = tx * p.tw - halo;
+  return r;
+}
+
+// Per-thread constants of one region: everything that does not depend on the row is computed once, so that the row
+// loop below is ~60 instructions per conv_a row and ~25 per conv_b row (it was 170: the epilogue warps, not the tensor
+// pipe, set the pace -- profiles/r01_umma_ncu.md).
+struct EpiCtx {
+  uint32_t tq;            // TMEM address of this warp's lane quarter, column 0
+  uint32_t x0, x1, t0, t1;  // shared byte addresses of this thread's pixel column in region row 0
+  int oy, he;             // row r is inside the extent iff (unsigned)(oy + r) < he
+  bool col_ok;            // this thread's column is inside the extent
+  bool col_out;           // ... and inside the tile (output) columns [halo, RW - halo) (and inside the image for the head)
+  __half* fout_col;       // feature-map address of (b, oy, gx); row r adds r * row_halves
+  uint8_t* out_col;       // output address of (b, oy, gx) (uint8 or float)
+  long long row_halves;   // we * 16
+  long long row_out;      // w * 3 elements
+  int h_img;              // rows of the image (head: gy < h)
+  // next region (prefetch of this warp's quarter-row by TMA)
+  int nb, noy, nox_q;     // image index, first row, first column of the quarter in the next region
+  int n_img;              // images in the batch: the lo part of image b is tensor-map image b + n_img
+  uint32_t nx0, nx1;      // shared destinations (region row 0) of the quarter in the two channel-half planes
+};
+
+template <int EPI, bool PREFETCH, int P, int GROUP>
+__device__ __forceinline__ void epilogue_layer(const Params& p, const CUtensorMap* tmap, const Smem& S, const EpiCtx& E,
+                                               const float* s_bias_next, const float* s_head, int set, int l, uint32_t parity) {
+  const int r_lo = l + 1, r_hi = p.rh - l - 1;
+  float bias[16];
+  if (EPI == EPI_RELU_TO_T) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bq = *reinterpret_cast<const float4*>(s_bias_next + 4 * q);
+      bias[4 * q] = bq.x; bias[4 * q + 1] = bq.y; bias[4 * q + 2] = bq.z; bias[4 * q + 3] = bq.w;
+    }
+  }
+  int waited = -1;   // highest mma_done index already observed in this layer
+  for (int r = set; r < p.rh; r += NSETS) {
+    const int grp = r / GROUP;
+    const int need = min(r + 1, p.rh - 1) / GROUP;   // row r is complete once input row r+1 has been multiplied
+    if (need > waited) {
+      mbar_wait(S.bars + (uint32_t)need * 8, parity);
+      tc_fence_after();
+      waited = need;
+    }
+    const uint32_t taddr = E.tq + (uint32_t)(r + 1) * 16;
+    const uint32_t po = (uint32_t)r * (RW * 16);
+    if (r >= r_lo && r < r_hi) {
+      const bool inside = E.col_ok && ((unsigned)(E.oy + r) < (unsigned)E.he);
+      uint32_t v[16];
+      tmem_ld16_issue(taddr, v);
+      if (EPI == EPI_RELU_TO_T) {
+        // T = ReLU(D); D <- X + b' (the residual the following conv_b accumulates onto)
+        if (P == 1) {
+          const uint4 xa = lds128(E.x0 + po), xb = lds128(E.x1 + po);
+          tmem_ld_wait(v);
+          {
+            float f[16];
+            const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 xv = unpack_h2(xs[i]);
+              f[2 * i] = xv.x + bias[2 * i];
+              f[2 * i + 1] = xv.y + bias[2 * i + 1];
+            }
+            tmem_st16(taddr, f);
+          }
+          const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
+          uint4 lo, hi;   // rounding to fp16 commutes with ReLU: one packed max instead of two fp32 ones
+          lo.x = relu_h2(pack_h2(__uint_as_float(v[0]), __uint_as_float(v[1]))) & m; lo.y = relu_h2(pack_h2(__uint_as_float(v[2]), __uint_as_float(v[3]))) & m;
+          lo.z = relu_h2(pack_h2(__uint_as_float(v[4]), __uint_as_float(v[5]))) & m; lo.w = relu_h2(pack_h2(__uint_as_float(v[6]), __uint_as_float(v[7]))) & m;
+          hi.x = relu_h2(pack_h2(__uint_as_float(v[8]), __uint_as_float(v[9]))) & m; hi.y = relu_h2(pack_h2(__uint_as_float(v[10]), __uint_as_float(v[11]))) & m;
+          hi.z = relu_h2(pack_h2(__uint_as_float(v[12]), __uint_as_float(v[13]))) & m; hi.w = relu_h2(pack_h2(__uint_as_float(v[14]), __uint_as_float(v[15]))) & m;
+          sts128(E.t0 + po, lo);
+          sts128(E.t1 + po, hi);
+        } else {
+          const uint4 xa = lds128(E.x0 + po), xb = lds128(E.x1 + po);
+          const uint4 xal = lds128(E.x0 + S.lo_off + po), xbl = lds128(E.x1 + S.lo_off + po);
+          tmem_ld_wait(v);
+          {
+            float f[16];
+            const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const uint32_t xl[8] = {xal.x, xal.y, xal.z, xal.w, xbl.x, xbl.y, xbl.z, xbl.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 xv = unpack_h2(xs[i]), lv = unpack_h2(xl[i]);
+              f[2 * i] = (xv.x + lv.x) + bias[2 * i];
+              f[2 * i + 1] = (xv.y + lv.y) + bias[2 * i + 1];
+            }
+            tmem_st16(taddr, f);
+          }
+          const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
+          uint32_t hv[8], lv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a = fmaxf(__uint_as_float(v[2 * i]), 0.f), b2 = fmaxf(__uint_as_float(v[2 * i + 1]), 0.f);
+            hv[i] = pack_h2(a, b2);
+            const float2 hf = unpack_h2(hv[i]);
+            lv[i] = pack_h2(a - hf.x, b2 - hf.y) & m;
+            hv[i] &= m;
+          }
+          sts128(E.t0 + po, make_uint4(hv[0], hv[1], hv[2], hv[3]));
+          sts128(E.t1 + po, make_uint4(hv[4], hv[5], hv[6], hv[7]));
+          sts128(E.t0 + S.lo_off + po, make_uint4(lv[0], lv[1], lv[2], lv[3]));
+          sts128(E.t1 + S.lo_off + po, make_uint4(lv[4], lv[5], lv[6], lv[7]));
+        }
+      } else {
+        tmem_ld_wait(v);
+        tmem_zero16(taddr);
+        if (EPI == EPI_RES_HEAD) {   // collapsed 1x1 head + tanh(2y)*0.51 + denormalise (+ round + uint8)
+          if (E.col_out && inside && (E.oy + r) < E.h_img) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 16; ++ch) {
+              const float4 wv = *reinterpret_cast<const float4*>(s_head + ch * 4);
+              const float fv = __uint_as_float(v[ch]);
+              s0 = fmaf(fv, wv.x, s0); s1 = fmaf(fv, wv.y, s1); s2 = fmaf(fv, wv.z, s2);
+            }
+            const float r0o = head_activation(s0), r1o = head_activation(s1), r2o = head_activation(s2);
+            if (p.out_u8) {
+              uint8_t* d = E.out_col + (long long)r * E.row_out;
+              d[0] = (uint8_t)__float2int_rn(r0o); d[1] = (uint8_t)__float2int_rn(r1o); d[2] = (uint8_t)__float2int_rn(r2o);
+            } else {
+              float* d = reinterpret_cast<float*>(E.out_col) + (long long)r * E.row_out;
+              d[0] = r0o; d[1] = r1o; d[2] = r2o;
+            }
+          }
+        } else if (P == 1) {
+          uint4 lo, hi;
+          lo.x = pack_h2(__uint_as_float(v[0]), __uint_as_float(v[1])); lo.y = pack_h2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+          lo.z = pack_h2(__uint_as_float(v[4]), __uint_as_float(v[5])); lo.w = pack_h2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+          hi.x = pack_h2(__uint_as_float(v[8]), __uint_as_float(v[9])); hi.y = pack_h2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+          hi.z = pack_h2(__uint_as_float(v[12]), __uint_as_float(v[13])); hi.w = pack_h2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+          if (EPI == EPI_RES_TO_X) {
+            const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
+            lo.x &= m; lo.y &= m; lo.z &= m; lo.w &= m; hi.x &= m; hi.y &= m; hi.z &= m; hi.w &= m;
+            sts128(E.x0 + po, lo);
+            sts128(E.x1 + po, hi);
+          } else if (E.col_out && inside) {
+            uint4* o = reinterpret_cast<uint4*>(E.fout_col + (long long)r * E.row_halves);
+            o[0] = lo;
+            o[1] = hi;
+          }
+        } else {
+          uint32_t hv[8], lv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a = __uint_as_float(v[2 * i]), b2 = __uint_as_float(v[2 * i + 1]);
+            hv[i] = pack_h2(a, b2);
+            const float2 hf = unpack_h2(hv[i]);
+            lv[i] = pack_h2(a - hf.x, b2 - hf.y);
+          }
+          if (EPI == EPI_RES_TO_X) {
+            const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
+            sts128(E.x0 + po, make_uint4(hv[0] & m, hv[1] & m, hv[2] & m, hv[3] & m));
+            sts128(E.x1 + po, make_uint4(hv[4] & m, hv[5] & m, hv[6] & m, hv[7] & m));
+            sts128(E.x0 + S.lo_off + po, make_uint4(lv[0] & m, lv[1] & m, lv[2] & m, lv[3] & m));
+            sts128(E.x1 + S.lo_off + po, make_uint4(lv[4] & m, lv[5] & m, lv[6] & m, lv[7] & m));
+          } else if (E.col_out && inside) {
+            uint4* o = reinterpret_cast<uint4*>(E.fout_col + (long long)r * E.row_halves);
+            o[0] = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+            o[1] = make_uint4(hv[4], hv[5], hv[6], hv[7]);
+            uint4* ol = reinterpret_cast<uint4*>(E.fout_col + p.plane_halves + (long long)r * E.row_halves);
+            ol[0] = make_uint4(lv[0], lv[1], lv[2], lv[3]);
+            ol[1] = make_uint4(lv[4], lv[5], lv[6], lv[7]);
+          }
+        }
+      }
+    } else if (EPI == EPI_RES_HEAD || EPI == EPI_RES_TO_GLOBAL) {
+      tmem_zero16(taddr);   // rows that fell out of the valid range hold stale partial sums: clean for the next region
+    }
+    fence_async_smem();   // T/X stores of this row -> async proxy (tensor core); X reads of this row -> before the TMA overwrite
+    if (PREFETCH) {
+      // X row r is dead for this region: one lane fetches the next region's quarter-row (2 halves x 512 B) by TMA; the
+      // x_ready barrier of the row group completes when the bytes have landed
+      __syncwarp();
+      if (elect_one_sync()) {
+        const uint32_t bar = S.bars + (uint32_t)(32 + grp) * 8;
+        mbar_arrive_expect_tx(bar, 1024u * P);
+        tma_load_q(E.nx0 + po, tmap, 0, E.nox_q, E.noy + r, E.nb, bar);
+        tma_load_q(E.nx1 + po, tmap, 1, E.nox_q, E.noy + r, E.nb, bar);
+        if (P == 2) {
+          tma_load_q(E.nx0 + S.lo_off + po, tmap, 0, E.nox_q, E.noy + r, E.nb + E.n_img, bar);
+          tma_load_q(E.nx1 + S.lo_off + po, tmap, 1, E.nox_q, E.noy + r, E.nb + E.n_img, bar);
+        }
+      }
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(S.bars + (uint32_t)(16 + grp) * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------- the pass kernel (persistent)
+template <bool LAST_PASS, int P, int GROUP>
+__global__ void __launch_bounds__(NTHREADS, 1)
+umma_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: no BSSY/BSYNC around role branches
+  const int nl = 2 * p.nblk, halo = 2 * p.nblk;
+  const int ng = (p.rh + GROUP - 1) / GROUP;
+  const bool tr = (p.trace != nullptr) && ((int)blockIdx.x == p.trace_block);
+  if (tr && tid == 0) p.trace[0] = clock64();
+  const uint32_t s0 = smem_u32(smem);
+  Smem S;
+  S.bars = s0 + SM_BARS; S.wts = s0 + SM_WTS;
+  S.plane_bytes = plane_bytes_of(p.rh);
+  {
+    const uint32_t pl = s0 + planes_offset(nl, P);
+    S.lo_off = 4 * S.plane_bytes;
+    S.X[0] = pl + 0 * S.plane_bytes + SLACK_PX * 16; S.X[1] = pl + 1 * S.plane_bytes + SLACK_PX * 16;
+    S.T[0] = pl + 2 * S.plane_bytes + SLACK_PX * 16; S.T[1] = pl + 3 * S.plane_bytes + SLACK_PX * 16;
+  }
+  uint8_t* g_planes = smem + planes_offset(nl, P);
+  float* s_head = reinterpret_cast<float*>(smem + SM_HEAD);
+  float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
+
+  // ---------------- one-time setup: barriers, TMEM, weights, the first region
+  // [0,16) mma_done[g] (tcgen05.commit); [16,32) epi_done[g]: every thread of the 128-pixel row arrives once per row of
+  // the group; [32,48) x_ready[g] (next region's X rows): one arrive.expect_tx per warp per row + the TMA bytes;
+  // [48] the first region's staging (one arrive.expect_tx per warp)
+  if (tid < 49) {
+    const int gi = tid & 15;
+    const int rows = max(0, min(GROUP, p.rh - gi * GROUP));
+    const uint32_t cnt = tid < 16 ? 1u : (tid < 32 ? (uint32_t)max(1, 128 * rows) : (tid < 48 ? (uint32_t)max(1, 4 * rows) : (uint32_t)(NTHREADS / 32)));
+    mbar_init(S.bars + tid * 8, cnt);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(s0 + SM_TMEM) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  for (int i = tid; i < nl * P * (W_LAYER_BYTES / 16); i += NTHREADS)
+    reinterpret_cast<uint4*>(smem + SM_WTS)[i] =
+        reinterpret_cast<const uint4*>(p.wumma + (size_t)(2 * p.blk0) * P * W_LAYER_BYTES)[i];
+  for (int i = tid; i < nl * C; i += NTHREADS) s_bias[i] = p.bias[(size_t)(2 * p.blk0) * C + i];
+  if (tid < C * 4) s_head[tid] = p.whead[tid];
+  // zero the plane slack (read by the -1/+1 tap shifts of the first / last row)
+  if (tid < 4 * P * 2 * SLACK_PX) {
+    const int pl = tid / (2 * SLACK_PX), k = tid % (2 * SLACK_PX);
+    const uint32_t off = (uint32_t)pl * S.plane_bytes + (k < SLACK_PX ? (uint32_t)k * 16u : S.plane_bytes - (uint32_t)(2 * SLACK_PX - k) * 16u);
+    *reinterpret_cast<uint4*>(g_planes + off) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_async_smem();   // barrier inits + slack zeros -> async proxy
+  __syncthreads();
+  {
+    // the first region: quarter-row boxes by TMA, spread over the warps' elected lanes, one barrier
+    const Region g0 = region_of(p, (int)blockIdx.x, halo);
+    const int nbox = p.rh * 8 * P;   // rows x 4 quarters x 2 halves x parts
+    const uint32_t bar = S.bars + 48 * 8;
+    if (elect_one_sync()) {
+      int mine = 0;
+      for (int i = warp; i < nbox; i += NTHREADS / 32) ++mine;
+      mbar_arrive_expect_tx(bar, (uint32_t)mine * 512u);
+      for (int i = warp; i < nbox; i += NTHREADS / 32) {
+        const int hf = i & 1, q = (i >> 1) & 3, r = (i >> 3) % p.rh, part = (i >> 3) / p.rh;
+        tma_load_q(S.X[hf] + part * S.lo_off + (uint32_t)(r * RW + q * 32) * 16u, &tmap, hf, g0.ox + q * 32, g0.oy + r,
+                   g0.b + part * p.n, bar);
+      }
+    }
+    mbar_wait(bar, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+  if (tr && tid == 0) p.trace[1] = clock64();
+
+  if (warp < EPI_WARPS) {
+    // ================= epilogue warps =================
+    const int quarter = warp & 3, set = warp >> 2;
+    const int c = quarter * 32 + lane;
+    EpiCtx E;
+    E.tq = tmem + ((uint32_t)(quarter * 32) << 16);
+    E.x0 = S.X[0] + (uint32_t)c * 16u; E.x1 = S.X[1] + (uint32_t)c * 16u;
+    E.t0 = S.T[0] + (uint32_t)c * 16u; E.t1 = S.T[1] + (uint32_t)c * 16u;
+    E.nx0 = S.X[0] + (uint32_t)(quarter * 32) * 16u; E.nx1 = S.X[1] + (uint32_t)(quarter * 32) * 16u;
+    E.he = p.he; E.h_img = p.h; E.n_img = p.n;
+    E.row_halves = (long long)p.we * 16; E.row_out = (long long)p.w * 3;
+    // zero this warp's share of the accumulator blocks, then release the MMA issuer
+    for (int blk = set; blk < p.rh + 2; blk += NSETS) tmem_zero16(E.tq + blk * 16);
+    tmem_wait_st();
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;\n" ::"r"(NTHREADS) : "memory");
+    uint32_t L = 0;   // global layer counter == mbarrier phase index
+    for (int it = (int)blockIdx.x; it < p.regions; it += (int)gridDim.x) {
+      const Region g = region_of(p, it, halo);
+      const bool has_next = (it + (int)gridDim.x) < p.regions;
+      {
+        const int gx = g.ox + c;
+        E.oy = g.oy;
+        E.col_ok = (gx >= 0) && (gx < p.we);
+        E.col_out = E.col_ok && (c >= halo) && (c < RW - halo) && (!LAST_PASS || gx < p.w);
+        E.fout_col = p.fout + ((((long long)g.b * p.he + g.oy) * p.we + gx) << 4);
+        E.out_col = reinterpret_cast<uint8_t*>(p.out) + ((((long long)g.b * p.h + g.oy) * p.w + gx) * 3) * (p.out_u8 ? 1 : 4);
+        if (has_next) {
+          const Region gn = region_of(p, it + (int)gridDim.x, halo);
+          E.nb = gn.b; E.noy = gn.oy; E.nox_q = gn.ox + quarter * 32;
+        }
+      }
+      for (int l = 0; l < nl; ++l, ++L) {
+        const float* s_bias_next = s_bias + (l + 1) * C;   // conv_a pre-loads the bias of the conv_b that follows
+        if ((l & 1) == 0) {
+          if (has_next && l == nl - 2) epilogue_layer<EPI_RELU_TO_T, true, P, GROUP>(p, &tmap, S, E, s_bias_next, s_head, set, l, L & 1u);
+          else epilogue_layer<EPI_RELU_TO_T, false, P, GROUP>(p, &tmap, S, E, s_bias_next, s_head, set, l, L & 1u);
+        } else if (l + 1 < nl) {
+          epilogue_layer<EPI_RES_TO_X, false, P, GROUP>(p, &tmap, S, E, s_bias_next, s_head, set, l, L & 1u);
+        } else {
+          epilogue_layer<LAST_PASS ? EPI_RES_HEAD : EPI_RES_TO_GLOBAL, false, P, GROUP>(p, &tmap, S, E, s_bias_next, s_head, set, l, L & 1u);
+        }
+        if (tr && lane == 0 && quarter == 0 && L < 8) p.trace[40 + set * 16 + L] = clock64();
+      }
+    }
+  } else {
+    // ================= MMA issuer warp =================
+    asm volatile("bar.sync 1, %0;\n" ::"r"(NTHREADS) : "memory");   // accumulators are zero
+    tc_fence_after();
+    if (elect_one_sync()) {
+      const uint32_t idesc = make_idesc_f16(128, 48);
+      // descriptors with the start-address field at pixel 0 / layer 0; the per-MMA part is an add of 16-byte units
+      const uint64_t adesc_x = make_desc(S.X[0], S.plane_bytes, 128), adesc_t = make_desc(S.T[0], S.plane_bytes, 128);
+      const uint64_t bdesc0 = make_desc(S.wts, 48 * 16, 128);
+      uint32_t L = 0;
+      int nreg = 0;   // regions finished by this CTA
+      for (int it = (int)blockIdx.x; it < p.regions; it += (int)gridDim.x, ++nreg) {
+        for (int l = 0; l < nl; ++l, ++L) {
+          const uint64_t ad0 = (l & 1) ? adesc_t : adesc_x;
+          const uint64_t bd0 = bdesc0 + (uint64_t)(l * P * (W_LAYER_BYTES / 16));
+          const int q_lo = l, q_hi = p.rh - l;
+          if (tr && L < 8) p.trace[8 + 2 * L] = clock64();
+          for (int grp = 0; grp < ng; ++grp) {
+            if (L > 0) {
+              const long long w0 = tr ? clock64() : 0;
+              const uint32_t par = (L - 1) & 1u;
+              if (grp == 0) mbar_wait(S.bars + (uint32_t)(16 + 0) * 8, par);
+              if (grp + 1 < ng) mbar_wait(S.bars + (uint32_t)(16 + grp + 1) * 8, par);
+              if (l == 0) {   // first layer of a later region: its X rows were fetched (cp.async) during the previous region
+                const uint32_t xpar = (uint32_t)(nreg - 1) & 1u;
+                if (grp == 0) mbar_wait(S.bars + (uint32_t)(32 + 0) * 8, xpar);
+                if (grp + 1 < ng) mbar_wait(S.bars + (uint32_t)(32 + grp + 1) * 8, xpar);
+                fence_async_smem();   // generic-proxy writes observed through the mbarrier -> async-proxy reads of the MMA
+              }
+              tc_fence_after();
+              if (tr && L < 8) p.trace[24 + L] += clock64() - w0;
+            }
+            const int row_end = min(grp * GROUP + GROUP, q_hi);
+            for (int q = max(grp * GROUP, q_lo); q < row_end; ++q) {
+              const uint64_t ad = ad0 + (uint64_t)(q * RW - 1);
+              const uint32_t d = tmem + (uint32_t)q * 16;
+              constexpr uint64_t BDX = 48 * 16 * 2 / 16, BLO = W_LAYER_BYTES / 16;   // next dx block / the lo weights, 16-byte units
+              if (P == 1) {
+                mma_f16_ss(d, ad, bd0, idesc, 1u);
+                mma_f16_ss(d, ad + 1, bd0 + BDX, idesc, 1u);
+                mma_f16_ss(d, ad + 2, bd0 + 2 * BDX, idesc, 1u);
+              } else {   // hi*hi + lo*hi + hi*lo: FP32-grade products (the F16X3 arithmetic)
+                const uint64_t alo = (uint64_t)(S.lo_off >> 4);
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  mma_f16_ss(d, ad + alo + dx, bd0 + dx * BDX, idesc, 1u);
+                  mma_f16_ss(d, ad + dx, bd0 + BLO + dx * BDX, idesc, 1u);
+                  mma_f16_ss(d, ad + dx, bd0 + dx * BDX, idesc, 1u);
+                }
+              }
+            }
+            umma_commit(S.bars + (uint32_t)grp * 8);
+          }
+          if (tr && L < 8) p.trace[9 + 2 * L] = clock64();
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (tr && tid == 0) p.trace[2] = clock64();
+  tc_fence_before();
+  __syncthreads();
+  if (tr && tid == 0) p.trace[3] = clock64();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+// ---------------------------------------------------------------------------- base conv -> fp16 NHWC16
+// normalise (utilities.py:449-461) + base conv k0 x k0, 3 -> 16 (backbone_resnet.py:258-262) over the work extent.
+// CTA tile 64 x 16 pixels; the uint8 halo tile goes to shared memory already normalised (exactly the reference's
+// x/255 - 0.5 in fp32): 0 outside the work extent (zero padding of the NORMALISED tensor), -0.5 on the raw-zero pow2
+// canvas (utilities.py:749).  Each thread owns 4 consecutive pixels x 16 cout.
+constexpr int BC_W = 64, BC_H = 16;
+__global__ void __launch_bounds__(256, 2)
+base_conv_f16_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, __half* __restrict__ out_lo /* or nullptr */,
+                     const float* __restrict__ w, int h, int wd, int he, int we, int k0) {
+  extern __shared__ __align__(16) float bsm[];
+  const int r0 = (k0 - 1) >> 1;
+  const int tw = BC_W + 2 * r0, th = BC_H + 2 * r0;
+  float* s_w = bsm;                              // [k0*k0*3][16]
+  float* s_in = bsm + k0 * k0 * 3 * C;           // [th][tw][3]
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * BC_W, y0 = blockIdx.y * BC_H, b = blockIdx.z;
+  for (int i = tid; i < k0 * k0 * 3 * C; i += 256) s_w[i] = w[i];
+  const uint8_t* img_b = img + (long long)b * h * wd * 3;
+  for (int i = tid; i < th * tw; i += 256) {
+    const int ly = i / tw, lx = i - ly * tw;
+    const int gy = y0 + ly - r0, gx = x0 + lx - r0;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (gy >= 0 && gy < he && gx >= 0 && gx < we) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      if (gy < h && gx < wd) {
+        const uint8_t* sp = img_b + ((long long)gy * wd + gx) * 3;
+        a0 = (float)sp[0]; a1 = (float)sp[1]; a2 = (float)sp[2];
+      }
+      v0 = __fsub_rn(__fdiv_rn(a0, 255.f), 0.5f);
+      v1 = __fsub_rn(__fdiv_rn(a1, 255.f), 0.5f);
+      v2 = __fsub_rn(__fdiv_rn(a2, 255.f), 0.5f);
+    }
+    s_in[i * 3 + 0] = v0; s_in[i * 3 + 1] = v1; s_in[i * 3 + 2] = v2;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][C];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[p][c] = 0.f;
+  for (int dy = 0; dy < k0; ++dy)
+    for (int dx = 0; dx < k0; ++dx) {
+      const float* ip = s_in + ((ty + dy) * tw + 4 * tx + dx) * 3;
+      const float* wp = s_w + (dy * k0 + dx) * 3 * C;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        float wv[C];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(wp + ci * C + 4 * q);
+          wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float xv = ip[p * 3 + ci];
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[p][c] = fmaf(xv, wv[c], acc[p][c]);
+        }
+      }
+    }
+  const int gy = y0 + ty;
+  if (gy >= he) return;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int gx = x0 + 4 * tx + p;
+    if (gx >= we) continue;
+    uint4 lo, hi;
+    lo.x = pack_h2(acc[p][0], acc[p][1]); lo.y = pack_h2(acc[p][2], acc[p][3]); lo.z = pack_h2(acc[p][4], acc[p][5]); lo.w = pack_h2(acc[p][6], acc[p][7]);
+    hi.x = pack_h2(acc[p][8], acc[p][9]); hi.y = pack_h2(acc[p][10], acc[p][11]); hi.z = pack_h2(acc[p][12], acc[p][13]); hi.w = pack_h2(acc[p][14], acc[p][15]);
+    const long long oo = (((long long)b * he + gy) * we + gx) << 4;
+    uint4* o = reinterpret_cast<uint4*>(out + oo);
+    o[0] = lo;
+    o[1] = hi;
+    if (out_lo) {   // the fp16 residual of every channel (F16X3 arithmetic)
+      uint4 l0, l1;
+      float2 f;
+      f = unpack_h2(lo.x); l0.x = pack_h2(acc[p][0] - f.x, acc[p][1] - f.y);
+      f = unpack_h2(lo.y); l0.y = pack_h2(acc[p][2] - f.x, acc[p][3] - f.y);
+      f = unpack_h2(lo.z); l0.z = pack_h2(acc[p][4] - f.x, acc[p][5] - f.y);
+      f = unpack_h2(lo.w); l0.w = pack_h2(acc[p][6] - f.x, acc[p][7] - f.y);
+      f = unpack_h2(hi.x); l1.x = pack_h2(acc[p][8] - f.x, acc[p][9] - f.y);
+      f = unpack_h2(hi.y); l1.y = pack_h2(acc[p][10] - f.x, acc[p][11] - f.y);
+      f = unpack_h2(hi.z); l1.z = pack_h2(acc[p][12] - f.x, acc[p][13] - f.y);
+      f = unpack_h2(hi.w); l1.w = pack_h2(acc[p][14] - f.x, acc[p][15] - f.y);
+      uint4* ol = reinterpret_cast<uint4*>(out_lo + oo);
+      ol[0] = l0;
+      ol[1] = l1;
+    }
+  }
+}
+
+}  // namespace umma3
+
+// ------------------------------------------------------------------------------------
+// host: pass planning
+// ------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_feature_tmap_x3(CUtensorMap* out, const __half* base, const Extent& e, int parts) {
+  static tmap_encode_fn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    BF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return BFCNN_ERR_CUDA;
+    }
+    enc = reinterpret_cast<tmap_encode_fn>(fn);
+  }
+  // fp16 NHWC16 viewed as {ch8, half, x, y, n}
+  const cuuint64_t dims[5] = {8, 2, (cuuint64_t)e.we, (cuuint64_t)e.he, (cuuint64_t)e.n * parts};   // lo planes follow the hi planes
+  const cuuint64_t strides[4] = {16, 32, (cuuint64_t)e.we * 32, (cuuint64_t)e.he * e.we * 32};
+  const cuuint32_t box[5] = {8, 1, 32, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (extent %d x %d x %d)", (int)r, e.n, e.he, e.we);
+    return BFCNN_ERR_CUDA;
+  }
+  return BFCNN_OK;
+}
+
+static int env_int_u3(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+int run_fused_stack_umma_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e, cudaStream_t st) {
+  using namespace umma3;
+  constexpr int P = 2;   // 1: fp16 operands (F16); 2: fp16 hi + lo operands, 3 MMAs per product (F16X3, FP32-grade)
+  const int N = h->arch.no_layers, k0 = h->arch.base_kernel;
+  if (N < 1) {
+    set_error("the fused tensor-core stack needs no_layers >= 1 (use BFCNN_PREC_FP32)");
+    return BFCNN_ERR_UNSUPPORTED;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    BF_CUDA(cudaFuncSetAttribute((const void*)umma_pass_kernel<false, 2, GROUP_X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    BF_CUDA(cudaFuncSetAttribute((const void*)umma_pass_kernel<true, 2, GROUP_X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    attr_set = true;
+  }
+  int kb = (P == 1) ? env_int_u3("BFCNN_KB_UMMA", 2) : env_int_u3("BFCNN_KB_UMMA_X3", 1);
+  kb = std::max(1, std::min(std::min(kb, N), MAX_LAYERS / 2));
+  const int passes = (N + kb - 1) / kb;
+  const size_t feat_halves = (size_t)e.n * e.he * e.we * C;
+  BF_CHECK(h->ws_feat[1].reserve(feat_halves * P * sizeof(__half)));
+  if (passes > 1) BF_CHECK(h->ws_feat[0].reserve(feat_halves * P * sizeof(__half)));
+
+  // pass "-1": base conv into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
+  {
+    const int r0 = (k0 - 1) / 2;
+    const size_t bsm = (size_t)(k0 * k0 * 3 * C + (BC_H + 2 * r0) * (BC_W + 2 * r0) * 3) * sizeof(float);
+    dim3 grid((e.we + BC_W - 1) / BC_W, (e.he + BC_H - 1) / BC_H, e.n);
+    BF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "image too large for the base conv grid");
+    __half* b_hi = h->ws_feat[1].as<__half>();
+    base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, b_hi, P == 2 ? b_hi + feat_halves : nullptr, h->d_base_f32.as<float>(), e.h, e.w,
+                                                 e.he, e.we, k0);
+    h->launches++;
+    BF_CUDA(cudaGetLastError());
+  }
+  for (int ps = 0; ps < passes; ++ps) {
+    Params p;
+    p.out = d_out;
+    p.fin = h->ws_feat[(ps + 1) & 1].as<__half>();
+    p.fout = (ps + 1 < passes) ? h->ws_feat[ps & 1].as<__half>() : nullptr;
+    p.wumma = (P == 1) ? h->d_conv_umma.as<uint8_t>() : h->d_conv_umma_x3.as<uint8_t>();
+    p.plane_halves = (long long)feat_halves;
+    p.bias = h->d_bias_f32.as<float>();
+    p.whead = h->d_head_f32.as<float>();
+    p.n = e.n; p.h = e.h; p.w = e.w; p.he = e.he; p.we = e.we;
+    p.blk0 = ps * kb;
+    p.nblk = std::min(kb, N - p.blk0);
+    p.last = (ps + 1 == passes); p.out_u8 = out_u8 ? 1 : 0;
+    const int nl = 2 * p.nblk, halo = 2 * p.nblk;
+    // shared-memory budget -> region rows (<= MAX_RH by TMEM capacity), a whole number of row groups when possible
+    const size_t fixed = planes_offset(nl, P) + 64;
+    int rh_max = MAX_RH;
+    while (rh_max > 0 && fixed + (size_t)4 * P * plane_bytes_of(rh_max) > (size_t)MAX_SMEM) --rh_max;
+    const int rows_needed = p.last ? e.h : e.he;
+    const int cols_needed = p.last ? e.w : e.we;
+    int th_max = rh_max - 2 * halo;
+    p.tw = RW - 2 * halo;
+    if (th_max < 1 || p.tw < 1) {
+      set_error("fused tcgen05 pass does not fit (kb=%d)", kb);
+      return BFCNN_ERR_INTERNAL;
+    }
+    const int GROUP = (P == 1) ? GROUP_F16 : GROUP_X3;
+    p.grp = GROUP;
+    if (rows_needed > th_max && (rh_max / GROUP) * GROUP - 2 * halo >= 1) th_max = (rh_max / GROUP) * GROUP - 2 * halo;
+    p.tiles_y = (rows_needed + th_max - 1) / th_max;
+    p.th = (rows_needed + p.tiles_y - 1) / p.tiles_y;   // balance the tile rows
+    p.rh = p.th + 2 * halo;
+    p.tiles_x = (cols_needed + p.tw - 1) / p.tw;
+    const size_t smem = planes_offset(nl, P) + (size_t)4 * P * plane_bytes_of(p.rh);
+    if (smem > (size_t)MAX_SMEM || p.rh > MAX_RH) {
+      set_error("internal: tcgen05 pass smem %zu rh %d", smem, p.rh);
+      return BFCNN_ERR_INTERNAL;
+    }
+    const long long regions = (long long)p.tiles_x * p.tiles_y * e.n;
+    BF_REQUIRE(regions < (1ll << 31), "too many tiles");
+    p.regions = (int)regions;
+    const int grid = (int)std::min<long long>(regions, h->sm_count);
+    static const int trace_on = env_int_u3("BFCNN_UMMA_TRACE", 0);
+    p.trace = nullptr; p.trace_block = 0;
+    if (trace_on && ps == std::min(1, passes - 1)) {
+      BF_CHECK(h->ws_feat[2].reserve(256 * sizeof(long long)));
+      BF_CUDA(cudaMemsetAsync(h->ws_feat[2].p, 0, 256 * sizeof(long long), st));
+      p.trace = h->ws_feat[2].as<long long>(); p.trace_block = grid / 2;
+    }
+    CUtensorMap tmap;
+    BF_CHECK(make_feature_tmap_x3(&tmap, p.fin, e, P));
+    if (p.last) umma_pass_kernel<true, 2, GROUP_X3><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
+    else umma_pass_kernel<false, 2, GROUP_X3><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
+    if (p.trace) {
+      long long t[256];
+      BF_CUDA(cudaMemcpyAsync(t, p.trace, sizeof(t), cudaMemcpyDeviceToHost, st));
+      BF_CUDA(cudaStreamSynchronize(st));
+      fprintf(stderr, "[umma trace] pass %d rh %d nl %d regions %d grid %d: setup %lld total %lld (%.0f per region)\n", ps, p.rh, nl,
+              p.regions, grid, t[1] - t[0], t[3] - t[0], (double)(t[3] - t[0]) / ((p.regions + grid - 1) / grid));
+      for (int L = 0; L < 8; ++L) {
+        fprintf(stderr, "  layer %d: mma issue [%lld .. %lld] waited %lld |", L, t[8 + 2 * L] - t[0], t[9 + 2 * L] - t[0], t[24 + L]);
+        for (int s = 0; s < NSETS; ++s) fprintf(stderr, " epi%d end %lld", s, t[40 + s * 16 + L] - t[0]);
+        fprintf(stderr, "\n");
+      }
+    }
+    h->launches++;
+    BF_CUDA(cudaGetLastError());
+  }
+  return BFCNN_OK;
+}
+
+}  // namespace bfcnn

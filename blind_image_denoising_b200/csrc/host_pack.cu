@@ -130,6 +130,21 @@ int pack_weights(bfcnn_handle* h) {
           umma[off] = __float2half_rn(conv[((size_t)l * 9 + tap) * C * C + k * C + co]);
         }
 
+  // hi/lo variant for the F16X3 arithmetic on tcgen05: per conv [hi][lo], each as above
+  std::vector<__half> umma3((size_t)2 * N * 2 * 3 * 48 * 16);
+  for (int l = 0; l < 2 * N; ++l)
+    for (int dxi = 0; dxi < 3; ++dxi)
+      for (int n = 0; n < 48; ++n)
+        for (int k = 0; k < 16; ++k) {
+          const int j = n / 16, co = n % 16, dy = 1 - j;
+          const int tap = (dy + 1) * 3 + dxi;
+          const size_t off = (size_t)dxi * 768 + (k / 8) * 384 + (n / 8) * 64 + (n % 8) * 8 + (k % 8);
+          const float v0 = conv[((size_t)l * 9 + tap) * C * C + k * C + co];
+          const __half hi = __float2half_rn(v0);
+          umma3[(size_t)(l * 2 + 0) * 2304 + off] = hi;
+          umma3[(size_t)(l * 2 + 1) * 2304 + off] = __float2half_rn(v0 - __half2float(hi));
+        }
+
   BF_CUDA(cudaSetDevice(h->device));
   const size_t nbase = (size_t)k0 * k0 * 3 * C;
   BF_CHECK(h->d_vars.reserve(L.total * sizeof(float)));
@@ -139,6 +154,7 @@ int pack_weights(bfcnn_handle* h) {
   BF_CHECK(h->d_head_f32.reserve(head.size() * sizeof(float)));
   BF_CHECK(h->d_conv_frag.reserve(std::max<size_t>(frag.size(), 1) * sizeof(uint32_t)));
   BF_CHECK(h->d_conv_umma.reserve(std::max<size_t>(umma.size(), 1) * sizeof(__half)));
+  BF_CHECK(h->d_conv_umma_x3.reserve(std::max<size_t>(umma3.size(), 1) * sizeof(__half)));
   BF_CUDA(cudaMemcpy(h->d_vars.p, v, L.total * sizeof(float), cudaMemcpyHostToDevice));
   BF_CUDA(cudaMemcpy(h->d_base_f32.p, v + L.base, nbase * sizeof(float), cudaMemcpyHostToDevice));
   if (N > 0) {
@@ -146,6 +162,7 @@ int pack_weights(bfcnn_handle* h) {
     BF_CUDA(cudaMemcpy(h->d_bias_f32.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
     BF_CUDA(cudaMemcpy(h->d_conv_frag.p, frag.data(), frag.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     BF_CUDA(cudaMemcpy(h->d_conv_umma.p, umma.data(), umma.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    BF_CUDA(cudaMemcpy(h->d_conv_umma_x3.p, umma3.data(), umma3.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
   BF_CUDA(cudaMemcpy(h->d_head_f32.p, head.data(), head.size() * sizeof(float), cudaMemcpyHostToDevice));
   h->packed_valid = true;

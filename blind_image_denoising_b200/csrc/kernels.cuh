@@ -35,6 +35,9 @@ int run_fused_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_
 // ---- fused_umma.cu: the fused stack on tcgen05 (UMMA, accumulators in TMEM), F16
 int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                          cudaStream_t st);
+// ---- fused_umma_x3.cu: the same stack in the F16X3 arithmetic (fp16 hi/lo operand parts, FP32-grade)
+int run_fused_stack_umma_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
+                            cudaStream_t st);
 
 // ---- train.cu
 int run_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, float* noisy_f32, int n,

@@ -11,9 +11,11 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-GATES = {"fp32": (0.5, 0.05), "f16x3": (0.5, 0.05), "f16": (2.0, 0.25), "f16_mma_sync": (2.0, 0.25)}
+GATES = {"fp32": (0.5, 0.05), "f16x3": (0.5, 0.05), "f16x3_mma_sync": (0.5, 0.05), "f16": (2.0, 0.25),
+         "f16_mma_sync": (2.0, 0.25)}
 # what the kernels actually achieve (regression guard, tighter than the gate)
-TIGHT = {"fp32": (0.02, 0.002), "f16x3": (0.02, 0.002), "f16": (2.0, 0.25), "f16_mma_sync": (2.0, 0.25)}
+TIGHT = {"fp32": (0.02, 0.002), "f16x3": (0.02, 0.002), "f16x3_mma_sync": (0.02, 0.002), "f16": (2.0, 0.25),
+         "f16_mma_sync": (2.0, 0.25)}
 
 
 def _model(n_layers, **kw):
@@ -35,12 +37,12 @@ def _check(y, yref, u8, u8ref, prec):
     assert mx <= GATES[prec][0] and mean <= GATES[prec][1], (prec, mx, mean)
     assert mx <= TIGHT[prec][0] and mean <= TIGHT[prec][1], ("regression", prec, mx, mean)
     du = np.abs(u8.astype(np.int32) - u8ref.astype(np.int32))
-    f16 = prec.startswith("f16") and prec != "f16x3"
+    f16 = prec in ("f16", "f16_mma_sync")
     assert du.max() <= (2 if f16 else 1)
     assert (du > 0).mean() < (0.25 if f16 else 0.01)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16", "f16_mma_sync"])
+@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16x3_mma_sync", "f16", "f16_mma_sync"])
 @pytest.mark.parametrize("n_layers,shape", [
     (1, (1, 32, 32, 3)),
     (6, (2, 64, 64, 3)),

@@ -11,7 +11,7 @@ for n_layers, shape in [(2, (1, 40, 200, 3)), (6, (2, 96, 80, 3)), (18, (1, 150,
     v = bf.synthetic_variables(arch, 0)
     x = np.random.default_rng(1).integers(0, 256, size=shape, dtype=np.uint8)
     yref, _ = O.denoise(v, x, pad_pow2=True)
-    for prec in ("f16", "f16_mma_sync"):
+    for prec in ("f16", "f16_mma_sync", "f16x3", "f16x3_mma_sync"):
         m = bf.Denoiser(arch, v, precision=prec)
         y = m(x, return_float=True)
         d = np.abs(y - yref)
@@ -22,7 +22,7 @@ arch = bf.Arch(no_layers=18)
 v = bf.synthetic_variables(arch, 0)
 x = torch.from_numpy(np.random.default_rng(0).integers(0, 256, size=(2, 2160, 3840, 3), dtype=np.uint8)).cuda()
 out = torch.empty_like(x)
-for prec in ("f16", "f16_mma_sync"):
+for prec in ("f16", "f16_mma_sync", "f16x3", "f16x3_mma_sync"):
     m = bf.Denoiser(arch, v, precision=prec, pad_pow2=False)
     for _ in range(2):
         m(x, out=out)
@@ -33,8 +33,8 @@ for prec in ("f16", "f16_mma_sync"):
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 5
     print(f"{prec}: {dt*1e3:.2f} ms per 2 frames -> {2*2160*3840/1e6/dt:.0f} MP/s (stack {m.last_stack_ms():.2f} ms)", flush=True)
-    res = out.clone() if prec == "f16" else res
-    if prec != "f16":
+    res = out.clone() if prec in ("f16", "f16x3") else res
+    if prec.endswith("mma_sync"):
         dd = (out.int() - res.int()).abs()
         print("u8 diff umma vs mma.sync: max", int(dd.max()), "frac>0", float((dd > 0).float().mean()))
     m.close()
