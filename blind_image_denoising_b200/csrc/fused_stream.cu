@@ -1,0 +1,450 @@
+// fused_stream.cu -- the fused conv-BN-ReLU residual stack on tcgen05 as a ROW-STREAMING pipeline (sm_100a).
+//
+// Same arithmetic and operand layouts as fused_umma.cu (M = 128 pixels of one image row per MMA, channel-half planes in
+// the SWIZZLE_NONE K-major layout so that a dx tap is a descriptor shift, N = 48 dy-scatter into three accumulator
+// blocks), but the work unit is no longer a 128 x rh region with a vertical halo that every layer recomputes.  A CTA
+// owns a 128-pixel-wide column strip segment and streams DOWN it: all 2*nblk conv layers of the pass are in flight at
+// once, layer l+1 trailing layer l by LAG = 3 row groups, every layer advancing one group of 2 rows per step.  Only the
+// horizontal halo (2*nblk columns per side) is recomputed: 94 % of the MMAs are useful at nblk = 2 (the region kernel:
+// 71 %), and a segment is as tall as the host cares to make it, so 148 CTAs get equal shares of the frame.
+//
+//   step s:  MMA issuer      layer l multiplies its input rows {2g, 2g+1}, g = s - 3l           (one elected thread)
+//            epilogue warps  layer l drains its output rows    {2w, 2w+1}, w = s - 3l - 1       (16 warps)
+//            TMA producer    input rows of layer 0, K0 groups deep ring                          (one elected thread)
+//
+//   * Shared memory holds four row RINGS (fp16, two channel-half planes each): X0 (TMA input of block 0, also the
+//     residual of block 0), T0 = ReLU(conv_a), X1 (block-0 output = block-1 input and residual), T1.
+//   * The 32 TMEM accumulator blocks (16 columns each) are one ring: row r of layer l lives in block (r + 14 l) & 31.
+//     At any step a layer has at most 7 rows touched-but-not-drained, the four windows sit 8 blocks apart and move
+//     together.  tcgen05.mma faults when its D columns run past column 511 (tools/umma_probe5.cu), so an MMA whose
+//     three blocks straddle the ring end is issued as N = 32 + N = 16 (2 input rows in 32); every output row still
+//     receives its nine partial products in the same order, so results do not depend on where a row sits in the ring
+//     -- strips, crops and whole frames stay bit-identical (tests/test_inference_gpu.py).
+//   * mbarriers: mma_done[s & 1] (tcgen05.commit after the MMAs of step s), epi_done[s & 1] (every epilogue thread,
+//     end of step s).  The issuer of step s waits for epi_done(s - 2), so the epilogue of step s - 1 overlaps the MMAs
+//     of step s; LAG = 3 is the smallest lag for which layer l+1's input group is already written by then.
+//     x_full[k] / x_free[k] (k < K0) couple the TMA producer to the issuer and to the block-0 residual readers.
+//   * Rows outside a layer's valid cone (the first / last rows of a segment, the halo columns) are computed and
+//     ignored; rows / columns outside the work extent are forced to zero by every epilogue (per-layer "same" padding).
+//
+// Reference arithmetic: module_denoiser.py:53-73, backbone_blocks.py:167-246 (block), model.py:297-342 (head),
+// utilities.py:435-443 (denormalise).
+#include "kernels.cuh"
+#include "umma_ptx.cuh"
+
+namespace bfcnn {
+namespace ustream {
+
+using namespace tc5;
+
+constexpr int RW = 128;                 // strip width == UMMA M
+constexpr int SLACK_PX = 8;             // pixels of slack before/after every plane (tap shift -1/+1)
+constexpr int EPI_WARPS = 16;           // 4 sets x 4 TMEM lane quarters
+constexpr int WARP_MMA = 16;          // warp 17 is the TMA producer
+constexpr int NTHREADS = 32 * 18;
+constexpr int LAG = 3;                  // steps between consecutive layers
+constexpr int K0 = 12;                  // X0 ring: groups of 2 rows (TMA prefetch depth)
+constexpr int KX = 8;                   // X1 ring groups: written at step w+4, last read (residual) at step w+10
+constexpr int KT = 2;                   // T rings: written at step w+1, read by the MMAs of step w+3
+constexpr int ROW_BYTES = RW * 16;      // one row of one channel-half plane
+constexpr int GROUP_BYTES = 2 * ROW_BYTES;
+constexpr int W_LAYER_BYTES = 3 * 48 * 16 * 2;   // B operand of one conv: [dx 3][N 48][K 16] fp16
+constexpr int MAX_SMEM = 232448;
+constexpr int MAX_NL = 4;
+constexpr int MIN_SHARE = 24;           // rows per CTA below which fewer CTAs are launched
+
+// barriers (8 B each)
+constexpr uint32_t BAR_MMA = 0, BAR_EPI = 2, BAR_XFULL = 4, BAR_XFREE = 4 + K0, NBARS = 4 + 2 * K0;
+constexpr uint32_t SM_BARS = 0, SM_TMEM = 512, SM_HEAD = 528, SM_BIAS = 784, SM_WTS = 1152;
+
+__host__ __device__ inline uint32_t plane_bytes_of(int rows) { return (uint32_t)(rows * RW + 2 * SLACK_PX) * 16u; }
+__host__ __device__ inline uint32_t rings_offset(int nl) { return (SM_WTS + (uint32_t)nl * W_LAYER_BYTES + 127u) & ~127u; }
+__host__ __device__ inline uint32_t smem_bytes(int nl) {
+  uint32_t b = rings_offset(nl) + 2 * plane_bytes_of(2 * K0) + 2 * plane_bytes_of(2 * KT);
+  if (nl > 2) b += 2 * plane_bytes_of(2 * KX) + 2 * plane_bytes_of(2 * KT);
+  return b;
+}
+
+struct Params {
+  const __half* fin;       // [n][he][we][16]  input feature map of this pass
+  __half* fout;            // [n][he][we][16]
+  void* out;               // [n][h][w][3] uint8 or float
+  const uint8_t* wumma;    // [2N][W_LAYER_BYTES]
+  const float* bias;       // [2N][16]
+  const float* whead;      // [16][4]
+  int n, h, w, he, we;
+  int blk0, nblk;
+  int out_u8;
+  int tw, tiles_x, rows_needed;   // output columns per strip, strips per image, output rows per strip
+  long long total_rows, share;    // linearised (image, strip, row) space and the rows of it each CTA owns
+};
+
+struct Seg { int b, j, ya, yb; };
+// the next segment of the linear row range [a, r1): rows [ya, yb) of strip j of image b
+__device__ __forceinline__ Seg seg_at(const Params& p, long long a, long long r1) {
+  Seg s;
+  const long long strip = a / p.rows_needed;
+  s.ya = (int)(a - strip * p.rows_needed);
+  s.yb = (int)min((long long)p.rows_needed, (long long)s.ya + (r1 - a));
+  s.b = (int)(strip / p.tiles_x);
+  s.j = (int)(strip - (long long)s.b * p.tiles_x);
+  return s;
+}
+
+// rings: byte address of pixel 0, row slot 0, channel half 0; the other half is +plane
+struct Rings {
+  uint32_t x0, t0, x1, t1;
+  uint32_t x0_plane, t_plane, x1_plane;
+};
+
+enum Kind { KIND_A = 0, KIND_B_TO_X = 1, KIND_B_OUT = 2 };
+
+struct EpiCtx {
+  uint32_t tq;             // TMEM address of this warp's lane quarter, column 0
+  uint32_t pix;            // byte offset of this thread's pixel inside a ring row
+  int y00, he, h_img;      // row rho of the segment is image row y00 + rho
+  int P, nl;
+  bool col_ok, col_out;
+  __half* fout_col;        // feature-map address of (b, y00, gx); row rho adds rho * row_halves
+  uint8_t* out_col;        // output address of (b, y00, gx)
+  long long row_halves, row_out;
+  int gb0;                 // X0 ring group slot of the segment's group 0
+};
+
+// one (layer, row) task of one warp: 32 pixels of output row rho of layer l
+template <int KIND, bool LAST_PASS>
+__device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const EpiCtx& E, uint32_t bars, const float (&bias)[16],
+                                         const float* s_head, int l, int rho) {
+  const uint32_t taddr = E.tq + (uint32_t)((rho + 14 * l) & 31) * 16u;
+  uint32_t v[16];
+  tmem_ld16_issue(taddr, v);
+  const bool inside = E.col_ok && ((unsigned)(E.y00 + rho) < (unsigned)E.he);
+  if (KIND == KIND_A) {
+    tmem_ld_wait(v);
+    tmem_zero16(taddr);
+    const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
+    uint4 lo, hi;
+    lo.x = relu_h2(pack_h2(__uint_as_float(v[0]), __uint_as_float(v[1]))) & m; lo.y = relu_h2(pack_h2(__uint_as_float(v[2]), __uint_as_float(v[3]))) & m;
+    lo.z = relu_h2(pack_h2(__uint_as_float(v[4]), __uint_as_float(v[5]))) & m; lo.w = relu_h2(pack_h2(__uint_as_float(v[6]), __uint_as_float(v[7]))) & m;
+    hi.x = relu_h2(pack_h2(__uint_as_float(v[8]), __uint_as_float(v[9]))) & m; hi.y = relu_h2(pack_h2(__uint_as_float(v[10]), __uint_as_float(v[11]))) & m;
+    hi.z = relu_h2(pack_h2(__uint_as_float(v[12]), __uint_as_float(v[13]))) & m; hi.w = relu_h2(pack_h2(__uint_as_float(v[14]), __uint_as_float(v[15]))) & m;
+    const uint32_t dst = (l == 0 ? R.t0 : R.t1) + (uint32_t)(rho & (2 * KT - 1)) * ROW_BYTES + E.pix;
+    sts128(dst, lo);
+    sts128(dst + R.t_plane, hi);
+  } else {
+    // residual: X of this block (fp16) + the BN constant b' + the accumulator
+    uint32_t xsrc, xplane;
+    if (l == 1) {
+      const int w = rho >> 1;
+      xsrc = R.x0 + (uint32_t)(((E.gb0 + w) % K0) * 2 + (rho & 1)) * ROW_BYTES + E.pix;
+      xplane = R.x0_plane;
+    } else {
+      xsrc = R.x1 + (uint32_t)(rho & (2 * KX - 1)) * ROW_BYTES + E.pix;
+      xplane = R.x1_plane;
+    }
+    const uint4 xa = lds128(xsrc), xb = lds128(xsrc + xplane);
+    tmem_ld_wait(v);
+    tmem_zero16(taddr);
+    float f[16];
+    {
+      const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 xv = unpack_h2(xs[i]);
+        f[2 * i] = __uint_as_float(v[2 * i]) + (xv.x + bias[2 * i]);
+        f[2 * i + 1] = __uint_as_float(v[2 * i + 1]) + (xv.y + bias[2 * i + 1]);
+      }
+    }
+    if (KIND == KIND_B_OUT && LAST_PASS) {   // collapsed 1x1 head + tanh(2y)*0.51 + denormalise (+ round + uint8)
+      if (E.col_out && inside && rho >= E.nl && rho < E.P - E.nl && (E.y00 + rho) < E.h_img) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          const float4 wv = *reinterpret_cast<const float4*>(s_head + ch * 4);
+          s0 = fmaf(f[ch], wv.x, s0); s1 = fmaf(f[ch], wv.y, s1); s2 = fmaf(f[ch], wv.z, s2);
+        }
+        const float r0o = head_activation(s0), r1o = head_activation(s1), r2o = head_activation(s2);
+        if (p.out_u8) {
+          uint8_t* d = E.out_col + (long long)rho * E.row_out;
+          d[0] = (uint8_t)__float2int_rn(r0o); d[1] = (uint8_t)__float2int_rn(r1o); d[2] = (uint8_t)__float2int_rn(r2o);
+        } else {
+          float* d = reinterpret_cast<float*>(E.out_col) + (long long)rho * E.row_out;
+          d[0] = r0o; d[1] = r1o; d[2] = r2o;
+        }
+      }
+    } else {
+      uint4 lo, hi;
+      lo.x = pack_h2(f[0], f[1]); lo.y = pack_h2(f[2], f[3]); lo.z = pack_h2(f[4], f[5]); lo.w = pack_h2(f[6], f[7]);
+      hi.x = pack_h2(f[8], f[9]); hi.y = pack_h2(f[10], f[11]); hi.z = pack_h2(f[12], f[13]); hi.w = pack_h2(f[14], f[15]);
+      if (KIND == KIND_B_TO_X) {
+        const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
+        lo.x &= m; lo.y &= m; lo.z &= m; lo.w &= m; hi.x &= m; hi.y &= m; hi.z &= m; hi.w &= m;
+        const uint32_t dst = R.x1 + (uint32_t)(rho & (2 * KX - 1)) * ROW_BYTES + E.pix;
+        sts128(dst, lo);
+        sts128(dst + R.x1_plane, hi);
+      } else if (E.col_out && inside && rho >= E.nl && rho < E.P - E.nl) {
+        uint4* o = reinterpret_cast<uint4*>(E.fout_col + (long long)rho * E.row_halves);
+        o[0] = lo;
+        o[1] = hi;
+      }
+    }
+    if (l == 1) {
+      // this thread's X0 pixel of the row is consumed: (generic read -> async-proxy TMA overwrite)
+      fence_async_smem();
+      mbar_arrive(bars + (BAR_XFREE + (uint32_t)((E.gb0 + (rho >> 1)) % K0)) * 8);
+    }
+  }
+}
+
+template <bool LAST_PASS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
+  const int nl = 2 * p.nblk, halo = nl;
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t bars = s0 + SM_BARS;
+  float* s_head = reinterpret_cast<float*>(smem + SM_HEAD);
+  float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
+  Rings R;
+  {
+    uint32_t o = s0 + rings_offset(nl);
+    R.x0_plane = plane_bytes_of(2 * K0); R.t_plane = plane_bytes_of(2 * KT); R.x1_plane = plane_bytes_of(2 * KX);
+    R.x0 = o + SLACK_PX * 16; o += 2 * R.x0_plane;
+    R.t0 = o + SLACK_PX * 16; o += 2 * R.t_plane;
+    R.x1 = o + SLACK_PX * 16; o += 2 * R.x1_plane;
+    R.t1 = o + SLACK_PX * 16;
+  }
+  const long long r0 = (long long)blockIdx.x * p.share, r1 = min(p.total_rows, r0 + p.share);
+
+  // ---------------- one-time setup: barriers, TMEM, weights, zeroed rings
+  if (tid < (int)NBARS) {
+    const uint32_t cnt = tid < (int)BAR_EPI ? 1u : (tid < (int)BAR_XFULL ? (uint32_t)(EPI_WARPS * 32) : (tid < (int)BAR_XFREE ? 1u : 256u));
+    mbar_init(bars + tid * 8, cnt);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(s0 + SM_TMEM) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  for (int i = tid; i < nl * (W_LAYER_BYTES / 16); i += NTHREADS)
+    reinterpret_cast<uint4*>(smem + SM_WTS)[i] = reinterpret_cast<const uint4*>(p.wumma + (size_t)(2 * p.blk0) * W_LAYER_BYTES)[i];
+  for (int i = tid; i < nl * C; i += NTHREADS) s_bias[i] = p.bias[(size_t)(2 * p.blk0) * C + i];
+  if (tid < C * 4) s_head[tid] = p.whead[tid];
+  {
+    // stale shared memory may hold NaN patterns; rows outside the valid cone are multiplied (and ignored), so start clean
+    const uint32_t ro = rings_offset(nl), n16 = (smem_bytes(nl) - ro) / 16;
+    for (uint32_t i = tid; i < n16; i += NTHREADS) reinterpret_cast<uint4*>(smem + ro)[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_async_smem();   // barrier inits + zeros -> async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+
+  if (warp < EPI_WARPS) {
+    // ================= epilogue warps =================
+    const int quarter = warp & 3, set = warp >> 2;
+    const int c = quarter * 32 + lane;
+    EpiCtx E;
+    E.tq = tmem + ((uint32_t)(quarter * 32) << 16);
+    E.pix = (uint32_t)c * 16u;
+    E.he = p.he; E.h_img = p.h; E.nl = nl;
+    E.row_halves = (long long)p.we * 16; E.row_out = (long long)p.w * 3;
+    // this warp's tasks of a step: t = set, set + 4 (< 2 nl): row parity t / nl of layer (t + parity) % nl
+    int tl[2], tpar[2], ntask = 0;
+    for (int t = set; t < 2 * nl && ntask < 2; t += 4) { tpar[ntask] = t / nl; tl[ntask] = (t + tpar[ntask]) % nl; ++ntask; }
+    float bias[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bias[i] = 0.f;
+    for (int k = 0; k < ntask; ++k)
+      if (tl[k] & 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bias[i] = s_bias[tl[k] * C + i];   // at most one conv_b layer per warp (nl = 2, 4)
+      }
+    for (int blk = set; blk < 32; blk += 4) tmem_zero16(E.tq + blk * 16);
+    tmem_wait_st();
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;\n" ::"r"(32 * (EPI_WARPS + 1)) : "memory");   // accumulators are zero -> MMA issuer
+    uint32_t S = 0;
+    long long gg = 0;
+    for (long long a = r0; a < r1;) {
+      const Seg sg = seg_at(p, a, r1);
+      a += sg.yb - sg.ya;
+      const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
+      {
+        const int gx = sg.j * p.tw - halo + c;
+        E.y00 = sg.ya - nl; E.P = P;
+        E.col_ok = (gx >= 0) && (gx < p.we);
+        E.col_out = E.col_ok && (c >= halo) && (c < RW - halo) && (!LAST_PASS || gx < p.w);
+        E.fout_col = p.fout + ((((long long)sg.b * p.he + E.y00) * p.we + gx) << 4);
+        E.out_col = reinterpret_cast<uint8_t*>(p.out) + ((((long long)sg.b * p.h + E.y00) * p.w + gx) * 3) * (p.out_u8 ? 1 : 4);
+        E.gb0 = (int)(gg % K0);
+      }
+      for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        mbar_wait(bars + (BAR_MMA + (S & 1u)) * 8, (S >> 1) & 1u);
+        tc_fence_after();
+        for (int k = 0; k < ntask; ++k) {
+          const int l = tl[k], w = sr - LAG * l - 1;
+          if (w < 0 || w >= Gm) continue;
+          const int rho = 2 * w + tpar[k];
+          if ((l & 1) == 0) epi_task<KIND_A, LAST_PASS>(p, R, E, bars, bias, s_head, l, rho);
+          else if (l + 1 < nl) epi_task<KIND_B_TO_X, LAST_PASS>(p, R, E, bars, bias, s_head, l, rho);
+          else epi_task<KIND_B_OUT, LAST_PASS>(p, R, E, bars, bias, s_head, l, rho);
+        }
+        fence_async_smem();   // T / X stores of this step -> async proxy (tensor core reads)
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bars + (BAR_EPI + (S & 1u)) * 8);
+      }
+      gg += Gm;
+    }
+  } else if (warp == WARP_MMA) {
+    // ================= MMA issuer =================
+    asm volatile("bar.sync 1, %0;\n" ::"r"(32 * (EPI_WARPS + 1)) : "memory");
+    tc_fence_after();
+    if (elect_one_sync()) {
+      const uint32_t idesc0 = make_idesc_f16(128, 0);   // + (blocks * 2) << 17: N = 16 per accumulator block
+      const uint64_t adesc_x0 = make_desc(R.x0, R.x0_plane, 128), adesc_t0 = make_desc(R.t0, R.t_plane, 128);
+      const uint64_t adesc_x1 = make_desc(R.x1, R.x1_plane, 128), adesc_t1 = make_desc(R.t1, R.t_plane, 128);
+      const uint64_t bdesc0 = make_desc(s0 + SM_WTS, 48 * 16, 128);
+      uint32_t S = 0;
+      long long gg = 0;
+      for (long long a = r0; a < r1;) {
+        const Seg sg = seg_at(p, a, r1);
+        a += sg.yb - sg.ya;
+        const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
+        const int gb0 = (int)(gg % K0);
+        const uint32_t ph0 = (uint32_t)(gg / K0);
+        for (int sr = 0; sr < nsteps; ++sr, ++S) {
+          if (S >= 2) mbar_wait(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
+          if (sr == 0 && S >= 1) mbar_wait(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);   // segment start: TMEM fully drained
+          if (sr < Gm) {
+            const int k = gb0 + sr;
+            mbar_wait(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (ph0 + (uint32_t)(k / K0)) & 1u);
+          }
+          tc_fence_after();
+          for (int l = 0; l < nl; ++l) {
+            const int g = sr - LAG * l;
+            if (g < 0 || g >= Gm) continue;
+            const uint64_t bd = bdesc0 + (uint64_t)(l * (W_LAYER_BYTES / 16));
+            const uint64_t adl = l == 0 ? adesc_x0 : (l == 1 ? adesc_t0 : (l == 2 ? adesc_x1 : adesc_t1));
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+              const int rho = 2 * g + par;
+              if (rho >= P) break;
+              int slot;   // ring row of input row rho
+              if (l == 0) slot = ((gb0 + g) % K0) * 2 + par;
+              else if (l == 2) slot = rho & (2 * KX - 1);
+              else slot = rho & (2 * KT - 1);
+              const uint64_t ad = adl + (uint64_t)(slot * RW - 1);
+              // accumulator blocks of output rows rho-1, rho, rho+1 (B blocks 0, 1, 2); the segment's first / last input
+              // row has no row above / below
+              const int jlo = (rho == 0) ? 1 : 0, jhi = (rho == P - 1) ? 1 : 2;
+              const int blk_lo = (rho - 1 + jlo + 14 * l) & 31, nb = jhi - jlo + 1;
+              const int n1 = min(nb, 32 - blk_lo);
+              {
+                const uint32_t d = tmem + (uint32_t)blk_lo * 16u;
+                const uint64_t b = bd + (uint64_t)(jlo * 16);
+                const uint32_t id = idesc0 + ((uint32_t)(2 * n1) << 17);
+                mma_f16_ss(d, ad, b, id, 1u);
+                mma_f16_ss(d, ad + 1, b + (48 * 16 * 2 / 16), id, 1u);
+                mma_f16_ss(d, ad + 2, b + 2 * (48 * 16 * 2 / 16), id, 1u);
+              }
+              if (n1 < nb) {   // the blocks wrap around the TMEM ring: second part at column 0
+                const uint64_t b = bd + (uint64_t)((jlo + n1) * 16);
+                const uint32_t id = idesc0 + ((uint32_t)(2 * (nb - n1)) << 17);
+                mma_f16_ss(tmem, ad, b, id, 1u);
+                mma_f16_ss(tmem, ad + 1, b + (48 * 16 * 2 / 16), id, 1u);
+                mma_f16_ss(tmem, ad + 2, b + 2 * (48 * 16 * 2 / 16), id, 1u);
+              }
+            }
+          }
+          umma_commit(bars + (BAR_MMA + (S & 1u)) * 8);
+        }
+        gg += Gm;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= TMA producer =================
+    if (elect_one_sync()) {
+      long long gg = 0;
+      for (long long a = r0; a < r1;) {
+        const Seg sg = seg_at(p, a, r1);
+        a += sg.yb - sg.ya;
+        const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1;
+        const int gx0 = sg.j * p.tw - halo, y00 = sg.ya - nl;
+        for (int g = 0; g < Gm; ++g, ++gg) {
+          const uint32_t k = (uint32_t)(gg % K0), n = (uint32_t)(gg / K0);
+          if (n >= 1) mbar_wait(bars + (BAR_XFREE + k) * 8, (n - 1) & 1u);
+          const uint32_t bar = bars + (BAR_XFULL + k) * 8;
+          mbar_arrive_expect_tx(bar, 2 * GROUP_BYTES);
+          const uint32_t dst = R.x0 + k * GROUP_BYTES;
+          tma_load_q(dst, &tmap, 0, gx0, y00 + 2 * g, sg.b, bar);
+          tma_load_q(dst + R.x0_plane, &tmap, 1, gx0, y00 + 2 * g, sg.b, bar);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+}  // namespace ustream
+
+int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e, cudaStream_t st) {
+  using namespace ustream;
+  const int N = h->arch.no_layers;
+  BF_REQUIRE(N >= 1, "the fused tensor-core stack needs no_layers >= 1 (use BFCNN_PREC_FP32)");
+  static bool attr_set = false;
+  if (!attr_set) {
+    BF_CUDA(cudaFuncSetAttribute((const void*)stream_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    BF_CUDA(cudaFuncSetAttribute((const void*)stream_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    attr_set = true;
+  }
+  const int kb = 2;
+  const int passes = (N + kb - 1) / kb;
+  const size_t feat_halves = (size_t)e.n * e.he * e.we * C;
+  BF_CHECK(h->ws_feat[1].reserve(feat_halves * sizeof(__half)));
+  if (passes > 1) BF_CHECK(h->ws_feat[0].reserve(feat_halves * sizeof(__half)));
+  // pass "-1": base conv into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
+  BF_CHECK(launch_base_conv_f16(h, d_in, h->ws_feat[1].as<__half>(), e, st));
+  for (int ps = 0; ps < passes; ++ps) {
+    Params p;
+    const bool last = (ps + 1 == passes);
+    p.out = d_out;
+    p.fin = h->ws_feat[(ps + 1) & 1].as<__half>();
+    p.fout = last ? nullptr : h->ws_feat[ps & 1].as<__half>();
+    p.wumma = h->d_conv_umma.as<uint8_t>();
+    p.bias = h->d_bias_f32.as<float>();
+    p.whead = h->d_head_f32.as<float>();
+    p.n = e.n; p.h = e.h; p.w = e.w; p.he = e.he; p.we = e.we;
+    p.blk0 = ps * kb;
+    p.nblk = std::min(kb, N - p.blk0);
+    p.out_u8 = out_u8 ? 1 : 0;
+    const int nl = 2 * p.nblk;
+    p.tw = RW - 2 * nl;
+    p.rows_needed = last ? e.h : e.he;
+    const int cols_needed = last ? e.w : e.we;
+    p.tiles_x = (cols_needed + p.tw - 1) / p.tw;
+    p.total_rows = (long long)e.n * p.tiles_x * p.rows_needed;
+    int grid = (int)std::min<long long>(h->sm_count, std::max<long long>(1, p.total_rows / MIN_SHARE));
+    p.share = (p.total_rows + grid - 1) / grid;
+    grid = (int)((p.total_rows + p.share - 1) / p.share);
+    const size_t smem = smem_bytes(nl);
+    BF_REQUIRE(smem <= (size_t)MAX_SMEM, "internal: streaming pass does not fit in shared memory");
+    CUtensorMap tmap;
+    BF_CHECK(make_feature_tmap(&tmap, p.fin, e, RW, 2));
+    if (last) stream_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
+    else stream_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
+    h->launches++;
+    BF_CUDA(cudaGetLastError());
+  }
+  return BFCNN_OK;
+}
+
+}  // namespace bfcnn

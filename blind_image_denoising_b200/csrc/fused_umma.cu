@@ -27,9 +27,8 @@
 //
 // Reference arithmetic: module_denoiser.py:53-73, utilities.py:449-461 (normalise), backbone_resnet.py:258-262
 // (base conv), backbone_blocks.py:167-246 (block), model.py:297-342 (head), utilities.py:435-443 (denormalise).
-#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
-
 #include "kernels.cuh"
+#include "umma_ptx.cuh"
 
 namespace bfcnn {
 namespace umma {
@@ -65,136 +64,7 @@ struct Params {
   int trace_block;
 };
 
-// ---------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version 1 (sm_100); layout type 0 = SWIZZLE_NONE
-  return d;
-}
-__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
-  uint32_t d = 0;
-  d |= 1u << 4;                    // D = F32
-  d |= 0u << 7;                    // A = F16
-  d |= 0u << 10;                   // B = F16   (both K-major: bits 15, 16 = 0)
-  d |= (uint32_t)(N >> 3) << 17;
-  d |= (uint32_t)(M >> 4) << 24;
-  return d;
-}
-__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// one lane of a converged warp; the compiler keeps the tcgen05 operands in uniform registers only on this path
-// (a plain `lane == 0` branch wraps every UTCHMMA in an ELECT/BRA.U.ANY loop: 392 instead of 143 cycles per row)
-__device__ __forceinline__ uint32_t elect_one_sync() {
-  uint32_t pred = 0;
-  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
-  return pred;
-}
-__device__ __forceinline__ void umma_commit(uint32_t mbar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t cnt) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(cnt) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_n(uint32_t mbar, uint32_t n) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(mbar), "r"(n) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
-// issue only; the registers are valid after tmem_ld_wait(v) (which carries them as in/out operands so that no use of
-// v can be scheduled above the wait)
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-               :: "memory");
-}
-__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
-  const uint32_t z = 0u;
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(taddr), "r"(z)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
-      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
-      "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
-// TMA: one quarter-row of one channel half (32 pixels x 16 B = 512 contiguous shared bytes) of the NHWC16 feature map,
-// addressed as a 5-D tensor {ch8, half, x, y, n}; out-of-extent coordinates (negative included) are zero-filled by the
-// hardware, which is exactly the "same" padding of the feature map.
-__device__ __forceinline__ void tma_load_q(uint32_t dst, const CUtensorMap* tmap, int hf, int gx, int gy, int b, uint32_t mbar) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(hf), "r"(gx), "r"(gy), "r"(b), "r"(mbar)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-// max(x, 0) on a packed pair; rounding to fp16 commutes with ReLU (round-to-nearest keeps the sign)
-__device__ __forceinline__ uint32_t relu_h2(uint32_t v) {
-  const __half2 z = __float2half2_rn(0.f);
-  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&v), z);
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
-__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+using namespace tc5;
 
 // ---------------------------------------------------------------------------- shared-memory map
 struct Smem {
@@ -607,7 +477,7 @@ base_conv_f16_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, 
 typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e) {
+int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e, int box_x, int box_y) {
   static tmap_encode_fn enc = nullptr;
   if (!enc) {
     void* fn = nullptr;
@@ -622,7 +492,7 @@ static int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent&
   // fp16 NHWC16 viewed as {ch8, half, x, y, n}
   const cuuint64_t dims[5] = {8, 2, (cuuint64_t)e.we, (cuuint64_t)e.he, (cuuint64_t)e.n};
   const cuuint64_t strides[4] = {16, 32, (cuuint64_t)e.we * 32, (cuuint64_t)e.he * e.we * 32};
-  const cuuint32_t box[5] = {8, 1, 32, 1, 1};
+  const cuuint32_t box[5] = {8, 1, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -639,8 +509,22 @@ static int env_int_u(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
+int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, const Extent& e, cudaStream_t st) {
+  using namespace umma;
+  const int k0 = h->arch.base_kernel, r0 = (k0 - 1) / 2;
+  const size_t bsm = (size_t)(k0 * k0 * 3 * C + (BC_H + 2 * r0) * (BC_W + 2 * r0) * 3) * sizeof(float);
+  dim3 grid((e.we + BC_W - 1) / BC_W, (e.he + BC_H - 1) / BC_H, e.n);
+  BF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "image too large for the base conv grid");
+  base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, feat, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, k0);
+  h->launches++;
+  BF_CUDA(cudaGetLastError());
+  return BFCNN_OK;
+}
+
 int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e, cudaStream_t st) {
   using namespace umma;
+  static const int engine_regions = env_int_u("BFCNN_UMMA_REGIONS", 0);
+  if (!engine_regions && h->arch.no_layers >= 1) return run_fused_stack_stream(h, d_in, d_out, out_u8, e, st);
   const int N = h->arch.no_layers, k0 = h->arch.base_kernel;
   if (N < 1) {
     set_error("the fused tensor-core stack needs no_layers >= 1 (use BFCNN_PREC_FP32)");
@@ -660,15 +544,7 @@ int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool
   if (passes > 1) BF_CHECK(h->ws_feat[0].reserve(feat_halves * sizeof(__half)));
 
   // pass "-1": base conv into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
-  {
-    const int r0 = (k0 - 1) / 2;
-    const size_t bsm = (size_t)(k0 * k0 * 3 * C + (BC_H + 2 * r0) * (BC_W + 2 * r0) * 3) * sizeof(float);
-    dim3 grid((e.we + BC_W - 1) / BC_W, (e.he + BC_H - 1) / BC_H, e.n);
-    BF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "image too large for the base conv grid");
-    base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, h->ws_feat[1].as<__half>(), h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, k0);
-    h->launches++;
-    BF_CUDA(cudaGetLastError());
-  }
+  BF_CHECK(launch_base_conv_f16(h, d_in, h->ws_feat[1].as<__half>(), e, st));
   for (int ps = 0; ps < passes; ++ps) {
     Params p;
     p.out = d_out;
@@ -716,7 +592,7 @@ int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool
       p.trace = h->ws_feat[2].as<long long>(); p.trace_block = grid / 2;
     }
     CUtensorMap tmap;
-    BF_CHECK(make_feature_tmap(&tmap, p.fin, e));
+    BF_CHECK(make_feature_tmap(&tmap, p.fin, e, 32, 1));
     if (p.last) umma_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     else umma_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     if (p.trace) {

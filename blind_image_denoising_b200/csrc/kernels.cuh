@@ -1,6 +1,8 @@
 // kernels.cuh -- launchers shared between the translation units of libbfcnn_b200.so
 #pragma once
 #include <algorithm>
+#include <cuda.h>   // CUtensorMap (types only)
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace bfcnn {
@@ -35,6 +37,12 @@ int run_fused_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_
 // ---- fused_umma.cu: the fused stack on tcgen05 (UMMA, accumulators in TMEM), F16
 int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                          cudaStream_t st);
+// fp16 NHWC16 feature map as a 5-D TMA tensor {ch8, half, x, y, n}, box = box_x pixels x box_y rows of one channel half
+int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e, int box_x, int box_y);
+int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, const Extent& e, cudaStream_t st);
+// ---- fused_stream.cu: the same arithmetic as a row-streaming pipeline (no vertical halo recompute); default F16 engine
+int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
+                           cudaStream_t st);
 // ---- fused_umma_x3.cu: the same stack in the F16X3 arithmetic (fp16 hi/lo operand parts, FP32-grade)
 int run_fused_stack_umma_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                             cudaStream_t st);
