@@ -276,7 +276,7 @@ def main():
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-        "kernel": {"f16": "umma_pass_kernel (tcgen05; + one base_conv_f16_kernel launch inside the timed stack)",
+        "kernel": {"f16": "ustream::stream_pass_kernel (tcgen05 row-streaming stack; + one base_conv3_mma_kernel launch inside the timed stack)",
                    "f16_mma_sync": "fused_pass_kernel<1>",
                    "f16x3": "umma3::umma_pass_kernel<P=2> (tcgen05, fp16 hi/lo operand parts)",
                    "f16x3_mma_sync": "fused_pass_kernel<2>",

@@ -40,8 +40,8 @@ using namespace tc5;
 constexpr int RW = 128;                 // strip width == UMMA M
 constexpr int SLACK_PX = 8;             // pixels of slack before/after every plane (tap shift -1/+1)
 constexpr int EPI_WARPS = 16;           // 4 sets x 4 TMEM lane quarters
-constexpr int WARP_MMA = 16;          // warp 17 is the TMA producer
-constexpr int NTHREADS = 32 * 18;
+constexpr int WARP_MMA = 16;            // warp 16 issues the MMAs, warp 17 waits on its barriers, warp 18 is the TMA producer
+constexpr int NTHREADS = 32 * 19;
 constexpr int LAG = 3;                  // steps between consecutive layers
 constexpr int K0 = 12;                  // X0 ring: groups of 2 rows (TMA prefetch depth)
 constexpr int KX = 8;                   // X1 ring groups: written at step w+4, last read (residual) at step w+10
@@ -77,7 +77,12 @@ struct Params {
   int out_u8;
   int tw, tiles_x, rows_needed;   // output columns per strip, strips per image, output rows per strip
   long long total_rows, share;    // linearised (image, strip, row) space and the rows of it each CTA owns
+  long long* trace;               // debug timeline (BFCNN_STREAM_TRACE=1) of CTA trace_block, steps [TRACE_S0, TRACE_S0 + 32)
+  int trace_block;
+  int helper;                     // 1: the issuer's barrier waits are done by the helper warp (default)
 };
+constexpr uint32_t TRACE_S0 = 100;
+#define STREAM_TRACE(slot) do { if (tr && S >= TRACE_S0 && S < TRACE_S0 + 32) p.trace[(S - TRACE_S0) * 8 + (slot)] = clock64(); } while (0)
 
 struct Seg { int b, j, ya, yb; };
 // the next segment of the linear row range [a, r1): rows [ya, yb) of strip j of image b
@@ -99,6 +104,16 @@ struct Rings {
 
 enum Kind { KIND_A = 0, KIND_B_TO_X = 1, KIND_B_OUT = 2 };
 
+// model.py:342 tanh(2y)*0.51, then utilities.py:435-443 (clip(+-0.5)+0.5)*255, with tanh(z) = 1 - 2/(exp(2z)+1) on the
+// fast exp / divide units (absolute error ~1e-6 of the +-1 range, 1e-4 on the 0-255 scale): the head sits on the
+// epilogue's critical path in the last pass
+__device__ __forceinline__ float head_activation_fast(float y) {
+  const float e = __expf(4.0f * y);
+  float t = (1.0f - __fdividef(2.0f, e + 1.0f)) * 0.51f;
+  t = fminf(fmaxf(t, -0.5f), 0.5f);
+  return (t + 0.5f) * 255.0f;
+}
+
 struct EpiCtx {
   uint32_t tq;             // TMEM address of this warp's lane quarter, column 0
   uint32_t pix;            // byte offset of this thread's pixel inside a ring row
@@ -114,7 +129,7 @@ struct EpiCtx {
 // one (layer, row) task of one warp: 32 pixels of output row rho of layer l
 template <int KIND, bool LAST_PASS>
 __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const EpiCtx& E, uint32_t bars, const float (&bias)[16],
-                                         const float* s_head, int l, int rho) {
+                                         const float* s_head, const float* s_bias_l, int l, int rho) {
   const uint32_t taddr = E.tq + (uint32_t)((rho + 14 * l) & 31) * 16u;
   uint32_t v[16];
   tmem_ld16_issue(taddr, v);
@@ -145,25 +160,22 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
     const uint4 xa = lds128(xsrc), xb = lds128(xsrc + xplane);
     tmem_ld_wait(v);
     tmem_zero16(taddr);
-    float f[16];
-    {
-      const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 xv = unpack_h2(xs[i]);
-        f[2 * i] = __uint_as_float(v[2 * i]) + (xv.x + bias[2 * i]);
-        f[2 * i + 1] = __uint_as_float(v[2 * i + 1]) + (xv.y + bias[2 * i + 1]);
-      }
-    }
-    if (KIND == KIND_B_OUT && LAST_PASS) {   // collapsed 1x1 head + tanh(2y)*0.51 + denormalise (+ round + uint8)
+    if (KIND == KIND_B_OUT && LAST_PASS) {
+      // collapsed 1x1 head + tanh(2y)*0.51 + denormalise (+ round + uint8), accumulated channel pair by channel pair
+      // (the 19-warp CTA caps the kernel at 96 registers; bias and head weights stay in shared memory)
       if (E.col_out && inside && rho >= E.nl && rho < E.P - E.nl && (E.y00 + rho) < E.h_img) {
+        const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int ch = 0; ch < 16; ++ch) {
-          const float4 wv = *reinterpret_cast<const float4*>(s_head + ch * 4);
-          s0 = fmaf(f[ch], wv.x, s0); s1 = fmaf(f[ch], wv.y, s1); s2 = fmaf(f[ch], wv.z, s2);
+        for (int i = 0; i < 8; ++i) {
+          const float2 xv = unpack_h2(xs[i]);
+          const float2 bb = *reinterpret_cast<const float2*>(s_bias_l + 2 * i);
+          const float f0 = __uint_as_float(v[2 * i]) + (xv.x + bb.x), f1 = __uint_as_float(v[2 * i + 1]) + (xv.y + bb.y);
+          const float4 w0 = *reinterpret_cast<const float4*>(s_head + 8 * i), w1 = *reinterpret_cast<const float4*>(s_head + 8 * i + 4);
+          s0 = fmaf(f0, w0.x, s0); s1 = fmaf(f0, w0.y, s1); s2 = fmaf(f0, w0.z, s2);
+          s0 = fmaf(f1, w1.x, s0); s1 = fmaf(f1, w1.y, s1); s2 = fmaf(f1, w1.z, s2);
         }
-        const float r0o = head_activation(s0), r1o = head_activation(s1), r2o = head_activation(s2);
+        const float r0o = head_activation_fast(s0), r1o = head_activation_fast(s1), r2o = head_activation_fast(s2);
         if (p.out_u8) {
           uint8_t* d = E.out_col + (long long)rho * E.row_out;
           d[0] = (uint8_t)__float2int_rn(r0o); d[1] = (uint8_t)__float2int_rn(r1o); d[2] = (uint8_t)__float2int_rn(r2o);
@@ -172,7 +184,30 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
           d[0] = r0o; d[1] = r1o; d[2] = r2o;
         }
       }
-    } else {
+      if (l == 1) {
+        fence_async_smem();
+        mbar_arrive(bars + (BAR_XFREE + (uint32_t)((E.gb0 + (rho >> 1)) % K0)) * 8);
+      }
+      return;
+    }
+    float f[16];
+    {
+      const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 xv = unpack_h2(xs[i]);
+        float b0, b1;
+        if (LAST_PASS) {   // 96-register cap (19 warps): the last pass keeps the bias in shared memory (broadcast loads)
+          const float2 bb = *reinterpret_cast<const float2*>(s_bias_l + 2 * i);
+          b0 = bb.x; b1 = bb.y;
+        } else {
+          b0 = bias[2 * i]; b1 = bias[2 * i + 1];
+        }
+        f[2 * i] = __uint_as_float(v[2 * i]) + (xv.x + b0);
+        f[2 * i + 1] = __uint_as_float(v[2 * i + 1]) + (xv.y + b1);
+      }
+    }
+    {
       uint4 lo, hi;
       lo.x = pack_h2(f[0], f[1]); lo.y = pack_h2(f[2], f[3]); lo.z = pack_h2(f[4], f[5]); lo.w = pack_h2(f[6], f[7]);
       hi.x = pack_h2(f[8], f[9]); hi.y = pack_h2(f[10], f[11]); hi.z = pack_h2(f[12], f[13]); hi.w = pack_h2(f[14], f[15]);
@@ -217,6 +252,8 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     R.t1 = o + SLACK_PX * 16;
   }
   const long long r0 = (long long)blockIdx.x * p.share, r1 = min(p.total_rows, r0 + p.share);
+  const bool tr = (p.trace != nullptr) && ((int)blockIdx.x == p.trace_block);
+  if (tr && tid == 0) p.trace[256] = clock64();
 
   // ---------------- one-time setup: barriers, TMEM, weights, zeroed rings
   if (tid < (int)NBARS) {
@@ -242,6 +279,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+  if (tr && tid == 0) p.trace[257] = clock64();
 
   if (warp < EPI_WARPS) {
     // ================= epilogue warps =================
@@ -258,7 +296,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     float bias[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) bias[i] = 0.f;
-    for (int k = 0; k < ntask; ++k)
+    for (int k = 0; k < ntask && !LAST_PASS; ++k)
       if (tl[k] & 1) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) bias[i] = s_bias[tl[k] * C + i];   // at most one conv_b layer per warp (nl = 2, 4)
@@ -285,46 +323,55 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
         mbar_wait(bars + (BAR_MMA + (S & 1u)) * 8, (S >> 1) & 1u);
         tc_fence_after();
+        if (lane == 0 && (warp == 0 || warp == 15)) STREAM_TRACE(warp == 0 ? 4 : 6);
         for (int k = 0; k < ntask; ++k) {
           const int l = tl[k], w = sr - LAG * l - 1;
           if (w < 0 || w >= Gm) continue;
           const int rho = 2 * w + tpar[k];
-          if ((l & 1) == 0) epi_task<KIND_A, LAST_PASS>(p, R, E, bars, bias, s_head, l, rho);
-          else if (l + 1 < nl) epi_task<KIND_B_TO_X, LAST_PASS>(p, R, E, bars, bias, s_head, l, rho);
-          else epi_task<KIND_B_OUT, LAST_PASS>(p, R, E, bars, bias, s_head, l, rho);
+          if ((l & 1) == 0) epi_task<KIND_A, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
+          else if (l + 1 < nl) epi_task<KIND_B_TO_X, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
+          else epi_task<KIND_B_OUT, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
         }
         fence_async_smem();   // T / X stores of this step -> async proxy (tensor core reads)
         tmem_wait_st();
         tc_fence_before();
+        if (lane == 0 && (warp == 0 || warp == 15)) STREAM_TRACE(warp == 0 ? 5 : 7);
         mbar_arrive(bars + (BAR_EPI + (S & 1u)) * 8);
       }
       gg += Gm;
     }
   } else if (warp == WARP_MMA) {
     // ================= MMA issuer =================
-    asm volatile("bar.sync 1, %0;\n" ::"r"(32 * (EPI_WARPS + 1)) : "memory");
-    tc_fence_after();
-    if (elect_one_sync()) {
-      const uint32_t idesc0 = make_idesc_f16(128, 0);   // + (blocks * 2) << 17: N = 16 per accumulator block
-      const uint64_t adesc_x0 = make_desc(R.x0, R.x0_plane, 128), adesc_t0 = make_desc(R.t0, R.t_plane, 128);
-      const uint64_t adesc_x1 = make_desc(R.x1, R.x1_plane, 128), adesc_t1 = make_desc(R.t1, R.t_plane, 128);
-      const uint64_t bdesc0 = make_desc(s0 + SM_WTS, 48 * 16, 128);
-      uint32_t S = 0;
-      long long gg = 0;
-      for (long long a = r0; a < r1;) {
-        const Seg sg = seg_at(p, a, r1);
-        a += sg.yb - sg.ya;
-        const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
-        const int gb0 = (int)(gg % K0);
-        const uint32_t ph0 = (uint32_t)(gg / K0);
-        for (int sr = 0; sr < nsteps; ++sr, ++S) {
-          if (S >= 2) mbar_wait(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
-          if (sr == 0 && S >= 1) mbar_wait(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);   // segment start: TMEM fully drained
-          if (sr < Gm) {
-            const int k = gb0 + sr;
-            mbar_wait(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (ph0 + (uint32_t)(k / K0)) & 1u);
+    // The issuing thread never touches shared memory: a completed mbarrier.try_wait on it costs ~360 cycles of tensor-pipe
+    // bubble (tools/umma_probe3.cu: the load queues behind the operand fetches, and the MMA queue is shallow).  The waits
+    // of step S are done by the helper warp, which then releases the issuer through a named barrier (bar.arrive /
+    // bar.sync 2 + (S & 1): hardware barrier, no shared-memory traffic).
+    asm volatile("bar.sync 1, %0;\n" ::"r"(32 * (EPI_WARPS + 1)) : "memory");   // accumulators are zero
+    const uint32_t idesc0 = make_idesc_f16(128, 0);   // + (blocks * 2) << 17: N = 16 per accumulator block
+    const uint64_t adesc_x0 = make_desc(R.x0, R.x0_plane, 128), adesc_t0 = make_desc(R.t0, R.t_plane, 128);
+    const uint64_t adesc_x1 = make_desc(R.x1, R.x1_plane, 128), adesc_t1 = make_desc(R.t1, R.t_plane, 128);
+    const uint64_t bdesc0 = make_desc(s0 + SM_WTS, 48 * 16, 128);
+    uint32_t S = 0;
+    long long gg = 0;
+    for (long long a = r0; a < r1;) {
+      const Seg sg = seg_at(p, a, r1);
+      a += sg.yb - sg.ya;
+      const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
+      const int gb0 = (int)(gg % K0);
+      for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        if (p.helper) asm volatile("bar.sync %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");   // the helper has seen this step's barriers
+        tc_fence_after();
+        if (elect_one_sync()) {
+          if (!p.helper) {
+            if (S >= 2) mbar_wait(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
+            if (sr == 0 && S >= 1) mbar_wait(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
+            if (sr < Gm) {
+              const long long k = gg + sr;
+              mbar_wait(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (uint32_t)(k / K0) & 1u);
+            }
+            tc_fence_after();
           }
-          tc_fence_after();
+          STREAM_TRACE(0);
           for (int l = 0; l < nl; ++l) {
             const int g = sr - LAG * l;
             if (g < 0 || g >= Gm) continue;
@@ -362,11 +409,39 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             }
           }
           umma_commit(bars + (BAR_MMA + (S & 1u)) * 8);
+          STREAM_TRACE(1);
         }
-        gg += Gm;
+        __syncwarp();
       }
+      gg += Gm;
     }
-    __syncwarp();
+    if (tr && lane == 0) { p.trace[258] = clock64(); p.trace[259] = S; }
+  } else if (warp == WARP_MMA + 1) {
+    // ================= barrier helper of the MMA issuer =================
+    // step S needs: epi_done(S-2) (lane 0: input rows written, accumulator blocks drained), x_full of layer 0's group
+    // (lane 1), and at a segment start epi_done(S-1) too (lane 2: every accumulator block drained before the ring
+    // restarts at row 0).  One barrier per lane, in parallel.
+    uint32_t S = 0;
+    long long gg = 0;
+    for (long long a = r0; a < r1 && p.helper;) {
+      const Seg sg = seg_at(p, a, r1);
+      a += sg.yb - sg.ya;
+      const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
+      for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        if (lane == 0) STREAM_TRACE(2);
+        if (lane == 0 && S >= 2) mbar_wait(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
+        if (lane == 1 && sr < Gm) {
+          const long long k = gg + sr;
+          mbar_wait(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (uint32_t)(k / K0) & 1u);
+        }
+        if (lane == 2 && sr == 0 && S >= 1) mbar_wait(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
+        __syncwarp();
+        if (lane == 0) STREAM_TRACE(3);
+        tc_fence_before();
+        asm volatile("bar.arrive %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");
+      }
+      gg += Gm;
+    }
   } else {
     // ================= TMA producer =================
     if (elect_one_sync()) {
@@ -391,6 +466,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && tid == 0) p.trace[260] = clock64();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
 }
 
@@ -437,12 +513,34 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
     grid = (int)((p.total_rows + p.share - 1) / p.share);
     const size_t smem = smem_bytes(nl);
     BF_REQUIRE(smem <= (size_t)MAX_SMEM, "internal: streaming pass does not fit in shared memory");
+    static const int trace_on = getenv("BFCNN_STREAM_TRACE") ? atoi(getenv("BFCNN_STREAM_TRACE")) : 0;
+    p.trace = nullptr; p.trace_block = 0;
+    p.helper = getenv("BFCNN_STREAM_HELPER") ? atoi(getenv("BFCNN_STREAM_HELPER")) : 1;
+    if (trace_on && ps == std::min(1, passes - 1)) {
+      BF_CHECK(h->ws_feat[2].reserve(264 * sizeof(long long)));
+      BF_CUDA(cudaMemsetAsync(h->ws_feat[2].p, 0, 264 * sizeof(long long), st));
+      p.trace = h->ws_feat[2].as<long long>(); p.trace_block = grid / 2;
+    }
     CUtensorMap tmap;
     BF_CHECK(make_feature_tmap(&tmap, p.fin, e, RW, 2));
     if (last) stream_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     else stream_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     h->launches++;
     BF_CUDA(cudaGetLastError());
+    if (p.trace) {
+      long long tb[264];
+      BF_CUDA(cudaMemcpyAsync(tb, p.trace, sizeof(tb), cudaMemcpyDeviceToHost, st));
+      BF_CUDA(cudaStreamSynchronize(st));
+      const long long t0 = tb[0];
+      fprintf(stderr, "[stream trace] kernel: setup %lld, issue loop end %lld (%lld steps, %.0f cycles/step), total %lld\n", tb[257] - tb[256],
+              tb[258] - tb[256], tb[259], (double)(tb[258] - tb[257]) / (double)std::max(1ll, tb[259]), tb[260] - tb[256]);
+      fprintf(stderr, "[stream trace] pass %d grid %d share %lld: step | issue start..end | waits start..end | epi w0 wake..arrive | epi w15 wake..arrive\n", ps, grid, p.share);
+      for (int i = 0; i < 32; ++i) {
+        fprintf(stderr, "  %3u |", TRACE_S0 + i);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld%s", tb[i * 8 + k] ? tb[i * 8 + k] - t0 : -1ll, (k & 1) ? " |" : "");
+        fprintf(stderr, "\n");
+      }
+    }
   }
   return BFCNN_OK;
 }
