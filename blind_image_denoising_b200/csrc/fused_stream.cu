@@ -80,6 +80,7 @@ struct Params {
   long long* trace;               // debug timeline (BFCNN_STREAM_TRACE=1) of CTA trace_block, steps [TRACE_S0, TRACE_S0 + 32)
   int trace_block;
   int helper;                     // 1: the issuer's barrier waits are done by the helper warp (default)
+  int dbg;                        // timing experiments only (wrong results): 1 skip epilogue st.shared, 2 skip ld.shared, 4 skip fences
 };
 constexpr uint32_t TRACE_S0 = 100;
 #define STREAM_TRACE(slot) do { if (tr && S >= TRACE_S0 && S < TRACE_S0 + 32) p.trace[(S - TRACE_S0) * 8 + (slot)] = clock64(); } while (0)
@@ -144,8 +145,10 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
     hi.x = relu_h2(pack_h2(__uint_as_float(v[8]), __uint_as_float(v[9]))) & m; hi.y = relu_h2(pack_h2(__uint_as_float(v[10]), __uint_as_float(v[11]))) & m;
     hi.z = relu_h2(pack_h2(__uint_as_float(v[12]), __uint_as_float(v[13]))) & m; hi.w = relu_h2(pack_h2(__uint_as_float(v[14]), __uint_as_float(v[15]))) & m;
     const uint32_t dst = (l == 0 ? R.t0 : R.t1) + (uint32_t)(rho & (2 * KT - 1)) * ROW_BYTES + E.pix;
-    sts128(dst, lo);
-    sts128(dst + R.t_plane, hi);
+    if (!(p.dbg & 1)) {
+      sts128(dst, lo);
+      sts128(dst + R.t_plane, hi);
+    }
   } else {
     // residual: X of this block (fp16) + the BN constant b' + the accumulator
     uint32_t xsrc, xplane;
@@ -157,7 +160,8 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
       xsrc = R.x1 + (uint32_t)(rho & (2 * KX - 1)) * ROW_BYTES + E.pix;
       xplane = R.x1_plane;
     }
-    const uint4 xa = lds128(xsrc), xb = lds128(xsrc + xplane);
+    uint4 xa = make_uint4(0u, 0u, 0u, 0u), xb = xa;
+    if (!(p.dbg & 2)) { xa = lds128(xsrc); xb = lds128(xsrc + xplane); }
     tmem_ld_wait(v);
     tmem_zero16(taddr);
     if (KIND == KIND_B_OUT && LAST_PASS) {
@@ -215,8 +219,10 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
         const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
         lo.x &= m; lo.y &= m; lo.z &= m; lo.w &= m; hi.x &= m; hi.y &= m; hi.z &= m; hi.w &= m;
         const uint32_t dst = R.x1 + (uint32_t)(rho & (2 * KX - 1)) * ROW_BYTES + E.pix;
-        sts128(dst, lo);
-        sts128(dst + R.x1_plane, hi);
+        if (!(p.dbg & 1)) {
+          sts128(dst, lo);
+          sts128(dst + R.x1_plane, hi);
+        }
       } else if (E.col_out && inside && rho >= E.nl && rho < E.P - E.nl) {
         uint4* o = reinterpret_cast<uint4*>(E.fout_col + (long long)rho * E.row_halves);
         o[0] = lo;
@@ -332,7 +338,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
           else if (l + 1 < nl) epi_task<KIND_B_TO_X, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
           else epi_task<KIND_B_OUT, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
         }
-        fence_async_smem();   // T / X stores of this step -> async proxy (tensor core reads)
+        if (!(p.dbg & 4)) fence_async_smem();   // T / X stores of this step -> async proxy (tensor core reads)
         tmem_wait_st();
         tc_fence_before();
         if (lane == 0 && (warp == 0 || warp == 15)) STREAM_TRACE(warp == 0 ? 5 : 7);
@@ -358,10 +364,22 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
       a += sg.yb - sg.ya;
       const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
       const int gb0 = (int)(gg % K0);
+      // per-layer issue state at the layer's group 0: A descriptor of input row 0 (pixel -1), its ring row, TMEM block of row -1
+      uint64_t st_ad[MAX_NL];
+      int st_slot[MAX_NL], st_blk[MAX_NL];
+#pragma unroll
+      for (int l = 0; l < MAX_NL; ++l) {
+        const uint64_t adl = l == 0 ? adesc_x0 : (l == 1 ? adesc_t0 : (l == 2 ? adesc_x1 : adesc_t1));
+        st_slot[l] = (l == 0) ? 2 * gb0 : 0;
+        st_ad[l] = adl + (uint64_t)(st_slot[l] * RW - 1);
+        st_blk[l] = (14 * l - 1) & 31;
+      }
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        if (lane == 0) STREAM_TRACE(0);
         if (p.helper) asm volatile("bar.sync %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");   // the helper has seen this step's barriers
         tc_fence_after();
         if (elect_one_sync()) {
+          STREAM_TRACE(1);
           if (!p.helper) {
             if (S >= 2) mbar_wait(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
             if (sr == 0 && S >= 1) mbar_wait(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
@@ -371,45 +389,67 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             }
             tc_fence_after();
           }
-          STREAM_TRACE(0);
-          for (int l = 0; l < nl; ++l) {
+#pragma unroll
+          for (int l = 0; l < MAX_NL; ++l) {
+            if (l >= nl) break;
             const int g = sr - LAG * l;
             if (g < 0 || g >= Gm) continue;
             const uint64_t bd = bdesc0 + (uint64_t)(l * (W_LAYER_BYTES / 16));
-            const uint64_t adl = l == 0 ? adesc_x0 : (l == 1 ? adesc_t0 : (l == 2 ? adesc_x1 : adesc_t1));
+            // incremental state of the layer (the issuing thread must not fall behind the shallow MMA queue: descriptor
+            // arithmetic from scratch cost ~200 cycles per group of six MMAs, 40 % of the issue time)
+            const uint64_t ad = st_ad[l];
+            const int blk0 = st_blk[l];   // accumulator block of output row 2g - 1
+            const int rho0 = 2 * g;
+            {
+              st_blk[l] = (blk0 + 2) & 31;
+              const int rows = (l == 0) ? 2 * K0 : ((l == 2) ? 2 * KX : 2 * KT);
+              st_slot[l] += 2;
+              st_ad[l] = ad + 2 * RW;
+              if (st_slot[l] >= rows) { st_slot[l] -= rows; st_ad[l] -= (uint64_t)(rows * RW); }
+            }
+            if (rho0 >= 1 && rho0 + 2 < P && blk0 <= 28) {
+              // fast path (7 groups in 8): both rows are interior rows of the segment and their four accumulator blocks
+              // do not wrap around the TMEM ring -> six N = 48 MMAs, straight-line
+              const uint32_t d = tmem + (uint32_t)blk0 * 16u;
+              const uint32_t id = idesc0 + (6u << 17);
+              mma_f16_ss(d, ad, bd, id, 1u);
+              mma_f16_ss(d, ad + 1, bd + (48 * 16 * 2 / 16), id, 1u);
+              mma_f16_ss(d, ad + 2, bd + 2 * (48 * 16 * 2 / 16), id, 1u);
+              mma_f16_ss(d + 16, ad + RW, bd, id, 1u);
+              mma_f16_ss(d + 16, ad + RW + 1, bd + (48 * 16 * 2 / 16), id, 1u);
+              mma_f16_ss(d + 16, ad + RW + 2, bd + 2 * (48 * 16 * 2 / 16), id, 1u);
+              continue;
+            }
 #pragma unroll
             for (int par = 0; par < 2; ++par) {
-              const int rho = 2 * g + par;
+              const int rho = rho0 + par;
               if (rho >= P) break;
-              int slot;   // ring row of input row rho
-              if (l == 0) slot = ((gb0 + g) % K0) * 2 + par;
-              else if (l == 2) slot = rho & (2 * KX - 1);
-              else slot = rho & (2 * KT - 1);
-              const uint64_t ad = adl + (uint64_t)(slot * RW - 1);
+              const uint64_t adr = ad + (uint64_t)(par * RW);
               // accumulator blocks of output rows rho-1, rho, rho+1 (B blocks 0, 1, 2); the segment's first / last input
               // row has no row above / below
               const int jlo = (rho == 0) ? 1 : 0, jhi = (rho == P - 1) ? 1 : 2;
-              const int blk_lo = (rho - 1 + jlo + 14 * l) & 31, nb = jhi - jlo + 1;
+              const int blk_lo = (blk0 + par + jlo) & 31, nb = jhi - jlo + 1;
               const int n1 = min(nb, 32 - blk_lo);
               {
                 const uint32_t d = tmem + (uint32_t)blk_lo * 16u;
                 const uint64_t b = bd + (uint64_t)(jlo * 16);
                 const uint32_t id = idesc0 + ((uint32_t)(2 * n1) << 17);
-                mma_f16_ss(d, ad, b, id, 1u);
-                mma_f16_ss(d, ad + 1, b + (48 * 16 * 2 / 16), id, 1u);
-                mma_f16_ss(d, ad + 2, b + 2 * (48 * 16 * 2 / 16), id, 1u);
+                mma_f16_ss(d, adr, b, id, 1u);
+                mma_f16_ss(d, adr + 1, b + (48 * 16 * 2 / 16), id, 1u);
+                mma_f16_ss(d, adr + 2, b + 2 * (48 * 16 * 2 / 16), id, 1u);
               }
               if (n1 < nb) {   // the blocks wrap around the TMEM ring: second part at column 0
                 const uint64_t b = bd + (uint64_t)((jlo + n1) * 16);
                 const uint32_t id = idesc0 + ((uint32_t)(2 * (nb - n1)) << 17);
-                mma_f16_ss(tmem, ad, b, id, 1u);
-                mma_f16_ss(tmem, ad + 1, b + (48 * 16 * 2 / 16), id, 1u);
-                mma_f16_ss(tmem, ad + 2, b + 2 * (48 * 16 * 2 / 16), id, 1u);
+                mma_f16_ss(tmem, adr, b, id, 1u);
+                mma_f16_ss(tmem, adr + 1, b + (48 * 16 * 2 / 16), id, 1u);
+                mma_f16_ss(tmem, adr + 2, b + 2 * (48 * 16 * 2 / 16), id, 1u);
               }
             }
           }
+          STREAM_TRACE(2);
           umma_commit(bars + (BAR_MMA + (S & 1u)) * 8);
-          STREAM_TRACE(1);
+          STREAM_TRACE(3);
         }
         __syncwarp();
       }
@@ -428,7 +468,6 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
       a += sg.yb - sg.ya;
       const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
-        if (lane == 0) STREAM_TRACE(2);
         if (lane == 0 && S >= 2) mbar_wait(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
         if (lane == 1 && sr < Gm) {
           const long long k = gg + sr;
@@ -436,7 +475,6 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         }
         if (lane == 2 && sr == 0 && S >= 1) mbar_wait(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
         __syncwarp();
-        if (lane == 0) STREAM_TRACE(3);
         tc_fence_before();
         asm volatile("bar.arrive %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");
       }
@@ -516,6 +554,7 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
     static const int trace_on = getenv("BFCNN_STREAM_TRACE") ? atoi(getenv("BFCNN_STREAM_TRACE")) : 0;
     p.trace = nullptr; p.trace_block = 0;
     p.helper = getenv("BFCNN_STREAM_HELPER") ? atoi(getenv("BFCNN_STREAM_HELPER")) : 1;
+    p.dbg = getenv("BFCNN_STREAM_DBG") ? atoi(getenv("BFCNN_STREAM_DBG")) : 0;
     if (trace_on && ps == std::min(1, passes - 1)) {
       BF_CHECK(h->ws_feat[2].reserve(264 * sizeof(long long)));
       BF_CUDA(cudaMemsetAsync(h->ws_feat[2].p, 0, 264 * sizeof(long long), st));
@@ -534,7 +573,7 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
       const long long t0 = tb[0];
       fprintf(stderr, "[stream trace] kernel: setup %lld, issue loop end %lld (%lld steps, %.0f cycles/step), total %lld\n", tb[257] - tb[256],
               tb[258] - tb[256], tb[259], (double)(tb[258] - tb[257]) / (double)std::max(1ll, tb[259]), tb[260] - tb[256]);
-      fprintf(stderr, "[stream trace] pass %d grid %d share %lld: step | issue start..end | waits start..end | epi w0 wake..arrive | epi w15 wake..arrive\n", ps, grid, p.share);
+      fprintf(stderr, "[stream trace] pass %d grid %d share %lld: step | loop top, after bar.sync | MMAs issued, committed | epi w0 wake..arrive | epi w15 wake..arrive\n", ps, grid, p.share);
       for (int i = 0; i < 32; ++i) {
         fprintf(stderr, "  %3u |", TRACE_S0 + i);
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld%s", tb[i * 8 + k] ? tb[i * 8 + k] - t0 : -1ll, (k & 1) ? " |" : "");
