@@ -83,7 +83,13 @@ struct Params {
   int dbg;                        // timing experiments only (wrong results): 1 skip epilogue st.shared, 2 skip ld.shared, 4 skip fences
 };
 constexpr uint32_t TRACE_S0 = 100;
+#ifdef BFCNN_STREAM_TRACE_BUILD   // compile-time: the timeline costs the issuer ~5 % even when it is switched off at run time
 #define STREAM_TRACE(slot) do { if (tr && S >= TRACE_S0 && S < TRACE_S0 + 32) p.trace[(S - TRACE_S0) * 8 + (slot)] = clock64(); } while (0)
+#define STREAM_TRACE_PTR(cond) ((tr && (cond) && S >= TRACE_S0 && S < TRACE_S0 + 32) ? p.trace + (S - TRACE_S0) * 8 + 4 : nullptr)
+#else
+#define STREAM_TRACE(slot) do { } while (0)
+#define STREAM_TRACE_PTR(cond) nullptr
+#endif
 
 struct Seg { int b, j, ya, yb; };
 // the next segment of the linear row range [a, r1): rows [ya, yb) of strip j of image b
@@ -130,14 +136,17 @@ struct EpiCtx {
 // one (layer, row) task of one warp: 32 pixels of output row rho of layer l
 template <int KIND, bool LAST_PASS>
 __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const EpiCtx& E, uint32_t bars, const float (&bias)[16],
-                                         const float* s_head, const float* s_bias_l, int l, int rho) {
+                                         const float* s_head, const float* s_bias_l, int l, int rho, long long* tp = nullptr) {
   const uint32_t taddr = E.tq + (uint32_t)((rho + 14 * l) & 31) * 16u;
   uint32_t v[16];
+  if (tp) tp[0] = clock64();
   tmem_ld16_issue(taddr, v);
   const bool inside = E.col_ok && ((unsigned)(E.y00 + rho) < (unsigned)E.he);
   if (KIND == KIND_A) {
     tmem_ld_wait(v);
+    if (tp) tp[1] = clock64();
     tmem_zero16(taddr);
+    if (tp) tp[2] = clock64();
     const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
     uint4 lo, hi;
     lo.x = relu_h2(pack_h2(__uint_as_float(v[0]), __uint_as_float(v[1]))) & m; lo.y = relu_h2(pack_h2(__uint_as_float(v[2]), __uint_as_float(v[3]))) & m;
@@ -149,6 +158,7 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
       sts128(dst, lo);
       sts128(dst + R.t_plane, hi);
     }
+    if (tp) tp[3] = clock64();
   } else {
     // residual: X of this block (fp16) + the BN constant b' + the accumulator
     uint32_t xsrc, xplane;
@@ -190,7 +200,8 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
       }
       if (l == 1) {
         fence_async_smem();
-        mbar_arrive(bars + (BAR_XFREE + (uint32_t)((E.gb0 + (rho >> 1)) % K0)) * 8);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + (BAR_XFREE + (uint32_t)((E.gb0 + (rho >> 1)) % K0)) * 8);
       }
       return;
     }
@@ -230,9 +241,10 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
       }
     }
     if (l == 1) {
-      // this thread's X0 pixel of the row is consumed: (generic read -> async-proxy TMA overwrite)
+      // this warp's X0 pixels of the row are consumed: (generic read -> async-proxy TMA overwrite)
       fence_async_smem();
-      mbar_arrive(bars + (BAR_XFREE + (uint32_t)((E.gb0 + (rho >> 1)) % K0)) * 8);
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(bars + (BAR_XFREE + (uint32_t)((E.gb0 + (rho >> 1)) % K0)) * 8);
     }
   }
 }
@@ -263,7 +275,9 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
 
   // ---------------- one-time setup: barriers, TMEM, weights, zeroed rings
   if (tid < (int)NBARS) {
-    const uint32_t cnt = tid < (int)BAR_EPI ? 1u : (tid < (int)BAR_XFULL ? (uint32_t)(EPI_WARPS * 32) : (tid < (int)BAR_XFREE ? 1u : 256u));
+    // epi_done: one arrival per epilogue warp; x_free: one per warp of the 2 rows x 4 quarters that read the group
+    // (32 same-address arrivals per warp showed up as ~200 extra shared-memory wavefronts per step)
+    const uint32_t cnt = tid < (int)BAR_EPI ? 1u : (tid < (int)BAR_XFULL ? (uint32_t)EPI_WARPS : (tid < (int)BAR_XFREE ? 1u : 8u));
     mbar_init(bars + tid * 8, cnt);
   }
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -329,20 +343,20 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
         mbar_wait(bars + (BAR_MMA + (S & 1u)) * 8, (S >> 1) & 1u);
         tc_fence_after();
-        if (lane == 0 && (warp == 0 || warp == 15)) STREAM_TRACE(warp == 0 ? 4 : 6);
         for (int k = 0; k < ntask; ++k) {
           const int l = tl[k], w = sr - LAG * l - 1;
           if (w < 0 || w >= Gm) continue;
           const int rho = 2 * w + tpar[k];
-          if ((l & 1) == 0) epi_task<KIND_A, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
+          if ((l & 1) == 0) epi_task<KIND_A, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho,
+                                                        STREAM_TRACE_PTR(warp == 0 && lane == 0));
           else if (l + 1 < nl) epi_task<KIND_B_TO_X, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
           else epi_task<KIND_B_OUT, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
         }
         if (!(p.dbg & 4)) fence_async_smem();   // T / X stores of this step -> async proxy (tensor core reads)
         tmem_wait_st();
         tc_fence_before();
-        if (lane == 0 && (warp == 0 || warp == 15)) STREAM_TRACE(warp == 0 ? 5 : 7);
-        mbar_arrive(bars + (BAR_EPI + (S & 1u)) * 8);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + (BAR_EPI + (S & 1u)) * 8);
       }
       gg += Gm;
     }
@@ -573,7 +587,7 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
       const long long t0 = tb[0];
       fprintf(stderr, "[stream trace] kernel: setup %lld, issue loop end %lld (%lld steps, %.0f cycles/step), total %lld\n", tb[257] - tb[256],
               tb[258] - tb[256], tb[259], (double)(tb[258] - tb[257]) / (double)std::max(1ll, tb[259]), tb[260] - tb[256]);
-      fprintf(stderr, "[stream trace] pass %d grid %d share %lld: step | loop top, after bar.sync | MMAs issued, committed | epi w0 wake..arrive | epi w15 wake..arrive\n", ps, grid, p.share);
+      fprintf(stderr, "[stream trace] pass %d grid %d share %lld: step | loop top, after bar.sync | MMAs issued, committed | epi w0 task A: start, ld done | zero issued, sts issued\n", ps, grid, p.share);
       for (int i = 0; i < 32; ++i) {
         fprintf(stderr, "  %3u |", TRACE_S0 + i);
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld%s", tb[i * 8 + k] ? tb[i * 8 + k] - t0 : -1ll, (k & 1) ? " |" : "");
