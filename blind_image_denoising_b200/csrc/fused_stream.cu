@@ -178,16 +178,21 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
       // collapsed 1x1 head + tanh(2y)*0.51 + denormalise (+ round + uint8), accumulated channel pair by channel pair
       // (the 19-warp CTA caps the kernel at 96 registers; bias and head weights stay in shared memory)
       if (E.col_out && inside && rho >= E.nl && rho < E.P - E.nl && (E.y00 + rho) < E.h_img) {
+        // s_head is packed [16 ch][3] here (12 broadcast LDS.128 per thread) and the BN constant b' of the last conv_b
+        // enters as bias[0..2] = sum_ch b'[ch] w[ch][j], folded once per thread
         const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        float s0 = bias[0], s1 = bias[1], s2 = bias[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 xv = unpack_h2(xs[i]);
-          const float2 bb = *reinterpret_cast<const float2*>(s_bias_l + 2 * i);
-          const float f0 = __uint_as_float(v[2 * i]) + (xv.x + bb.x), f1 = __uint_as_float(v[2 * i + 1]) + (xv.y + bb.y);
-          const float4 w0 = *reinterpret_cast<const float4*>(s_head + 8 * i), w1 = *reinterpret_cast<const float4*>(s_head + 8 * i + 4);
-          s0 = fmaf(f0, w0.x, s0); s1 = fmaf(f0, w0.y, s1); s2 = fmaf(f0, w0.z, s2);
-          s0 = fmaf(f1, w1.x, s0); s1 = fmaf(f1, w1.y, s1); s2 = fmaf(f1, w1.z, s2);
+        for (int q = 0; q < 4; ++q) {   // 4 channels = 12 weights = 3 float4 per iteration
+          const float4 wa = *reinterpret_cast<const float4*>(s_head + 12 * q), wb = *reinterpret_cast<const float4*>(s_head + 12 * q + 4);
+          const float4 wc = *reinterpret_cast<const float4*>(s_head + 12 * q + 8);
+          const float2 x01 = unpack_h2(xs[2 * q]), x23 = unpack_h2(xs[2 * q + 1]);
+          const float f0 = __uint_as_float(v[4 * q]) + x01.x, f1 = __uint_as_float(v[4 * q + 1]) + x01.y;
+          const float f2 = __uint_as_float(v[4 * q + 2]) + x23.x, f3 = __uint_as_float(v[4 * q + 3]) + x23.y;
+          s0 = fmaf(f0, wa.x, s0); s1 = fmaf(f0, wa.y, s1); s2 = fmaf(f0, wa.z, s2);
+          s0 = fmaf(f1, wa.w, s0); s1 = fmaf(f1, wb.x, s1); s2 = fmaf(f1, wb.y, s2);
+          s0 = fmaf(f2, wb.z, s0); s1 = fmaf(f2, wb.w, s1); s2 = fmaf(f2, wc.x, s2);
+          s0 = fmaf(f3, wc.y, s0); s1 = fmaf(f3, wc.z, s1); s2 = fmaf(f3, wc.w, s2);
         }
         const float r0o = head_activation_fast(s0), r1o = head_activation_fast(s1), r2o = head_activation_fast(s2);
         if (p.out_u8) {
@@ -288,7 +293,11 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
   for (int i = tid; i < nl * (W_LAYER_BYTES / 16); i += NTHREADS)
     reinterpret_cast<uint4*>(smem + SM_WTS)[i] = reinterpret_cast<const uint4*>(p.wumma + (size_t)(2 * p.blk0) * W_LAYER_BYTES)[i];
   for (int i = tid; i < nl * C; i += NTHREADS) s_bias[i] = p.bias[(size_t)(2 * p.blk0) * C + i];
-  if (tid < C * 4) s_head[tid] = p.whead[tid];
+  if (LAST_PASS) {
+    if (tid < C * 3) s_head[tid] = p.whead[(tid / 3) * 4 + (tid % 3)];   // packed [16][3]
+  } else if (tid < C * 4) {
+    s_head[tid] = p.whead[tid];
+  }
   {
     // stale shared memory may hold NaN patterns; rows outside the valid cone are multiplied (and ignored), so start clean
     const uint32_t ro = rings_offset(nl), n16 = (smem_bytes(nl) - ro) / 16;
@@ -321,6 +330,14 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) bias[i] = s_bias[tl[k] * C + i];   // at most one conv_b layer per warp (nl = 2, 4)
       }
+    if (LAST_PASS) {   // the head's share of the last conv_b's BN constant (the other conv_b layers read s_bias per task)
+      for (int ch = 0; ch < C; ++ch) {
+        const float bv = p.bias[(size_t)(2 * p.blk0 + nl - 1) * C + ch];
+        bias[0] = fmaf(bv, p.whead[ch * 4 + 0], bias[0]);
+        bias[1] = fmaf(bv, p.whead[ch * 4 + 1], bias[1]);
+        bias[2] = fmaf(bv, p.whead[ch * 4 + 2], bias[2]);
+      }
+    }
     for (int blk = set; blk < 32; blk += 4) tmem_zero16(E.tq + blk * 16);
     tmem_wait_st();
     tc_fence_before();
@@ -341,7 +358,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         E.gb0 = (int)(gg % K0);
       }
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
-        mbar_wait(bars + (BAR_MMA + (S & 1u)) * 8, (S >> 1) & 1u);
+        mbar_wait_sleep(bars + (BAR_MMA + (S & 1u)) * 8, (S >> 1) & 1u);
         tc_fence_after();
         for (int k = 0; k < ntask; ++k) {
           const int l = tl[k], w = sr - LAG * l - 1;
@@ -395,11 +412,11 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         if (elect_one_sync()) {
           STREAM_TRACE(1);
           if (!p.helper) {
-            if (S >= 2) mbar_wait(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
-            if (sr == 0 && S >= 1) mbar_wait(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
+            if (S >= 2) mbar_wait_sleep(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
+            if (sr == 0 && S >= 1) mbar_wait_sleep(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
             if (sr < Gm) {
               const long long k = gg + sr;
-              mbar_wait(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (uint32_t)(k / K0) & 1u);
+              mbar_wait_sleep(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (uint32_t)(k / K0) & 1u);
             }
             tc_fence_after();
           }
@@ -482,12 +499,12 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
       a += sg.yb - sg.ya;
       const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
-        if (lane == 0 && S >= 2) mbar_wait(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
+        if (lane == 0 && S >= 2) mbar_wait_sleep(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
         if (lane == 1 && sr < Gm) {
           const long long k = gg + sr;
-          mbar_wait(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (uint32_t)(k / K0) & 1u);
+          mbar_wait_sleep(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (uint32_t)(k / K0) & 1u);
         }
-        if (lane == 2 && sr == 0 && S >= 1) mbar_wait(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
+        if (lane == 2 && sr == 0 && S >= 1) mbar_wait_sleep(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
         __syncwarp();
         tc_fence_before();
         asm volatile("bar.arrive %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");
@@ -505,7 +522,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         const int gx0 = sg.j * p.tw - halo, y00 = sg.ya - nl;
         for (int g = 0; g < Gm; ++g, ++gg) {
           const uint32_t k = (uint32_t)(gg % K0), n = (uint32_t)(gg / K0);
-          if (n >= 1) mbar_wait(bars + (BAR_XFREE + k) * 8, (n - 1) & 1u);
+          if (n >= 1) mbar_wait_sleep(bars + (BAR_XFREE + k) * 8, (n - 1) & 1u);
           const uint32_t bar = bars + (BAR_XFULL + k) * 8;
           mbar_arrive_expect_tx(bar, 2 * GROUP_BYTES);
           const uint32_t dst = R.x0 + k * GROUP_BYTES;

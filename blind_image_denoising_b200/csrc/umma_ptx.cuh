@@ -60,6 +60,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
   } while (!done);
 }
+// the same with a suspend-time hint (the thread sleeps in hardware until the phase completes or the hint expires):
+// fewer polls, each of which is a shared-memory wavefront competing with the tensor-core operand fetches
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t mbar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done) : "r"(mbar), "r"(parity), "r"(0x989680u) : "memory");
+  } while (!done);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
