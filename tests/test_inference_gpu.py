@@ -191,3 +191,38 @@ def test_base_kernel_sizes(native_lib, k0):
         m = bf.Denoiser(arch, v, precision=prec)
         _check(m(x, return_float=True), yref, m(x), u8ref, prec)
         m.close()
+
+
+@pytest.mark.parametrize("n_layers,shape", [
+    (6, (96, 24, 40, 3)),      # many short strips: every CTA of the streaming kernel walks several segments
+    (3, (40, 17, 300, 3)),     # odd block count (last pass has one block = two conv layers), 3 strips per image
+    (6, (3, 700, 130, 3)),     # tall strips cut in the middle by the equal-share partition
+])
+def test_streaming_segments(native_lib, n_layers, shape):
+    """fused_stream.cu: segment hand-over inside a CTA (pipeline drain, TMEM ring restart, X0 ring running on across
+    segments), odd block counts and strip cuts -- against the oracle, and bit-identical to the same images run one by one."""
+    rng = np.random.default_rng(11)
+    x = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    m = _model(n_layers, precision="f16")
+    yref, u8ref = _oracle(n_layers, x)
+    y, u8 = m(x, return_float=True), m(x)
+    _check(y, yref, u8, u8ref, "f16")
+    for i in (0, shape[0] // 2, shape[0] - 1):
+        assert np.array_equal(m(x[i:i + 1]), u8[i:i + 1])
+    m.close()
+
+
+def test_streaming_matches_region_engine(native_lib, monkeypatch):
+    """The row-streaming stack and the region kernel (BFCNN_UMMA_REGIONS=1) run the same arithmetic up to the order of the
+    residual add and the head's tanh evaluation; both round activations to fp16 after every layer, so over 36 layers the
+    uint8 results differ by at most 1 LSB on a modest fraction of values (each is within the f16 gate of the oracle)."""
+    x = np.random.default_rng(12).integers(0, 256, size=(2, 333, 517, 3), dtype=np.uint8)
+    m = _model(18, precision="f16")
+    a = m(x)
+    monkeypatch.setenv("BFCNN_UMMA_REGIONS", "1")
+    b = m(x)
+    monkeypatch.delenv("BFCNN_UMMA_REGIONS")
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 0.15
+    assert np.array_equal(a, m(x))
+    m.close()
