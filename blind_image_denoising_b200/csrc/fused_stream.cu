@@ -10,6 +10,7 @@
 //
 //   step s:  MMA issuer      layer l multiplies its input rows {2g, 2g+1}, g = s - 3l           (one elected thread)
 //            epilogue warps  layer l drains its output rows    {2w, 2w+1}, w = s - 3l - 1       (16 warps)
+//            barrier helper  waits on the mbarriers of step s for the issuer                    (one warp)
 //            TMA producer    input rows of layer 0, K0 groups deep ring                          (one elected thread)
 //
 //   * Shared memory holds four row RINGS (fp16, two channel-half planes each): X0 (TMA input of block 0, also the
@@ -20,10 +21,13 @@
 //     three blocks straddle the ring end is issued as N = 32 + N = 16 (2 input rows in 32); every output row still
 //     receives its nine partial products in the same order, so results do not depend on where a row sits in the ring
 //     -- strips, crops and whole frames stay bit-identical (tests/test_inference_gpu.py).
-//   * mbarriers: mma_done[s & 1] (tcgen05.commit after the MMAs of step s), epi_done[s & 1] (every epilogue thread,
-//     end of step s).  The issuer of step s waits for epi_done(s - 2), so the epilogue of step s - 1 overlaps the MMAs
-//     of step s; LAG = 3 is the smallest lag for which layer l+1's input group is already written by then.
-//     x_full[k] / x_free[k] (k < K0) couple the TMA producer to the issuer and to the block-0 residual readers.
+//   * mbarriers: mma_done[s & 1] (tcgen05.commit after the MMAs of step s), epi_done[s & 1] (one arrival per epilogue
+//     warp at the end of step s).  Step s may be issued once epi_done(s - 2) has completed, so the epilogue of step s - 1
+//     overlaps the MMAs of step s; LAG = 3 is the smallest lag for which layer l+1's input group is already written by
+//     then.  x_full[k] / x_free[k] (k < K0) couple the TMA producer to the issuer and to the block-0 residual readers.
+//   * The issuing thread never touches shared memory (a completed mbarrier.try_wait on it costs ~360 cycles of
+//     tensor-pipe bubble, tools/umma_probe3.cu): the helper warp does the waits and releases it through a named barrier.
+//     Its descriptor arithmetic is incremental (from scratch it cost 40 % of the issue time).
 //   * Rows outside a layer's valid cone (the first / last rows of a segment, the halo columns) are computed and
 //     ignored; rows / columns outside the work extent are forced to zero by every epilogue (per-layer "same" padding).
 //
@@ -79,8 +83,6 @@ struct Params {
   long long total_rows, share;    // linearised (image, strip, row) space and the rows of it each CTA owns
   long long* trace;               // debug timeline (BFCNN_STREAM_TRACE=1) of CTA trace_block, steps [TRACE_S0, TRACE_S0 + 32)
   int trace_block;
-  int helper;                     // 1: the issuer's barrier waits are done by the helper warp (default)
-  int dbg;                        // timing experiments only (wrong results): 1 skip epilogue st.shared, 2 skip ld.shared, 4 skip fences
 };
 constexpr uint32_t TRACE_S0 = 100;
 #ifdef BFCNN_STREAM_TRACE_BUILD   // compile-time: the timeline costs the issuer ~5 % even when it is switched off at run time
@@ -154,10 +156,8 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
     hi.x = relu_h2(pack_h2(__uint_as_float(v[8]), __uint_as_float(v[9]))) & m; hi.y = relu_h2(pack_h2(__uint_as_float(v[10]), __uint_as_float(v[11]))) & m;
     hi.z = relu_h2(pack_h2(__uint_as_float(v[12]), __uint_as_float(v[13]))) & m; hi.w = relu_h2(pack_h2(__uint_as_float(v[14]), __uint_as_float(v[15]))) & m;
     const uint32_t dst = (l == 0 ? R.t0 : R.t1) + (uint32_t)(rho & (2 * KT - 1)) * ROW_BYTES + E.pix;
-    if (!(p.dbg & 1)) {
-      sts128(dst, lo);
-      sts128(dst + R.t_plane, hi);
-    }
+    sts128(dst, lo);
+    sts128(dst + R.t_plane, hi);
     if (tp) tp[3] = clock64();
   } else {
     // residual: X of this block (fp16) + the BN constant b' + the accumulator
@@ -170,8 +170,7 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
       xsrc = R.x1 + (uint32_t)(rho & (2 * KX - 1)) * ROW_BYTES + E.pix;
       xplane = R.x1_plane;
     }
-    uint4 xa = make_uint4(0u, 0u, 0u, 0u), xb = xa;
-    if (!(p.dbg & 2)) { xa = lds128(xsrc); xb = lds128(xsrc + xplane); }
+    const uint4 xa = lds128(xsrc), xb = lds128(xsrc + xplane);
     tmem_ld_wait(v);
     tmem_zero16(taddr);
     if (KIND == KIND_B_OUT && LAST_PASS) {
@@ -235,10 +234,8 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
         const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
         lo.x &= m; lo.y &= m; lo.z &= m; lo.w &= m; hi.x &= m; hi.y &= m; hi.z &= m; hi.w &= m;
         const uint32_t dst = R.x1 + (uint32_t)(rho & (2 * KX - 1)) * ROW_BYTES + E.pix;
-        if (!(p.dbg & 1)) {
-          sts128(dst, lo);
-          sts128(dst + R.x1_plane, hi);
-        }
+        sts128(dst, lo);
+        sts128(dst + R.x1_plane, hi);
       } else if (E.col_out && inside && rho >= E.nl && rho < E.P - E.nl) {
         uint4* o = reinterpret_cast<uint4*>(E.fout_col + (long long)rho * E.row_halves);
         o[0] = lo;
@@ -369,7 +366,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
           else if (l + 1 < nl) epi_task<KIND_B_TO_X, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
           else epi_task<KIND_B_OUT, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
         }
-        if (!(p.dbg & 4)) fence_async_smem();   // T / X stores of this step -> async proxy (tensor core reads)
+        fence_async_smem();   // T / X stores of this step -> async proxy (tensor core reads)
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -407,19 +404,10 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
       }
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
         if (lane == 0) STREAM_TRACE(0);
-        if (p.helper) asm volatile("bar.sync %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");   // the helper has seen this step's barriers
+        asm volatile("bar.sync %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");   // the helper has seen this step's barriers
         tc_fence_after();
         if (elect_one_sync()) {
           STREAM_TRACE(1);
-          if (!p.helper) {
-            if (S >= 2) mbar_wait_sleep(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
-            if (sr == 0 && S >= 1) mbar_wait_sleep(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
-            if (sr < Gm) {
-              const long long k = gg + sr;
-              mbar_wait_sleep(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (uint32_t)(k / K0) & 1u);
-            }
-            tc_fence_after();
-          }
 #pragma unroll
           for (int l = 0; l < MAX_NL; ++l) {
             if (l >= nl) break;
@@ -431,13 +419,14 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             const uint64_t ad = st_ad[l];
             const int blk0 = st_blk[l];   // accumulator block of output row 2g - 1
             const int rho0 = 2 * g;
-            {
+            // advance the state AFTER the MMAs are queued (the thread would otherwise block on the full queue anyway)
+            auto advance = [&]() {
               st_blk[l] = (blk0 + 2) & 31;
               const int rows = (l == 0) ? 2 * K0 : ((l == 2) ? 2 * KX : 2 * KT);
               st_slot[l] += 2;
               st_ad[l] = ad + 2 * RW;
               if (st_slot[l] >= rows) { st_slot[l] -= rows; st_ad[l] -= (uint64_t)(rows * RW); }
-            }
+            };
             if (rho0 >= 1 && rho0 + 2 < P && blk0 <= 28) {
               // fast path (7 groups in 8): both rows are interior rows of the segment and their four accumulator blocks
               // do not wrap around the TMEM ring -> six N = 48 MMAs, straight-line
@@ -449,6 +438,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
               mma_f16_ss(d + 16, ad + RW, bd, id, 1u);
               mma_f16_ss(d + 16, ad + RW + 1, bd + (48 * 16 * 2 / 16), id, 1u);
               mma_f16_ss(d + 16, ad + RW + 2, bd + 2 * (48 * 16 * 2 / 16), id, 1u);
+              advance();
               continue;
             }
 #pragma unroll
@@ -477,6 +467,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 mma_f16_ss(tmem, adr + 2, b + 2 * (48 * 16 * 2 / 16), id, 1u);
               }
             }
+            advance();
           }
           STREAM_TRACE(2);
           umma_commit(bars + (BAR_MMA + (S & 1u)) * 8);
@@ -494,7 +485,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     // restarts at row 0).  One barrier per lane, in parallel.
     uint32_t S = 0;
     long long gg = 0;
-    for (long long a = r0; a < r1 && p.helper;) {
+    for (long long a = r0; a < r1;) {
       const Seg sg = seg_at(p, a, r1);
       a += sg.yb - sg.ya;
       const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
@@ -584,8 +575,6 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
     BF_REQUIRE(smem <= (size_t)MAX_SMEM, "internal: streaming pass does not fit in shared memory");
     static const int trace_on = getenv("BFCNN_STREAM_TRACE") ? atoi(getenv("BFCNN_STREAM_TRACE")) : 0;
     p.trace = nullptr; p.trace_block = 0;
-    p.helper = getenv("BFCNN_STREAM_HELPER") ? atoi(getenv("BFCNN_STREAM_HELPER")) : 1;
-    p.dbg = getenv("BFCNN_STREAM_DBG") ? atoi(getenv("BFCNN_STREAM_DBG")) : 0;
     if (trace_on && ps == std::min(1, passes - 1)) {
       BF_CHECK(h->ws_feat[2].reserve(264 * sizeof(long long)));
       BF_CUDA(cudaMemsetAsync(h->ws_feat[2].p, 0, 264 * sizeof(long long), st));
