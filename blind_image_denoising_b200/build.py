@@ -45,7 +45,8 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: str):
         obj = objdir / (src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        extra = os.environ.get("BFCNN_NVCC_EXTRA", "").split()   # e.g. -DBFCNN_STREAM_TRACE_BUILD (kernel timeline)
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs[src] = r.stdout + r.stderr
         if r.returncode != 0:

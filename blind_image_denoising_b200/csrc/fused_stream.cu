@@ -113,6 +113,18 @@ struct Rings {
 
 enum Kind { KIND_A = 0, KIND_B_TO_X = 1, KIND_B_OUT = 2 };
 
+// Every shared-memory descriptor of this kernel has SBO = 128 B, version 1, SWIZZLE_NONE: the high word is one constant
+// and the issuer's arithmetic (tap shifts, ring rows, weight blocks) touches the 14-bit start-address field of the low
+// word only -- 32-bit adds instead of 64-bit ones on the issuing thread.
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ void mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc)
+      : "memory");
+}
+
 // model.py:342 tanh(2y)*0.51, then utilities.py:435-443 (clip(+-0.5)+0.5)*255, with tanh(z) = 1 - 2/(exp(2z)+1) on the
 // fast exp / divide units (absolute error ~1e-6 of the +-1 range, 1e-4 on the 0-255 scale): the head sits on the
 // epilogue's critical path in the last pass
@@ -382,9 +394,9 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     // bar.sync 2 + (S & 1): hardware barrier, no shared-memory traffic).
     asm volatile("bar.sync 1, %0;\n" ::"r"(32 * (EPI_WARPS + 1)) : "memory");   // accumulators are zero
     const uint32_t idesc0 = make_idesc_f16(128, 0);   // + (blocks * 2) << 17: N = 16 per accumulator block
-    const uint64_t adesc_x0 = make_desc(R.x0, R.x0_plane, 128), adesc_t0 = make_desc(R.t0, R.t_plane, 128);
-    const uint64_t adesc_x1 = make_desc(R.x1, R.x1_plane, 128), adesc_t1 = make_desc(R.t1, R.t_plane, 128);
-    const uint64_t bdesc0 = make_desc(s0 + SM_WTS, 48 * 16, 128);
+    const uint32_t adesc_x0 = desc_lo(R.x0, R.x0_plane), adesc_t0 = desc_lo(R.t0, R.t_plane);
+    const uint32_t adesc_x1 = desc_lo(R.x1, R.x1_plane), adesc_t1 = desc_lo(R.t1, R.t_plane);
+    const uint32_t bdesc0 = desc_lo(s0 + SM_WTS, 48 * 16);
     uint32_t S = 0;
     long long gg = 0;
     for (long long a = r0; a < r1;) {
@@ -393,13 +405,13 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
       const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
       const int gb0 = (int)(gg % K0);
       // per-layer issue state at the layer's group 0: A descriptor of input row 0 (pixel -1), its ring row, TMEM block of row -1
-      uint64_t st_ad[MAX_NL];
+      uint32_t st_ad[MAX_NL];
       int st_slot[MAX_NL], st_blk[MAX_NL];
 #pragma unroll
       for (int l = 0; l < MAX_NL; ++l) {
-        const uint64_t adl = l == 0 ? adesc_x0 : (l == 1 ? adesc_t0 : (l == 2 ? adesc_x1 : adesc_t1));
+        const uint32_t adl = l == 0 ? adesc_x0 : (l == 1 ? adesc_t0 : (l == 2 ? adesc_x1 : adesc_t1));
         st_slot[l] = (l == 0) ? 2 * gb0 : 0;
-        st_ad[l] = adl + (uint64_t)(st_slot[l] * RW - 1);
+        st_ad[l] = adl + (uint32_t)(st_slot[l] * RW - 1);
         st_blk[l] = (14 * l - 1) & 31;
       }
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
@@ -413,10 +425,10 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             if (l >= nl) break;
             const int g = sr - LAG * l;
             if (g < 0 || g >= Gm) continue;
-            const uint64_t bd = bdesc0 + (uint64_t)(l * (W_LAYER_BYTES / 16));
+            const uint32_t bd = bdesc0 + (uint32_t)(l * (W_LAYER_BYTES / 16));
             // incremental state of the layer (the issuing thread must not fall behind the shallow MMA queue: descriptor
             // arithmetic from scratch cost ~200 cycles per group of six MMAs, 40 % of the issue time)
-            const uint64_t ad = st_ad[l];
+            const uint32_t ad = st_ad[l];
             const int blk0 = st_blk[l];   // accumulator block of output row 2g - 1
             const int rho0 = 2 * g;
             // advance the state AFTER the MMAs are queued (the thread would otherwise block on the full queue anyway)
@@ -425,19 +437,19 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
               const int rows = (l == 0) ? 2 * K0 : ((l == 2) ? 2 * KX : 2 * KT);
               st_slot[l] += 2;
               st_ad[l] = ad + 2 * RW;
-              if (st_slot[l] >= rows) { st_slot[l] -= rows; st_ad[l] -= (uint64_t)(rows * RW); }
+              if (st_slot[l] >= rows) { st_slot[l] -= rows; st_ad[l] -= (uint32_t)(rows * RW); }
             };
             if (rho0 >= 1 && rho0 + 2 < P && blk0 <= 28) {
               // fast path (7 groups in 8): both rows are interior rows of the segment and their four accumulator blocks
               // do not wrap around the TMEM ring -> six N = 48 MMAs, straight-line
               const uint32_t d = tmem + (uint32_t)blk0 * 16u;
               const uint32_t id = idesc0 + (6u << 17);
-              mma_f16_ss(d, ad, bd, id, 1u);
-              mma_f16_ss(d, ad + 1, bd + (48 * 16 * 2 / 16), id, 1u);
-              mma_f16_ss(d, ad + 2, bd + 2 * (48 * 16 * 2 / 16), id, 1u);
-              mma_f16_ss(d + 16, ad + RW, bd, id, 1u);
-              mma_f16_ss(d + 16, ad + RW + 1, bd + (48 * 16 * 2 / 16), id, 1u);
-              mma_f16_ss(d + 16, ad + RW + 2, bd + 2 * (48 * 16 * 2 / 16), id, 1u);
+              mma_lo(d, ad, bd, id);
+              mma_lo(d, ad + 1, bd + (48 * 16 * 2 / 16), id);
+              mma_lo(d, ad + 2, bd + 2 * (48 * 16 * 2 / 16), id);
+              mma_lo(d + 16, ad + RW, bd, id);
+              mma_lo(d + 16, ad + RW + 1, bd + (48 * 16 * 2 / 16), id);
+              mma_lo(d + 16, ad + RW + 2, bd + 2 * (48 * 16 * 2 / 16), id);
               advance();
               continue;
             }
@@ -445,7 +457,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             for (int par = 0; par < 2; ++par) {
               const int rho = rho0 + par;
               if (rho >= P) break;
-              const uint64_t adr = ad + (uint64_t)(par * RW);
+              const uint32_t adr = ad + (uint32_t)(par * RW);
               // accumulator blocks of output rows rho-1, rho, rho+1 (B blocks 0, 1, 2); the segment's first / last input
               // row has no row above / below
               const int jlo = (rho == 0) ? 1 : 0, jhi = (rho == P - 1) ? 1 : 2;
@@ -453,18 +465,18 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
               const int n1 = min(nb, 32 - blk_lo);
               {
                 const uint32_t d = tmem + (uint32_t)blk_lo * 16u;
-                const uint64_t b = bd + (uint64_t)(jlo * 16);
+                const uint32_t b = bd + (uint32_t)(jlo * 16);
                 const uint32_t id = idesc0 + ((uint32_t)(2 * n1) << 17);
-                mma_f16_ss(d, adr, b, id, 1u);
-                mma_f16_ss(d, adr + 1, b + (48 * 16 * 2 / 16), id, 1u);
-                mma_f16_ss(d, adr + 2, b + 2 * (48 * 16 * 2 / 16), id, 1u);
+                mma_lo(d, adr, b, id);
+                mma_lo(d, adr + 1, b + (48 * 16 * 2 / 16), id);
+                mma_lo(d, adr + 2, b + 2 * (48 * 16 * 2 / 16), id);
               }
               if (n1 < nb) {   // the blocks wrap around the TMEM ring: second part at column 0
-                const uint64_t b = bd + (uint64_t)((jlo + n1) * 16);
+                const uint32_t b = bd + (uint32_t)((jlo + n1) * 16);
                 const uint32_t id = idesc0 + ((uint32_t)(2 * (nb - n1)) << 17);
-                mma_f16_ss(tmem, adr, b, id, 1u);
-                mma_f16_ss(tmem, adr + 1, b + (48 * 16 * 2 / 16), id, 1u);
-                mma_f16_ss(tmem, adr + 2, b + 2 * (48 * 16 * 2 / 16), id, 1u);
+                mma_lo(tmem, adr, b, id);
+                mma_lo(tmem, adr + 1, b + (48 * 16 * 2 / 16), id);
+                mma_lo(tmem, adr + 2, b + 2 * (48 * 16 * 2 / 16), id);
               }
             }
             advance();
