@@ -17,7 +17,7 @@ import numpy as np
 from . import _native
 from .arch import (Arch, arch_from_config, arch_from_name, arch_from_variable_shapes,
                    default_pipeline_config)
-from .denoiser import Denoiser
+from .denoiser import Denoiser, PipelinedDenoiser
 from .tensorbundle import read_model_variables, write_model_variables
 from .weights import synthetic_variables
 
@@ -138,7 +138,7 @@ def synthetic_model(no_layers: int, seed: int = 0, **kwargs) -> Denoiser:
 
 __all__ = [
     "models", "configs", "CONFIGS_DICT", "load_model", "load_denoiser_model",
-    "load_default_denoiser", "load_config", "load_variables", "synthetic_model", "Denoiser", "Arch",
+    "load_default_denoiser", "load_config", "load_variables", "synthetic_model", "Denoiser", "PipelinedDenoiser", "Arch",
     "arch_from_config", "arch_from_name", "default_pipeline_config", "synthetic_variables",
     "read_model_variables", "write_model_variables",
 ]

@@ -90,6 +90,13 @@ int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int
     BF_CHECK(pack_weights(h));
   }
   const bool in_host = !(flags & BFCNN_FLAG_IN_DEVICE), out_host = !(flags & BFCNN_FLAG_OUT_DEVICE);
+  if (in_host && out_host && st == nullptr) {
+    // host in, host out, no caller stream: run on a stream the handle owns instead of the legacy default stream, so
+    // that two handles driven from two host threads overlap (the copies of one batch with the conv stack of the other;
+    // blind_image_denoising_b200.PipelinedDenoiser).  The call still returns only after its D2H copy has completed.
+    if (!h->s_compute) BF_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    st = h->s_compute;
+  }
   if (in_host) BF_CHECK(h->ws_in.reserve(in_bytes));
   if (out_host) BF_CHECK(h->ws_out.reserve(out_bytes));
   const uint8_t* d_in = in_host ? h->ws_in.as<uint8_t>() : in;
@@ -228,6 +235,7 @@ void bfcnn_destroy(bfcnn_handle* h) {
   h->ws_train.release(); h->ws_stats.release(); h->ws_grads.release();
   h->adam_m.release(); h->adam_v.release();
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->s_compute) cudaStreamDestroy(h->s_compute);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
   if (h->ev0) cudaEventDestroy(h->ev0);

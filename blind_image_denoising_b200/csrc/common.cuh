@@ -103,6 +103,7 @@ struct bfcnn_handle {
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the host-buffer pipeline (api.cu)
+  cudaStream_t s_compute = nullptr;               // compute stream of host-to-host calls without a caller stream (api.cu)
   std::vector<cudaEvent_t> ev_pool;
   bool ev_valid = false;
   int sm_count = 148;

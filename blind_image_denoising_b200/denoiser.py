@@ -115,3 +115,43 @@ class Denoiser:
             out = np.empty((n, h, w, 3), dtype=np.float32 if return_float else np.uint8)
         _native.check(fn(self._h, x.ctypes.data, out.ctypes.data, n, h, w, prec, flags, None))
         return out
+
+
+class PipelinedDenoiser:
+    """`depth` model instances on ONE GPU fed from a small thread pool.
+
+    A `Denoiser` call on host arrays returns only after its result has been copied back, so a single instance leaves
+    the GPU idle while the first chunk goes up and the last one comes down.  ctypes releases the GIL and every handle
+    owns its streams and workspaces, so with two instances the copies of one batch overlap the conv stack of the
+    other.  `map` keeps the order of its inputs; `__call__` is the plain synchronous call on instance 0."""
+
+    def __init__(self, factory, depth: int = 2):
+        from concurrent.futures import ThreadPoolExecutor
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.models = [factory() for _ in range(depth)]
+        # one worker thread per instance: a handle is not re-entrant (SURVEY 8b), calls on it stay in order
+        self._pools = [ThreadPoolExecutor(max_workers=1) for _ in range(depth)]
+
+    def __call__(self, image, **kwargs):
+        return self.models[0](image, **kwargs)
+
+    def map(self, images, outs=None, **kwargs):
+        """Denoise a sequence of host batches; yields the results in order (outs: optional matching output buffers)."""
+        futures = []
+        for i, x in enumerate(images):
+            k = i % len(self.models)
+            kw = dict(kwargs)
+            if outs is not None:
+                kw["out"] = outs[i]
+            futures.append(self._pools[k].submit(self.models[k], x, **kw))
+            if len(futures) >= 2 * len(self.models):   # bounded look-ahead
+                yield futures.pop(0).result()
+        for f in futures:
+            yield f.result()
+
+    def close(self):
+        for pl in self._pools:
+            pl.shutdown(wait=True)
+        for m in self.models:
+            m.close()

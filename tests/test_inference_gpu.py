@@ -226,3 +226,19 @@ def test_streaming_matches_region_engine(native_lib, monkeypatch):
     assert d.max() <= 1 and (d > 0).mean() < 0.15
     assert np.array_equal(a, m(x))
     m.close()
+
+
+def test_pipelined_denoiser_matches_single_instance(native_lib):
+    """PipelinedDenoiser.map: two model instances on one GPU driven from two host threads (the copies of one batch
+    overlap the conv stack of the other); results come back in input order and equal the single-instance call."""
+    import blind_image_denoising_b200 as bf
+    rng = np.random.default_rng(21)
+    batches = [rng.integers(0, 256, size=(2, 300, 200 + 16 * i, 3), dtype=np.uint8) for i in range(7)]
+    single = _model(6, precision="f16", pad_pow2=False)
+    ref = [single(b) for b in batches]
+    single.close()
+    pipe = bf.PipelinedDenoiser(lambda: _model(6, precision="f16", pad_pow2=False), depth=2)
+    got = list(pipe.map(batches))
+    assert len(got) == len(ref) and all(np.array_equal(a, b) for a, b in zip(got, ref))
+    assert np.array_equal(pipe(batches[0]), ref[0])
+    pipe.close()
