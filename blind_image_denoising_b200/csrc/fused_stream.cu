@@ -21,8 +21,9 @@
 //     three blocks straddle the ring end is issued as N = 32 + N = 16 (2 input rows in 32); every output row still
 //     receives its nine partial products in the same order, so results do not depend on where a row sits in the ring
 //     -- strips, crops and whole frames stay bit-identical (tests/test_inference_gpu.py).
-//   * mbarriers: mma_done[s & 1] (tcgen05.commit after the MMAs of step s), epi_done[s & 1] (one arrival per epilogue
-//     warp at the end of step s).  Step s may be issued once epi_done(s - 2) has completed, so the epilogue of step s - 1
+//   * mbarriers: mma_done[l][s & 1] (tcgen05.commit after layer l's MMAs of step s: the epilogue of layer l runs while
+//     the later layers of the step are still being multiplied), epi_done[s & 1] (one arrival per epilogue warp at the end
+//     of step s).  Step s may be issued once epi_done(s - 2) has completed, so the epilogue of step s - 1
 //     overlaps the MMAs of step s; LAG = 3 is the smallest lag for which layer l+1's input group is already written by
 //     then.  x_full[k] / x_free[k] (k < K0) couple the TMA producer to the issuer and to the block-0 residual readers.
 //   * The issuing thread never touches shared memory (a completed mbarrier.try_wait on it costs ~360 cycles of
@@ -47,9 +48,10 @@ constexpr int EPI_WARPS = 16;           // 4 sets x 4 TMEM lane quarters
 constexpr int WARP_MMA = 16;            // warp 16 issues the MMAs, warp 17 waits on its barriers, warp 18 is the TMA producer
 constexpr int NTHREADS = 32 * 19;
 constexpr int LAG = 3;                  // steps between consecutive layers
-constexpr int K0 = 12;                  // X0 ring: groups of 2 rows (TMA prefetch depth)
+constexpr int K0 = 11;                  // X0 ring: groups of 2 rows (TMA prefetch depth)
 constexpr int KX = 8;                   // X1 ring groups: written at step w+4, last read (residual) at step w+10
-constexpr int KT = 2;                   // T rings: written at step w+1, read by the MMAs of step w+3
+constexpr int KT = 3;                   // T rings: written by the epilogue of layer l at step w+1 (which has only seen layer l's
+                                        // MMAs of that step), read by the MMAs of layer l+1 at step w+3: three groups
 constexpr int ROW_BYTES = RW * 16;      // one row of one channel-half plane
 constexpr int GROUP_BYTES = 2 * ROW_BYTES;
 constexpr int W_LAYER_BYTES = 3 * 48 * 16 * 2;   // B operand of one conv: [dx 3][N 48][K 16] fp16
@@ -58,7 +60,9 @@ constexpr int MAX_NL = 4;
 constexpr int MIN_SHARE = 24;           // rows per CTA below which fewer CTAs are launched
 
 // barriers (8 B each)
-constexpr uint32_t BAR_MMA = 0, BAR_EPI = 2, BAR_XFULL = 4, BAR_XFREE = 4 + K0, NBARS = 4 + 2 * K0;
+// mma_done[l][s & 1] (per layer: the epilogue of layer l starts while the later layers of the step are still being
+// multiplied), epi_done[s & 1], x_full[k], x_free[k]
+constexpr uint32_t BAR_MMA = 0, BAR_EPI = 2 * 4, BAR_XFULL = BAR_EPI + 2, BAR_XFREE = BAR_XFULL + K0, NBARS = BAR_XFREE + K0;
 constexpr uint32_t SM_BARS = 0, SM_TMEM = 512, SM_HEAD = 528, SM_BIAS = 784, SM_WTS = 1152;
 
 __host__ __device__ inline uint32_t plane_bytes_of(int rows) { return (uint32_t)(rows * RW + 2 * SLACK_PX) * 16u; }
@@ -167,7 +171,7 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
     lo.z = relu_h2(pack_h2(__uint_as_float(v[4]), __uint_as_float(v[5]))) & m; lo.w = relu_h2(pack_h2(__uint_as_float(v[6]), __uint_as_float(v[7]))) & m;
     hi.x = relu_h2(pack_h2(__uint_as_float(v[8]), __uint_as_float(v[9]))) & m; hi.y = relu_h2(pack_h2(__uint_as_float(v[10]), __uint_as_float(v[11]))) & m;
     hi.z = relu_h2(pack_h2(__uint_as_float(v[12]), __uint_as_float(v[13]))) & m; hi.w = relu_h2(pack_h2(__uint_as_float(v[14]), __uint_as_float(v[15]))) & m;
-    const uint32_t dst = (l == 0 ? R.t0 : R.t1) + (uint32_t)(rho & (2 * KT - 1)) * ROW_BYTES + E.pix;
+    const uint32_t dst = (l == 0 ? R.t0 : R.t1) + ((uint32_t)rho % (2 * KT)) * ROW_BYTES + E.pix;
     sts128(dst, lo);
     sts128(dst + R.t_plane, hi);
     if (tp) tp[3] = clock64();
@@ -331,6 +335,10 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     // this warp's tasks of a step: t = set, set + 4 (< 2 nl): row parity t / nl of layer (t + parity) % nl
     int tl[2], tpar[2], ntask = 0;
     for (int t = set; t < 2 * nl && ntask < 2; t += 4) { tpar[ntask] = t / nl; tl[ntask] = (t + tpar[ntask]) % nl; ++ntask; }
+    if (ntask == 2 && tl[1] < tl[0]) {   // lower layer first: its MMAs of a step complete first
+      const int a_ = tl[0], b_ = tpar[0];
+      tl[0] = tl[1]; tpar[0] = tpar[1]; tl[1] = a_; tpar[1] = b_;
+    }
     float bias[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) bias[i] = 0.f;
@@ -367,10 +375,10 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         E.gb0 = (int)(gg % K0);
       }
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
-        mbar_wait_sleep(bars + (BAR_MMA + (S & 1u)) * 8, (S >> 1) & 1u);
-        tc_fence_after();
         for (int k = 0; k < ntask; ++k) {
           const int l = tl[k], w = sr - LAG * l - 1;
+          mbar_wait_sleep(bars + (BAR_MMA + 2u * (uint32_t)l + (S & 1u)) * 8, (S >> 1) & 1u);
+          tc_fence_after();
           if (w < 0 || w >= Gm) continue;
           const int rho = 2 * w + tpar[k];
           if ((l & 1) == 0) epi_task<KIND_A, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho,
@@ -424,7 +432,8 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
           for (int l = 0; l < MAX_NL; ++l) {
             if (l >= nl) break;
             const int g = sr - LAG * l;
-            if (g < 0 || g >= Gm) continue;
+            const uint32_t mbar_l = bars + (BAR_MMA + 2u * (uint32_t)l + (S & 1u)) * 8;
+            if (g < 0 || g >= Gm) { umma_commit(mbar_l); continue; }
             const uint32_t bd = bdesc0 + (uint32_t)(l * (W_LAYER_BYTES / 16));
             // incremental state of the layer (the issuing thread must not fall behind the shallow MMA queue: descriptor
             // arithmetic from scratch cost ~200 cycles per group of six MMAs, 40 % of the issue time)
@@ -450,6 +459,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
               mma_lo(d + 16, ad + RW, bd, id);
               mma_lo(d + 16, ad + RW + 1, bd + (48 * 16 * 2 / 16), id);
               mma_lo(d + 16, ad + RW + 2, bd + 2 * (48 * 16 * 2 / 16), id);
+              umma_commit(mbar_l);
               advance();
               continue;
             }
@@ -479,10 +489,10 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 mma_lo(tmem, adr + 2, b + 2 * (48 * 16 * 2 / 16), id);
               }
             }
+            umma_commit(mbar_l);
             advance();
           }
           STREAM_TRACE(2);
-          umma_commit(bars + (BAR_MMA + (S & 1u)) * 8);
           STREAM_TRACE(3);
         }
         __syncwarp();
