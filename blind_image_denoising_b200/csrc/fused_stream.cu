@@ -335,7 +335,9 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     // this warp's tasks of a step: t = set, set + 4 (< 2 nl): row parity t / nl of layer (t + parity) % nl
     int tl[2], tpar[2], ntask = 0;
     for (int t = set; t < 2 * nl && ntask < 2; t += 4) { tpar[ntask] = t / nl; tl[ntask] = (t + tpar[ntask]) % nl; ++ntask; }
-    if (ntask == 2 && tl[1] < tl[0]) {   // lower layer first: its MMAs of a step complete first
+    // the layer whose MMAs are issued first in a step (order 3, 1, 2, 0) comes first
+    auto issue_rank = [](int l) { return l == 3 ? 0 : (l == 1 ? 1 : (l == 2 ? 2 : 3)); };
+    if (ntask == 2 && issue_rank(tl[1]) < issue_rank(tl[0])) {
       const int a_ = tl[0], b_ = tpar[0];
       tl[0] = tl[1]; tpar[0] = tpar[1]; tl[1] = a_; tpar[1] = b_;
     }
@@ -428,9 +430,12 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         tc_fence_after();
         if (elect_one_sync()) {
           STREAM_TRACE(1);
+          // issue order inside a step: conv_b layers first (3, 1, 2, 0) -- the layers of a step are independent of each
+          // other, and the conv_b epilogues (residual load, global / head stores) are the long ones
 #pragma unroll
-          for (int l = 0; l < MAX_NL; ++l) {
-            if (l >= nl) break;
+          for (int li = 0; li < MAX_NL; ++li) {
+            const int l = (li == 0) ? 3 : ((li == 1) ? 1 : ((li == 2) ? 2 : 0));
+            if (l >= nl) continue;
             const int g = sr - LAG * l;
             const uint32_t mbar_l = bars + (BAR_MMA + 2u * (uint32_t)l + (S & 1u)) * 8;
             if (g < 0 || g >= Gm) { umma_commit(mbar_l); continue; }
