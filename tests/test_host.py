@@ -123,3 +123,47 @@ def test_pretrained_dirs_hold_the_synthetic_weights():
         v = bf.load_variables(bf.models[name]["directory"])
         ref = synthetic_variables(Arch(no_layers=n), 0)
         assert all(np.array_equal(x, y) for x, y in zip(v, ref))
+
+
+def test_pipelined_denoiser_host_logic():
+    """PipelinedDenoiser.map (no GPU: stand-in instances): results in input order, every instance is driven from ONE
+    thread at a time (a handle is not re-entrant), `outs` are routed to the matching call, look-ahead is bounded."""
+    import threading
+    import time
+    from blind_image_denoising_b200.denoiser import PipelinedDenoiser
+
+    class Fake:
+        made = []
+
+        def __init__(self):
+            self.busy = threading.Lock()
+            self.calls = []
+            self.closed = False
+            Fake.made.append(self)
+
+        def __call__(self, x, out=None, scale=1):
+            assert self.busy.acquire(blocking=False), "two threads inside one instance"
+            try:
+                time.sleep(0.002 * (x % 3))
+                self.calls.append(x)
+                y = x * 10 * scale
+                if out is not None:
+                    out.append(y)
+                return y
+            finally:
+                self.busy.release()
+
+        def close(self):
+            self.closed = True
+
+    pipe = PipelinedDenoiser(Fake, depth=3)
+    outs = [[] for _ in range(20)]
+    got = list(pipe.map(range(20), outs=outs, scale=2))
+    assert got == [20 * i for i in range(20)]
+    assert [o[0] for o in outs] == got
+    assert [m.calls for m in Fake.made] == [list(range(k, 20, 3)) for k in range(3)]
+    assert pipe(7) == 70
+    pipe.close()
+    assert all(m.closed for m in Fake.made)
+    with pytest.raises(ValueError):
+        PipelinedDenoiser(Fake, depth=0)
