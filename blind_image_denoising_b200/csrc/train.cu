@@ -763,8 +763,8 @@ wgrad3x3_kernel(const float* __restrict__ A, const float* __restrict__ G, float*
 }
 
 // base conv wgrad: dWb[tap][c3][co] = sum_p xn[p + tap][c3] * G[p][co], xn = clip(x,0,255)/255 - 0.5 inside the
-// image, 0 outside (zero padding of the NORMALISED tensor).  Thread t owns outputs t, t+256, ...
-constexpr int WB_W = 32, WB_H = 8, WB_MAX_PER_THREAD = 10;  // k0 <= 7: 2352 outputs
+// image, 0 outside (zero padding of the NORMALISED tensor).  Thread = one (tap, c3), all 16 cout, every ngroups-th pixel.
+constexpr int WB_W = 32, WB_H = 8;  // k0 <= 7: 2352 outputs <= the 4096 floats of the gradient tile (group sums reuse it)
 __global__ void __launch_bounds__(256)
 wgrad_base_kernel(const float* __restrict__ img, const float* __restrict__ G, float* __restrict__ partial,
                   int n, int h, int w, int k0, int tiles_x, int tiles_y) {
@@ -775,9 +775,14 @@ wgrad_base_kernel(const float* __restrict__ img, const float* __restrict__ G, fl
   float* s_g = smem + ((ah * aw * 3 + 3) & ~3);  // [WB_H][WB_W][16]
   const int tid = threadIdx.x;
   const int nout = k0 * k0 * 3 * C;
-  float acc[WB_MAX_PER_THREAD];
+  // thread -> ((tap, c3) = u, pixel group): ncombo = k0*k0*3 <= 147, ngroups = 256 / ncombo (k0 = 3: 27 combos x 9 groups)
+  const int ncombo = k0 * k0 * 3, ngroups = 256 / ncombo;
+  const bool active = tid < ngroups * ncombo;
+  const int u = tid % ncombo, grp = tid / ncombo;
+  const int c3 = u % 3, tap = u / 3, dy = tap / k0, dx = tap % k0;
+  float acc[C];
 #pragma unroll
-  for (int k = 0; k < WB_MAX_PER_THREAD; ++k) acc[k] = 0.f;
+  for (int k = 0; k < C; ++k) acc[k] = 0.f;
   const int ntiles = tiles_x * tiles_y * n;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
@@ -803,39 +808,56 @@ wgrad_base_kernel(const float* __restrict__ img, const float* __restrict__ G, fl
       reinterpret_cast<float4*>(s_g)[i] = v;
     }
     __syncthreads();
+    if (active) {
+      // register tiling: one (tap, c3) and all 16 cout per thread, every `ngroups`-th pixel of the tile: 1 scalar + 4
+      // broadcast vector loads per 16 FMAs (one output per thread needed 2 loads per FMA and was LDS-bound)
+      for (int px = grp; px < WB_H * WB_W; px += ngroups) {
+        const int y = px / WB_W, x = px - y * WB_W;
+        const float av = s_a[((y + dy) * aw + x + dx) * 3 + c3];
+        const float4* gp = reinterpret_cast<const float4*>(s_g + px * C);
 #pragma unroll
-    for (int k = 0; k < WB_MAX_PER_THREAD; ++k) {
-      const int o = tid + 256 * k;
-      if (o < nout) {
-        const int co = o % C, c3 = (o / C) % 3, tap = o / (3 * C);
-        const int dy = tap / k0, dx = tap % k0;
-        float a = acc[k];
-        for (int y = 0; y < WB_H; ++y) {
-          const float* ar = s_a + ((y + dy) * aw + dx) * 3 + c3;
-          const float* gr = s_g + (y * WB_W) * C + co;
-#pragma unroll 8
-          for (int x = 0; x < WB_W; ++x) a = fmaf(ar[x * 3], gr[x * C], a);
+        for (int q = 0; q < 4; ++q) {
+          const float4 gv = gp[q];
+          acc[4 * q] = fmaf(av, gv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(av, gv.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(av, gv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(av, gv.w, acc[4 * q + 3]);
         }
-        acc[k] = a;
       }
     }
   }
-  float* dst = partial + (size_t)blockIdx.x * nout;
+  // the pixel groups of the CTA are summed in fixed order (deterministic); s_g (256 x 16 floats) holds [ngroups][nout]
+  __syncthreads();
+  if (active) {
 #pragma unroll
-  for (int k = 0; k < WB_MAX_PER_THREAD; ++k) {
-    const int o = tid + 256 * k;
-    if (o < nout) dst[o] = acc[k];
+    for (int co = 0; co < C; ++co) s_g[grp * nout + u * C + co] = acc[co];
+  }
+  __syncthreads();
+  float* dst = partial + (size_t)blockIdx.x * nout;
+  for (int o = tid; o < nout; o += 256) {
+    float a = 0.f;
+    for (int gq = 0; gq < ngroups; ++gq) a += s_g[gq * nout + o];
+    dst[o] = a;
   }
 }
 
 // out[i] = sum_cta partial[cta][i] (fixed order) + reg1 * sign(w[i])      (L1(0.01)*lambda, loss.py:181-187)
-__global__ void __launch_bounds__(256)
+// 32 outputs x 8 part-lanes per CTA: warp j sums parts j, j+8, ... (coalesced 128-byte rows) in order, the 8 warp sums are
+// combined in fixed order through shared memory, so the result is deterministic (one thread per output over ~300 parts
+// was latency-bound: 25 us per launch, 26 launches per step).
+constexpr int WR_OUT = 32, WR_LANES = 8;
+__global__ void __launch_bounds__(WR_OUT * WR_LANES)
 wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int nout, const float* __restrict__ wts, float reg1,
                     float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nout) return;
+  __shared__ double s_sum[WR_LANES][WR_OUT];
+  const int j = threadIdx.x >> 5, li = threadIdx.x & 31;
+  const int i = blockIdx.x * WR_OUT + li;
   double a = 0;
-  for (int p = 0; p < nparts; ++p) a += (double)partial[(size_t)p * nout + i];
+  if (i < nout)
+    for (int p = j; p < nparts; p += WR_LANES) a += (double)partial[(size_t)p * nout + i];
+  s_sum[j][li] = a;
+  __syncthreads();
+  if (j != 0 || i >= nout) return;
+#pragma unroll
+  for (int k = 1; k < WR_LANES; ++k) a += s_sum[k][li];
   const float wv = wts[i];
   const float sg = (wv > 0.f) ? 1.f : ((wv < 0.f) ? -1.f : 0.f);
   out[i] = (float)(a + (double)reg1 * (double)sg);
@@ -1048,7 +1070,7 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
       wgrad3x3_kernel<<<wg_blocks, 256, WG_SMEM, st>>>(act, grad, partial, n, height, width, tiles_x, tiles_y);
       h->launches++;
     }
-    wgrad_reduce_kernel<<<9, 256, 0, st>>>(partial, parts, 2304, wts, reg1, out);
+    wgrad_reduce_kernel<<<2304 / WR_OUT, WR_OUT * WR_LANES, 0, st>>>(partial, parts, 2304, wts, reg1, out);
     h->launches++;
     return BFCNN_OK;
   };
@@ -1075,7 +1097,7 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
     const int blocks = std::min(wg_grid, btx * bty * n);
     const size_t smem = (size_t)((((WB_H + 2 * r0) * (WB_W + 2 * r0) * 3 + 3) & ~3) + WB_H * WB_W * C) * sizeof(float);
     wgrad_base_kernel<<<blocks, 256, smem, st>>>(noisy, dX, partial, n, height, width, k0, btx, bty);
-    wgrad_reduce_kernel<<<(unsigned)((nbase + 255) / 256), 256, 0, st>>>(partial, blocks, (int)nbase, vars + L.base, reg1,
+    wgrad_reduce_kernel<<<(unsigned)((nbase + WR_OUT - 1) / WR_OUT), WR_OUT * WR_LANES, 0, st>>>(partial, blocks, (int)nbase, vars + L.base, reg1,
                                                                          flat_grads + L.t_base);
     h->launches += 2;
   }
