@@ -1094,7 +1094,8 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   {
     const int r0 = (k0 - 1) / 2;
     const int btx = (width + WB_W - 1) / WB_W, bty = (height + WB_H - 1) / WB_H;
-    const int blocks = std::min(wg_grid, btx * bty * n);
+    // latency-bound tile loads: up to 6 CTAs per SM, as many as the partial-sum buffer holds rows for
+    const int blocks = (int)std::min<size_t>(std::min<size_t>((size_t)btx * bty * n, (size_t)6 * h->sm_count), part_floats / nbase);
     const size_t smem = (size_t)((((WB_H + 2 * r0) * (WB_W + 2 * r0) * 3 + 3) & ~3) + WB_H * WB_W * C) * sizeof(float);
     wgrad_base_kernel<<<blocks, 256, smem, st>>>(noisy, dX, partial, n, height, width, k0, btx, bty);
     wgrad_reduce_kernel<<<(unsigned)((nbase + WR_OUT - 1) / WR_OUT), WR_OUT * WR_LANES, 0, st>>>(partial, blocks, (int)nbase, vars + L.base, reg1,
