@@ -84,7 +84,8 @@ struct Params {
   int blk0, nblk;
   int out_u8;
   int tw, tiles_x, rows_needed;   // output columns per strip, strips per image, output rows per strip
-  long long total_rows, share;    // linearised (image, strip, row) space and the rows of it each CTA owns
+  long long total_rows, share;    // linearised (image, strip, row) space; COST units each CTA owns (see cost_to_row)
+  int seg_overhead;               // cost of starting a segment at a strip start, in rows (halo rows + pipeline fill / drain)
   long long* trace;               // debug timeline (BFCNN_STREAM_TRACE=1) of CTA trace_block, steps [TRACE_S0, TRACE_S0 + 32)
   int trace_block;
 };
@@ -97,6 +98,15 @@ constexpr uint32_t TRACE_S0 = 100;
 #define STREAM_TRACE_PTR(cond) nullptr
 #endif
 
+// Work is split in COST space: every strip costs rows_needed + seg_overhead units, the first seg_overhead of which stand
+// for the halo rows and the pipeline fill / drain a CTA pays when it starts a new segment at a strip boundary.  Equal
+// cost ranges instead of equal row ranges keep CTAs whose range spans two strips from running ~28 rows longer than the
+// others (6 % at one 4K frame per pass).
+__device__ __forceinline__ long long cost_to_row(const Params& p, long long c) {
+  const long long per = (long long)p.rows_needed + p.seg_overhead;
+  const long long s = c / per, off = c - s * per;
+  return s * p.rows_needed + max(0ll, min((long long)p.rows_needed, off - p.seg_overhead));
+}
 struct Seg { int b, j, ya, yb; };
 // the next segment of the linear row range [a, r1): rows [ya, yb) of strip j of image b
 __device__ __forceinline__ Seg seg_at(const Params& p, long long a, long long r1) {
@@ -287,7 +297,8 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     R.x1 = o + SLACK_PX * 16; o += 2 * R.x1_plane;
     R.t1 = o + SLACK_PX * 16;
   }
-  const long long r0 = (long long)blockIdx.x * p.share, r1 = min(p.total_rows, r0 + p.share);
+  const long long r0 = min(p.total_rows, cost_to_row(p, (long long)blockIdx.x * p.share));
+  const long long r1 = min(p.total_rows, cost_to_row(p, ((long long)blockIdx.x + 1) * p.share));
   const bool tr = (p.trace != nullptr) && ((int)blockIdx.x == p.trace_block);
   if (tr && tid == 0) p.trace[256] = clock64();
 
@@ -595,9 +606,11 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
     const int cols_needed = last ? e.w : e.we;
     p.tiles_x = (cols_needed + p.tw - 1) / p.tw;
     p.total_rows = (long long)e.n * p.tiles_x * p.rows_needed;
+    p.seg_overhead = 2 * nl + 2 * (LAG * (nl - 1) + 1);
+    const long long total_cost = (long long)e.n * p.tiles_x * ((long long)p.rows_needed + p.seg_overhead);
     int grid = (int)std::min<long long>(h->sm_count, std::max<long long>(1, p.total_rows / MIN_SHARE));
-    p.share = (p.total_rows + grid - 1) / grid;
-    grid = (int)((p.total_rows + p.share - 1) / p.share);
+    p.share = (total_cost + grid - 1) / grid;
+    grid = (int)((total_cost + p.share - 1) / p.share);
     const size_t smem = smem_bytes(nl);
     BF_REQUIRE(smem <= (size_t)MAX_SMEM, "internal: streaming pass does not fit in shared memory");
     static const int trace_on = getenv("BFCNN_STREAM_TRACE") ? atoi(getenv("BFCNN_STREAM_TRACE")) : 0;
