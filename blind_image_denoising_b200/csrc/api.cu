@@ -328,7 +328,8 @@ int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, in
 
 int bfcnn_set_train_engine(bfcnn_handle* h, int engine) {
   BF_REQUIRE(h != nullptr, "handle is NULL");
-  BF_REQUIRE(engine == 0 || engine == 1, "engine must be 0 (FP32 FFMA) or 1 (tensor cores, fp16 hi/lo split)");
+  BF_REQUIRE(engine == 0 || engine == 1 || engine == 2,
+             "engine must be 0 (FP32 FFMA), 1 (mma.sync, fp16 hi/lo split) or 2 (tcgen05, fp16 hi/lo split)");
   h->train_engine = engine;
   return BFCNN_OK;
 }
@@ -344,7 +345,8 @@ int bfcnn_conv3x3(bfcnn_handle* h, const float* in, const float* weights, float*
   const ConvEpi epi = relu ? CONV_RELU : CONV_PLAIN;
   if (engine == 0) return launch_conv3x3_f32(h, in, out, weights, nullptr, nullptr, nullptr, epi, e, st);
   if (engine == 1) return launch_conv3x3_x3(h, in, out, weights, nullptr, nullptr, epi, e, 64.0f, st);
-  set_error("invalid argument: engine must be 0 (FP32 FFMA) or 1 (tensor cores, fp16 hi/lo split)");
+  if (engine == 2) return launch_conv3x3_t5(h, in, out, weights, nullptr, nullptr, epi, e, 64.0f, st);
+  set_error("invalid argument: engine must be 0 (FP32 FFMA), 1 (mma.sync hi/lo split) or 2 (tcgen05 hi/lo split)");
   return BFCNN_ERR_INVALID_ARGUMENT;
 }
 

@@ -99,7 +99,7 @@ struct bfcnn_handle {
   bfcnn::DevBuf ws_grads;               // scratch gradients
   bfcnn::DevBuf adam_m, adam_v;         // Adam moments over the trainable vector
 
-  int train_engine = 1;   // convs of the training step: 1 = tensor cores, fp16 hi/lo split (conv_x3.cu), 0 = FP32 FFMA
+  int train_engine = 2;   // convs of the training step: 2 = tcgen05, fp16 hi/lo split (conv_t5.cu), 1 = the same on mma.sync (conv_x3.cu), 0 = FP32 FFMA
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the host-buffer pipeline (api.cu)

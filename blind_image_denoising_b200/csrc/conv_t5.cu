@@ -1,0 +1,373 @@
+// conv_t5.cu -- the training-step 3x3 16->16 convolution on tcgen05 at FP32-grade accuracy (F16X3 arithmetic).
+//
+// Same contract as conv3x3_x3_kernel (conv_x3.cu): fp32 NHWC16 in, fp32 NHWC16 out, zero "same" padding, fused epilogue
+// (ReLU / residual add / per-channel batch statistics / ReLU mask for the backward pass), activations and weights split
+// on the fly into fp16 hi + lo parts, every product issued as lo*hi + hi*lo + hi*hi with fp32 accumulation.  The engine
+// is the row-streaming pipeline of fused_stream.cu reduced to ONE layer:
+//
+//   * a CTA owns a 128-lane column strip segment (126 output columns + one halo column per side) and streams down it in
+//     steps of G = 4 rows;
+//   * four converter warps read the fp32 rows (coalesced 64 B per pixel), scale, split into hi / lo and store the four
+//     fp16 channel-half planes (SWIZZLE_NONE K-major UMMA layout, a dx tap is a descriptor shift) into a ring of 4 groups;
+//   * one elected thread issues, per input row, 9 MMAs (3 dx x {lo*hi, hi*lo, hi*hi}, M128 N48 K16): the N = 48 dy-scatter
+//     accumulates the row into the TMEM blocks of output rows q-1, q, q+1 (block = row & 31; MMAs whose blocks straddle
+//     the end of the 32-block ring are split, as in fused_stream.cu); its mbarrier waits are done by a helper warp;
+//   * 16 epilogue warps (one row quarter each per step) drain the finished rows: scale, epilogue op, 64-byte fp32 stores.
+//
+// Per 128-pixel row the shared-memory data pipe moves 9 x 5.5 KB of operands + 8 KB of plane stores (~450 cycles), HBM
+// moves 128 x (64 + 64 [+ 64]) bytes: at 2.1 MP per conv the kernel is HBM-bound (~45-65 us; conv_x3.cu: 117-181 us).
+//
+// Reference: the forward convs of backbone_blocks.py:167-246 in training mode and the dgrad convs of
+// train_loop.py:302-304 (a correlation of dOut with the flipped, transposed kernel, prepared by the caller).
+#include "kernels.cuh"
+#include "umma_ptx.cuh"
+
+namespace bfcnn {
+namespace t5 {
+
+using namespace tc5;
+
+constexpr int RW = 128, SLACK_PX = 8;
+constexpr int G = 4;                    // rows per step
+constexpr int EPI_WARPS = 16;           // G rows x 4 TMEM lane quarters: one task per warp per step
+constexpr int WARP_MMA = 16, WARP_HELP = 17, WARP_CVT = 18, CVT_WARPS = 4;   // converter warps per group
+constexpr int CVT_GROUPS = 3;           // converter groups take alternate steps: two global-load latencies in flight
+constexpr int NTHREADS = 32 * (WARP_CVT + CVT_GROUPS * CVT_WARPS);
+constexpr int KIN = 4;                  // input ring: groups of G rows
+constexpr int ROW_BYTES = RW * 16;
+constexpr int PLANE_BYTES = (KIN * G * RW + 2 * SLACK_PX) * 16;   // one channel-half plane of the hi or lo part
+constexpr int W_PART_BYTES = 3 * 48 * 16 * 2;                     // B operand of one part: [dx 3][N 48][K 16] fp16
+constexpr float W_SCALE = 256.f;        // as conv_x3.cu: keeps the low part of the weights out of the fp16 subnormals
+constexpr uint32_t BAR_MMA = 0, BAR_EPI = 2, BAR_FULL = 4, BAR_FREE = 4 + KIN, NBARS = 4 + 2 * KIN;
+constexpr uint32_t SM_BARS = 0, SM_TMEM = 256, SM_STAT = 384, SM_WTS = 512, SM_PLANES = SM_WTS + 2 * W_PART_BYTES;   // 9728
+constexpr int SMEM_BYTES = SM_PLANES + 4 * PLANE_BYTES;
+constexpr int MIN_SHARE = 16;
+constexpr int SEG_OVERHEAD = 2 + 2 * G;   // halo rows + pipeline fill / drain of a segment, in rows (cost-space split)
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
+
+struct Params {
+  const float* in;
+  float* out;
+  const float* w;       // [9][16 cin][16 cout] fp32
+  const float* res;     // residual / mask source (fp32 NHWC16) or nullptr
+  double* stats;        // [32]: per-channel sum, sum of squares (CONV_STATS)
+  int n, h, wd;
+  int tiles_x;
+  long long total_rows, share;
+  float in_scale, out_scale;
+};
+
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ void mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ long long cost_to_row(const Params& p, long long c) {
+  const long long per = (long long)p.h + SEG_OVERHEAD;
+  const long long s = c / per, off = c - s * per;
+  return s * p.h + max(0ll, min((long long)p.h, off - SEG_OVERHEAD));
+}
+struct Seg { int b, j, ya, yb; };
+__device__ __forceinline__ Seg seg_at(const Params& p, long long a, long long r1) {
+  Seg s;
+  const long long strip = a / p.h;
+  s.ya = (int)(a - strip * p.h);
+  s.yb = (int)min((long long)p.h, (long long)s.ya + (r1 - a));
+  s.b = (int)(strip / p.tiles_x);
+  s.j = (int)(strip - (long long)s.b * p.tiles_x);
+  return s;
+}
+// hi / lo split of 8 consecutive channels (one 16-byte chunk of each part)
+__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  hi.x = pack_h2(a.x, a.y); hi.y = pack_h2(a.z, a.w); hi.z = pack_h2(b.x, b.y); hi.w = pack_h2(b.z, b.w);
+  float2 f;
+  f = unpack_h2(hi.x); lo.x = pack_h2(a.x - f.x, a.y - f.y);
+  f = unpack_h2(hi.y); lo.y = pack_h2(a.z - f.x, a.w - f.y);
+  f = unpack_h2(hi.z); lo.z = pack_h2(b.x - f.x, b.y - f.y);
+  f = unpack_h2(hi.w); lo.w = pack_h2(b.z - f.x, b.w - f.y);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv3x3_t5_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t bars = s0 + SM_BARS;
+  float* s_stat = reinterpret_cast<float*>(smem + SM_STAT);   // [32]
+  // planes: hi half 0, hi half 1, lo half 0, lo half 1; pixel 0 of ring row 0 sits SLACK_PX pixels into each plane
+  const uint32_t pl0 = s0 + SM_PLANES + SLACK_PX * 16;
+  const long long r0 = min(p.total_rows, cost_to_row(p, (long long)blockIdx.x * p.share));
+  const long long r1 = min(p.total_rows, cost_to_row(p, ((long long)blockIdx.x + 1) * p.share));
+
+  // ---------------- setup: barriers, TMEM, weights (fp32 -> scaled hi / lo in the UMMA B layout), zeroed planes
+  if (tid < (int)NBARS) {
+    const uint32_t cnt = tid < (int)BAR_EPI ? 1u : (tid < (int)BAR_FULL ? (uint32_t)EPI_WARPS : (tid < (int)BAR_FREE ? (uint32_t)CVT_WARPS : 1u));
+    mbar_init(bars + tid * 8, cnt);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(s0 + SM_TMEM) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid < 2 * C) s_stat[tid] = 0.f;
+  {
+    __half* wh = reinterpret_cast<__half*>(smem + SM_WTS);
+    __half* wl = wh + W_PART_BYTES / 2;
+    for (int i = tid; i < 3 * 48 * 16; i += NTHREADS) {
+      const int dxi = i / 768, r = i - dxi * 768, nn = r >> 4, k = r & 15;   // (dx, n = j*16 + cout, k = cin)
+      const int j = nn >> 4, co = nn & 15, tap = (2 - j) * 3 + dxi;            // block j <-> dy = 1 - j (host_pack.cu)
+      const float v = p.w[(tap * C + k) * C + co] * W_SCALE;
+      const __half hv = __float2half_rn(v);
+      const int off = dxi * 768 + (k >> 3) * 384 + (nn >> 3) * 64 + (nn & 7) * 8 + (k & 7);
+      wh[off] = hv;
+      wl[off] = __float2half_rn(v - __half2float(hv));
+    }
+    for (uint32_t i = tid; i < (uint32_t)(4 * PLANE_BYTES) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + SM_PLANES)[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+
+  if (warp < EPI_WARPS) {
+    // ================= epilogue warps =================
+    const int quarter = warp & 3, rsel = warp >> 2;   // row of the group
+    const int c = quarter * 32 + lane;
+    const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16);
+    for (int blk = rsel; blk < 32; blk += 4) tmem_zero16(tq + blk * 16);
+    tmem_wait_st();
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;\n" ::"r"(32 * (EPI_WARPS + 1)) : "memory");
+    float ssum[C], ssq[C];
+    if (EPI == CONV_STATS) {
+#pragma unroll
+      for (int i = 0; i < C; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+    }
+    uint32_t S = 0;
+    for (long long a = r0; a < r1;) {
+      const Seg sg = seg_at(p, a, r1);
+      a += sg.yb - sg.ya;
+      const int P = (sg.yb - sg.ya) + 2, Gm = (P + G - 1) / G, nsteps = Gm + 1;
+      const int y00 = sg.ya - 1, gx = sg.j * (RW - 2) - 1 + c;
+      const bool col_out = (c >= 1) && (c < RW - 1) && (gx < p.wd);
+      const long long px0 = ((long long)sg.b * p.h + y00) * p.wd + gx;   // pixel index of (b, y00, gx)
+      for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        mbar_wait_sleep(bars + (BAR_MMA + (S & 1u)) * 8, (S >> 1) & 1u);
+        tc_fence_after();
+        const int w = sr - 1;
+        if (w >= 0) {
+          const int rho = G * w + rsel;
+          const uint32_t taddr = tq + (uint32_t)(rho & 31) * 16u;
+          uint32_t v[16];
+          tmem_ld16_issue(taddr, v);
+          const bool ok = col_out && rho >= 1 && rho < P - 1;
+          const long long o = (px0 + (long long)rho * p.wd) * C;
+          float4 rv[4];
+          if ((EPI == CONV_RESIDUAL || EPI == CONV_MASK) && ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const float4*>(p.res + o + 4 * q);
+          }
+          tmem_ld_wait(v);
+          tmem_zero16(taddr);
+          if (ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 f = make_float4(__uint_as_float(v[4 * q]) * p.out_scale, __uint_as_float(v[4 * q + 1]) * p.out_scale,
+                                     __uint_as_float(v[4 * q + 2]) * p.out_scale, __uint_as_float(v[4 * q + 3]) * p.out_scale);
+              if (EPI == CONV_STATS) {
+                ssum[4 * q] += f.x; ssum[4 * q + 1] += f.y; ssum[4 * q + 2] += f.z; ssum[4 * q + 3] += f.w;
+                ssq[4 * q] += f.x * f.x; ssq[4 * q + 1] += f.y * f.y; ssq[4 * q + 2] += f.z * f.z; ssq[4 * q + 3] += f.w * f.w;
+              }
+              if (EPI == CONV_RELU) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+              if (EPI == CONV_RESIDUAL) { f.x += rv[q].x; f.y += rv[q].y; f.z += rv[q].z; f.w += rv[q].w; }
+              if (EPI == CONV_MASK) {   // ReLU backward: pass the gradient where the saved activation is > 0
+                f.x = rv[q].x > 0.f ? f.x : 0.f; f.y = rv[q].y > 0.f ? f.y : 0.f;
+                f.z = rv[q].z > 0.f ? f.z : 0.f; f.w = rv[q].w > 0.f ? f.w : 0.f;
+              }
+              *reinterpret_cast<float4*>(p.out + o + 4 * q) = f;
+            }
+          }
+          tmem_wait_st();
+          tc_fence_before();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + (BAR_EPI + (S & 1u)) * 8);
+      }
+    }
+    if (EPI == CONV_STATS) {
+      // per-channel sums of this thread's pixels -> warp -> CTA (shared float atomics) -> global (double atomics)
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) {
+        float a = ssum[ch], s2 = ssq[ch];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, m); s2 += __shfl_xor_sync(0xffffffffu, s2, m); }
+        if (lane == 0) { atomicAdd(&s_stat[ch], a); atomicAdd(&s_stat[C + ch], s2); }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ================= MMA issuer =================
+    asm volatile("bar.sync 1, %0;\n" ::"r"(32 * (EPI_WARPS + 1)) : "memory");
+    const uint32_t idesc0 = make_idesc_f16(128, 0);
+    const uint32_t a_hi = desc_lo(pl0, PLANE_BYTES) - 1u;          // row 0, pixel -1 of the hi part; + RW per ring row
+    const uint32_t a_lo = a_hi + (uint32_t)(2 * PLANE_BYTES / 16);
+    const uint32_t b_hi = desc_lo(s0 + SM_WTS, 48 * 16), b_lo = b_hi + (uint32_t)(W_PART_BYTES / 16);
+    constexpr uint32_t BDX = 48 * 16 * 2 / 16;
+    uint32_t S = 0;
+    for (long long a = r0; a < r1;) {
+      const Seg sg = seg_at(p, a, r1);
+      a += sg.yb - sg.ya;
+      const int P = (sg.yb - sg.ya) + 2, Gm = (P + G - 1) / G, nsteps = Gm + 1;
+      for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        asm volatile("bar.sync %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");   // the helper has seen this step's barriers
+        tc_fence_after();
+        if (elect_one_sync()) {
+          if (sr < Gm) {
+            const uint32_t slot_row = (uint32_t)((S % KIN) * G);   // ring rows of this step's group (S counts groups too: see below)
+#pragma unroll 1
+            for (int i = 0; i < G; ++i) {
+              const int rho = G * sr + i;
+              if (rho >= P) break;
+              const uint32_t arow = (slot_row + (uint32_t)i) * RW;
+              const int jlo = (rho == 0) ? 1 : 0, jhi = (rho == P - 1) ? 1 : 2;
+              const int blk_lo = (rho - 1 + jlo) & 31, nb = jhi - jlo + 1;
+              const int n1 = min(nb, 32 - blk_lo);
+#pragma unroll 1
+              for (int part = 0; part < 2; ++part) {   // blocks [blk_lo, blk_lo + n1), then the wrapped rest at column 0
+                const int nblk = part == 0 ? n1 : nb - n1;
+                if (nblk <= 0) break;
+                const uint32_t d = tmem + (part == 0 ? (uint32_t)blk_lo * 16u : 0u);
+                const uint32_t boff = (uint32_t)((jlo + (part == 0 ? 0 : n1)) * 16);
+                const uint32_t id = idesc0 + ((uint32_t)(2 * nblk) << 17);
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  mma_lo(d, a_lo + arow + dx, b_hi + boff + dx * BDX, id);
+                  mma_lo(d, a_hi + arow + dx, b_lo + boff + dx * BDX, id);
+                  mma_lo(d, a_hi + arow + dx, b_hi + boff + dx * BDX, id);
+                }
+              }
+            }
+          }
+          umma_commit(bars + (BAR_MMA + (S & 1u)) * 8);
+          umma_commit(bars + (BAR_FREE + (S % KIN)) * 8);   // the ring rows of this step may be overwritten (every step
+                                                             // uses its slot, the epilogue-only one with nothing in it)
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == WARP_HELP) {
+    // ================= barrier helper of the MMA issuer =================
+    uint32_t S = 0;
+    for (long long a = r0; a < r1;) {
+      const Seg sg = seg_at(p, a, r1);
+      a += sg.yb - sg.ya;
+      const int P = (sg.yb - sg.ya) + 2, Gm = (P + G - 1) / G, nsteps = Gm + 1;
+      for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        if (lane == 0 && S >= 2) mbar_wait_sleep(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
+        if (lane == 1) mbar_wait_sleep(bars + (BAR_FULL + (S % KIN)) * 8, (S / KIN) & 1u);
+        if (lane == 2 && sr == 0 && S >= 1) mbar_wait_sleep(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
+        __syncwarp();
+        tc_fence_before();
+        asm volatile("bar.arrive %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");
+      }
+    }
+  } else {
+    // ================= converter warps: fp32 rows -> scaled hi / lo fp16 planes =================
+    // The ring slot of a step is S % KIN for EVERY step (the epilogue-only step at the end of a segment arrives with an
+    // empty slot), so issuer, helper and converters index barriers and rows by the same global step counter and every
+    // barrier completes exactly one phase per KIN steps.
+    const int cw = warp - WARP_CVT, cgrp = cw / CVT_WARPS;
+    const int c = (cw % CVT_WARPS) * 32 + lane;   // pixel column of the strip
+    uint32_t S = 0;
+    for (long long a = r0; a < r1;) {
+      const Seg sg = seg_at(p, a, r1);
+      a += sg.yb - sg.ya;
+      const int P = (sg.yb - sg.ya) + 2, Gm = (P + G - 1) / G, nsteps = Gm + 1;
+      const int y00 = sg.ya - 1, gx = sg.j * (RW - 2) - 1 + c;
+      const bool col_in = (gx >= 0) && (gx < p.wd);
+      const float* in_b = p.in + (long long)sg.b * p.h * p.wd * C;
+      for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        if ((int)(S % CVT_GROUPS) != cgrp) continue;   // the other converter group's step
+        const uint32_t slot = S % KIN;
+        if (S >= (uint32_t)KIN) mbar_wait_sleep(bars + (BAR_FREE + slot) * 8, ((S / KIN) - 1u) & 1u);
+#pragma unroll
+        for (int i = 0; i < G && sr < Gm; ++i) {
+          const int rho = G * sr + i, gy = y00 + rho;
+          float4 f[4];
+          const bool ok = col_in && rho < P && gy >= 0 && gy < p.h;
+          if (ok) {
+            const float4* src = reinterpret_cast<const float4*>(in_b + ((long long)gy * p.wd + gx) * C);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              f[q] = src[q];
+              f[q].x *= p.in_scale; f[q].y *= p.in_scale; f[q].z *= p.in_scale; f[q].w *= p.in_scale;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) f[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          uint4 h0, l0, h1, l1;
+          split8(f[0], f[1], h0, l0);
+          split8(f[2], f[3], h1, l1);
+          const uint32_t dst = pl0 + ((slot * G + (uint32_t)i) * RW + (uint32_t)c) * 16u;
+          sts128(dst, h0);
+          sts128(dst + PLANE_BYTES, h1);
+          sts128(dst + 2 * PLANE_BYTES, l0);
+          sts128(dst + 3 * PLANE_BYTES, l1);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + (BAR_FULL + slot) * 8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (EPI == CONV_STATS && tid < 2 * C) atomicAdd(&p.stats[tid], (double)s_stat[tid]);
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+}  // namespace t5
+
+int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
+                      ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st) {
+  using namespace t5;
+  BF_REQUIRE(in_scale > 0.f, "in_scale must be a positive power of two");
+  static bool attr_set = false;
+  if (!attr_set) {
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  Params p;
+  p.in = in; p.out = out; p.w = w; p.res = res; p.stats = stats;
+  p.n = e.n; p.h = e.he; p.wd = e.we;
+  p.tiles_x = (e.we + (RW - 2) - 1) / (RW - 2);
+  p.total_rows = (long long)e.n * p.tiles_x * e.he;
+  const long long total_cost = (long long)e.n * p.tiles_x * ((long long)e.he + SEG_OVERHEAD);
+  int grid = (int)std::min<long long>(h->sm_count, std::max<long long>(1, p.total_rows / MIN_SHARE));
+  p.share = (total_cost + grid - 1) / grid;
+  grid = (int)((total_cost + p.share - 1) / p.share);
+  p.in_scale = in_scale;
+  p.out_scale = 1.0f / (in_scale * W_SCALE);
+  switch (epi) {
+    case CONV_PLAIN: conv3x3_t5_kernel<CONV_PLAIN><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
+    case CONV_RELU: conv3x3_t5_kernel<CONV_RELU><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
+    case CONV_RESIDUAL: conv3x3_t5_kernel<CONV_RESIDUAL><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
+    case CONV_STATS: conv3x3_t5_kernel<CONV_STATS><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
+    case CONV_MASK: conv3x3_t5_kernel<CONV_MASK><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
+    default: set_error("unsupported conv epilogue"); return BFCNN_ERR_INTERNAL;
+  }
+  h->launches++;
+  BF_CUDA(cudaGetLastError());
+  return BFCNN_OK;
+}
+
+}  // namespace bfcnn

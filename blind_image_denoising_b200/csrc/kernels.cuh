@@ -27,6 +27,10 @@ int launch_head(bfcnn_handle* h, const float* feat, void* out, bool out_u8, cons
 int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
                       ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st);
 
+// ---- conv_t5.cu: the same layer contract on tcgen05 (row-streaming, F16X3 arithmetic); default training conv engine
+int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
+                      ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st);
+
 int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, float* partial, int max_parts, const Extent& e,
                        float g_scale, int* parts_out, cudaStream_t st);
 

@@ -1010,12 +1010,14 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
 
   // conv engine: tensor cores with the fp16 hi/lo split (FP32-grade, conv_x3.cu) unless BFCNN_TRAIN_CONV=fp32
   // conv engine: tensor cores with the fp16 hi/lo split (conv_x3.cu; default) or FP32 FFMA (bfcnn_set_train_engine)
-  const int x3_mode = h->train_engine == 1 ? 3 : 0;
+  const int x3_mode = h->train_engine >= 1 ? 3 : 0;
+  const bool t5 = h->train_engine == 2;   // the same arithmetic on tcgen05 (conv_t5.cu)
   // back-propagated gradients are ~255/(n*h*w*3) in magnitude: a power-of-two pre-scale brings them to O(1) for the split
   const float gscale = exp2f(floorf(log2f(fmaxf((float)(npx * 3) / 256.f, 1.f))));
   auto conv = [&](const float* in, float* out, const float* wts, const float* res, double* stats, ConvEpi epi) {
     const bool backward = (epi == CONV_MASK || epi == CONV_RESIDUAL);
     const bool use_x3 = (x3_mode & (backward ? 2 : 1)) != 0;
+    if (use_x3 && t5) return launch_conv3x3_t5(h, in, out, wts, res, stats, epi, e, backward ? gscale * 64.0f : 64.0f, st);
     return use_x3 ? launch_conv3x3_x3(h, in, out, wts, res, stats, epi, e, backward ? gscale * 64.0f : 64.0f, st)
                   : launch_conv3x3_f32(h, in, out, wts, nullptr, res, stats, epi, e, st);
   };

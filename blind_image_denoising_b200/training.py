@@ -133,7 +133,7 @@ class Trainer:
 
     def __init__(self, arch: Arch, variables: Sequence[np.ndarray], *, device: int = 0,
                  loss_config: Optional[Dict] = None, optimizer_config: Optional[Dict] = None,
-                 process_group=None, conv_engine: str = "x3"):
+                 process_group=None, conv_engine: str = "t5"):
         torch = _torch()
         self._lib = _native.load_library()
         self.arch = arch
@@ -145,9 +145,10 @@ class Trainer:
         _native.check(self._lib.bfcnn_create(ctypes.byref(carch), flat.ctypes.data, flat.size, self.device,
                                              ctypes.byref(h)))
         self._h = h
-        if conv_engine not in ("x3", "fp32"):
-            raise ValueError("conv_engine must be 'x3' (tensor cores, fp16 hi/lo split) or 'fp32' (FFMA)")
-        _native.check(self._lib.bfcnn_set_train_engine(self._h, 1 if conv_engine == "x3" else 0))
+        engines = {"fp32": 0, "x3": 1, "t5": 2}
+        if conv_engine not in engines:
+            raise ValueError("conv_engine must be 't5' (tcgen05, fp16 hi/lo split), 'x3' (mma.sync, fp16 hi/lo split) or 'fp32' (FFMA)")
+        _native.check(self._lib.bfcnn_set_train_engine(self._h, engines[conv_engine]))
         self.conv_engine = conv_engine
         self.loss_cfg = loss_cfg_from_config(loss_config if loss_config is not None else
                                              {"hinge": 0.5, "cutoff": 255.0, "mae_multiplier": 1.0,

@@ -157,15 +157,16 @@ int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, in
                      int width, const bfcnn_loss_cfg* cfg, float* flat_grads, float* losses5,
                      int update_moving, void* stream);
 
-/* Engine of the 3x3 convs inside bfcnn_train_step: 1 (default) = tensor cores with the fp16 hi/lo split (3 MMAs per
- * product, conv error ~4e-6 on O(1) data, i.e. FP32-grade), 0 = FP32 FFMA (conv error ~1e-6).  The two differ only in
- * rounding; on tiny batches a single ReLU whose pre-activation is ~1e-6 can switch and move one pixel's worth of
- * gradient (tests/test_training_gpu.py states the gates per engine). */
+/* Engine of the 3x3 convs inside bfcnn_train_step: 2 (default) = tcgen05 with the fp16 hi/lo split (3 MMAs per product,
+ * conv error ~4e-6 on O(1) data, i.e. FP32-grade; row-streaming kernel, conv_t5.cu), 1 = the same arithmetic on
+ * mma.sync (conv_x3.cu), 0 = FP32 FFMA (conv error ~1e-6).  They differ only in rounding; on tiny batches a single ReLU
+ * whose pre-activation is ~1e-6 can switch and move one pixel's worth of gradient (tests/test_training_gpu.py states the
+ * gates per engine). */
 int bfcnn_set_train_engine(bfcnn_handle* h, int engine);
 
 /* One 3x3 16->16 "same" convolution layer (keras Conv2D of utilities.py:195-196, no bias), device float32 NHWC16
- * in/out, weights [3,3,16,16] HWIO on the device.  engine 0 = FP32 FFMA, 1 = tensor cores with the fp16 hi/lo split
- * (the engines of the training step); exposed so that the layer kernels can be tested in isolation. */
+ * in/out, weights [3,3,16,16] HWIO on the device.  engine 0 = FP32 FFMA, 1 = mma.sync with the fp16 hi/lo split, 2 = tcgen05
+ * with the fp16 hi/lo split (the engines of the training step); exposed so that the layer kernels can be tested in isolation. */
 int bfcnn_conv3x3(bfcnn_handle* h, const float* in, const float* weights, float* out, int n, int height, int width,
                   int engine, int relu, void* stream);
 
