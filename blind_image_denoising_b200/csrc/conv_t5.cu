@@ -7,15 +7,18 @@
 //
 //   * a CTA owns a 128-lane column strip segment (126 output columns + one halo column per side) and streams down it in
 //     steps of G = 4 rows;
-//   * four converter warps read the fp32 rows (coalesced 64 B per pixel), scale, split into hi / lo and store the four
-//     fp16 channel-half planes (SWIZZLE_NONE K-major UMMA layout, a dx tap is a descriptor shift) into a ring of 4 groups;
+//   * two groups of 8 converter warps take alternate steps: a thread owns one channel half of one pixel, issues the
+//     256-bit loads of its 4 rows BEFORE it waits for the ring slot (two steps of global loads in flight), scales, splits
+//     into hi / lo and stores the fp16 channel-half planes (SWIZZLE_NONE K-major UMMA layout, a dx tap is a descriptor
+//     shift) into a ring of 4 groups;
 //   * one elected thread issues, per input row, 9 MMAs (3 dx x {lo*hi, hi*lo, hi*hi}, M128 N48 K16): the N = 48 dy-scatter
 //     accumulates the row into the TMEM blocks of output rows q-1, q, q+1 (block = row & 31; MMAs whose blocks straddle
 //     the end of the 32-block ring are split, as in fused_stream.cu); its mbarrier waits are done by a helper warp;
-//   * 16 epilogue warps (one row quarter each per step) drain the finished rows: scale, epilogue op, 64-byte fp32 stores.
+//   * 8 epilogue warps (two row quarters each per step) drain the finished rows: scale, epilogue op, two 256-bit stores
+//     per pixel (16-byte stores at a 64-byte stride were the critical path: 115 -> 72 us with full-sector accesses).
 //
 // Per 128-pixel row the shared-memory data pipe moves 9 x 5.5 KB of operands + 8 KB of plane stores (~450 cycles), HBM
-// moves 128 x (64 + 64 [+ 64]) bytes: at 2.1 MP per conv the kernel is HBM-bound (~45-65 us; conv_x3.cu: 117-181 us).
+// moves 128 x (64 + 64 [+ 64]) bytes (HBM floor 41-62 us at 2.1 MP); measured 72 us (conv_x3.cu: 117-181 us).
 //
 // Reference: the forward convs of backbone_blocks.py:167-246 in training mode and the dgrad convs of
 // train_loop.py:302-304 (a correlation of dOut with the flipped, transposed kernel, prepared by the caller).
@@ -29,9 +32,10 @@ using namespace tc5;
 
 constexpr int RW = 128, SLACK_PX = 8;
 constexpr int G = 4;                    // rows per step
-constexpr int EPI_WARPS = 16;           // G rows x 4 TMEM lane quarters: one task per warp per step
-constexpr int WARP_MMA = 16, WARP_HELP = 17, WARP_CVT = 18, CVT_WARPS = 4;   // converter warps per group
-constexpr int CVT_GROUPS = 3;           // converter groups take alternate steps: two global-load latencies in flight
+constexpr int EPI_WARPS = 8;            // G rows x 4 TMEM lane quarters = 16 tasks per step, two per warp
+constexpr int WARP_MMA = 8, WARP_HELP = 9, WARP_CVT = 10, CVT_WARPS = 8;   // converter warps per group: thread = (pixel, half)
+constexpr int CVT_GROUPS = 2;           // converter groups take alternate steps; each issues its loads BEFORE it waits for
+                                        // the ring slot, so two steps of global loads are in flight
 constexpr int NTHREADS = 32 * (WARP_CVT + CVT_GROUPS * CVT_WARPS);
 constexpr int KIN = 4;                  // input ring: groups of G rows
 constexpr int ROW_BYTES = RW * 16;
@@ -78,6 +82,16 @@ __device__ __forceinline__ Seg seg_at(const Params& p, long long a, long long r1
   s.b = (int)(strip / p.tiles_x);
   s.j = (int)(strip - (long long)s.b * p.tiles_x);
   return s;
+}
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread moves a whole 32-byte sector, so an fp32 NHWC16 pixel is
+// two full-sector stores instead of four half-sector ones (the 16-byte stores were the epilogue's critical path)
+__device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float4& a, const float4& b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y),
+               "f"(b.z), "f"(b.w) : "memory");
 }
 // hi / lo split of 8 consecutive channels (one 16-byte chunk of each part)
 __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
@@ -136,10 +150,10 @@ conv3x3_t5_kernel(const Params p) {
 
   if (warp < EPI_WARPS) {
     // ================= epilogue warps =================
-    const int quarter = warp & 3, rsel = warp >> 2;   // row of the group
+    const int quarter = warp & 3, rsel0 = warp >> 2;   // rows rsel0 and rsel0 + 2 of the group
     const int c = quarter * 32 + lane;
     const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16);
-    for (int blk = rsel; blk < 32; blk += 4) tmem_zero16(tq + blk * 16);
+    for (int blk = rsel0; blk < 32; blk += 2) tmem_zero16(tq + blk * 16);
     tmem_wait_st();
     tc_fence_before();
     asm volatile("bar.sync 1, %0;\n" ::"r"(32 * (EPI_WARPS + 1)) : "memory");
@@ -160,7 +174,8 @@ conv3x3_t5_kernel(const Params p) {
         mbar_wait_sleep(bars + (BAR_MMA + (S & 1u)) * 8, (S >> 1) & 1u);
         tc_fence_after();
         const int w = sr - 1;
-        if (w >= 0) {
+#pragma unroll 1
+        for (int rsel = rsel0; rsel < G && w >= 0; rsel += 2) {
           const int rho = G * w + rsel;
           const uint32_t taddr = tq + (uint32_t)(rho & 31) * 16u;
           uint32_t v[16];
@@ -169,12 +184,13 @@ conv3x3_t5_kernel(const Params p) {
           const long long o = (px0 + (long long)rho * p.wd) * C;
           float4 rv[4];
           if ((EPI == CONV_RESIDUAL || EPI == CONV_MASK) && ok) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const float4*>(p.res + o + 4 * q);
+            ldg256(p.res + o, rv[0], rv[1]);
+            ldg256(p.res + o + 8, rv[2], rv[3]);
           }
           tmem_ld_wait(v);
           tmem_zero16(taddr);
           if (ok) {
+            float4 fo[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float4 f = make_float4(__uint_as_float(v[4 * q]) * p.out_scale, __uint_as_float(v[4 * q + 1]) * p.out_scale,
@@ -189,8 +205,10 @@ conv3x3_t5_kernel(const Params p) {
                 f.x = rv[q].x > 0.f ? f.x : 0.f; f.y = rv[q].y > 0.f ? f.y : 0.f;
                 f.z = rv[q].z > 0.f ? f.z : 0.f; f.w = rv[q].w > 0.f ? f.w : 0.f;
               }
-              *reinterpret_cast<float4*>(p.out + o + 4 * q) = f;
+              fo[q] = f;
             }
+            stg256(p.out + o, fo[0], fo[1]);
+            stg256(p.out + o + 8, fo[2], fo[3]);
           }
           tmem_wait_st();
           tc_fence_before();
@@ -253,7 +271,7 @@ conv3x3_t5_kernel(const Params p) {
             }
           }
           umma_commit(bars + (BAR_MMA + (S & 1u)) * 8);
-          umma_commit(bars + (BAR_FREE + (S % KIN)) * 8);   // the ring rows of this step may be overwritten (every step
+          umma_commit(bars + (BAR_FREE + (S % KIN)) * 8);
                                                              // uses its slot, the epilogue-only one with nothing in it)
         }
         __syncwarp();
@@ -281,7 +299,8 @@ conv3x3_t5_kernel(const Params p) {
     // empty slot), so issuer, helper and converters index barriers and rows by the same global step counter and every
     // barrier completes exactly one phase per KIN steps.
     const int cw = warp - WARP_CVT, cgrp = cw / CVT_WARPS;
-    const int c = (cw % CVT_WARPS) * 32 + lane;   // pixel column of the strip
+    const int ct = (cw % CVT_WARPS) * 32 + lane;
+    const int c = ct >> 1, hf = ct & 1;   // pixel column of the strip, channel half
     uint32_t S = 0;
     for (long long a = r0; a < r1;) {
       const Seg sg = seg_at(p, a, r1);
@@ -289,35 +308,33 @@ conv3x3_t5_kernel(const Params p) {
       const int P = (sg.yb - sg.ya) + 2, Gm = (P + G - 1) / G, nsteps = Gm + 1;
       const int y00 = sg.ya - 1, gx = sg.j * (RW - 2) - 1 + c;
       const bool col_in = (gx >= 0) && (gx < p.wd);
-      const float* in_b = p.in + (long long)sg.b * p.h * p.wd * C;
+      const float* in_b = p.in + (long long)sg.b * p.h * p.wd * C + 8 * hf;
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
         if ((int)(S % CVT_GROUPS) != cgrp) continue;   // the other converter group's step
         const uint32_t slot = S % KIN;
+        // all loads of the step first (no shared-memory store in between: they stay in flight together, and while this
+        // group waits for its ring slot)
+        float4 f[G][2];
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          const int rho = G * sr + i, gy = y00 + rho;
+          if (sr < Gm && col_in && rho < P && gy >= 0 && gy < p.h) {
+            ldg256(in_b + ((long long)gy * p.wd + gx) * C, f[i][0], f[i][1]);
+          } else {
+            f[i][0] = make_float4(0.f, 0.f, 0.f, 0.f); f[i][1] = f[i][0];
+          }
+        }
         if (S >= (uint32_t)KIN) mbar_wait_sleep(bars + (BAR_FREE + slot) * 8, ((S / KIN) - 1u) & 1u);
 #pragma unroll
         for (int i = 0; i < G && sr < Gm; ++i) {
-          const int rho = G * sr + i, gy = y00 + rho;
-          float4 f[4];
-          const bool ok = col_in && rho < P && gy >= 0 && gy < p.h;
-          if (ok) {
-            const float4* src = reinterpret_cast<const float4*>(in_b + ((long long)gy * p.wd + gx) * C);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              f[q] = src[q];
-              f[q].x *= p.in_scale; f[q].y *= p.in_scale; f[q].z *= p.in_scale; f[q].w *= p.in_scale;
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) f[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          uint4 h0, l0, h1, l1;
-          split8(f[0], f[1], h0, l0);
-          split8(f[2], f[3], h1, l1);
-          const uint32_t dst = pl0 + ((slot * G + (uint32_t)i) * RW + (uint32_t)c) * 16u;
-          sts128(dst, h0);
-          sts128(dst + PLANE_BYTES, h1);
-          sts128(dst + 2 * PLANE_BYTES, l0);
-          sts128(dst + 3 * PLANE_BYTES, l1);
+          float4 u = f[i][0], v = f[i][1];
+          u.x *= p.in_scale; u.y *= p.in_scale; u.z *= p.in_scale; u.w *= p.in_scale;
+          v.x *= p.in_scale; v.y *= p.in_scale; v.z *= p.in_scale; v.w *= p.in_scale;
+          uint4 hi, lo;
+          split8(u, v, hi, lo);
+          const uint32_t dst = pl0 + (uint32_t)hf * PLANE_BYTES + ((slot * G + (uint32_t)i) * RW + (uint32_t)c) * 16u;
+          sts128(dst, hi);
+          sts128(dst + 2 * PLANE_BYTES, lo);
         }
         fence_async_smem();
         __syncwarp();
