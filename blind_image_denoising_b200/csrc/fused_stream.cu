@@ -263,9 +263,7 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
         sts128(dst, lo);
         sts128(dst + R.x1_plane, hi);
       } else if (E.col_out && inside && rho >= E.nl && rho < E.P - E.nl) {
-        uint4* o = reinterpret_cast<uint4*>(E.fout_col + (long long)rho * E.row_halves);
-        o[0] = lo;
-        o[1] = hi;
+        stg256(E.fout_col + (long long)rho * E.row_halves, lo, hi);   // the pixel's 32 bytes as one full-sector store
       }
     }
     if (l == 1) {
