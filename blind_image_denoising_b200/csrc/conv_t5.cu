@@ -171,22 +171,34 @@ conv3x3_t5_kernel(const Params p) {
       const bool col_out = (c >= 1) && (c < RW - 1) && (gx < p.wd);
       const long long px0 = ((long long)sg.b * p.h + y00) * p.wd + gx;   // pixel index of (b, y00, gx)
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        const int w = sr - 1;
+        // the residual / mask operand of BOTH rows of this step is fetched before the wait for the MMAs (its address does
+        // not depend on them): the global-load latency hides behind the wait instead of sitting on the epilogue's path
+        float4 rva[2][4];
+        if (EPI == CONV_RESIDUAL || EPI == CONV_MASK) {
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+            const int rho = G * w + rsel0 + 2 * k2;
+            if (w >= 0 && col_out && rho >= 1 && rho < P - 1) {
+              const long long o = (px0 + (long long)rho * p.wd) * C;
+              ldg256(p.res + o, rva[k2][0], rva[k2][1]);
+              ldg256(p.res + o + 8, rva[k2][2], rva[k2][3]);
+            }
+          }
+        }
         mbar_wait_sleep(bars + (BAR_MMA + (S & 1u)) * 8, (S >> 1) & 1u);
         tc_fence_after();
-        const int w = sr - 1;
-#pragma unroll 1
-        for (int rsel = rsel0; rsel < G && w >= 0; rsel += 2) {
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          if (w < 0) break;
+          const int rsel = rsel0 + 2 * k2;
           const int rho = G * w + rsel;
           const uint32_t taddr = tq + (uint32_t)(rho & 31) * 16u;
           uint32_t v[16];
           tmem_ld16_issue(taddr, v);
           const bool ok = col_out && rho >= 1 && rho < P - 1;
           const long long o = (px0 + (long long)rho * p.wd) * C;
-          float4 rv[4];
-          if ((EPI == CONV_RESIDUAL || EPI == CONV_MASK) && ok) {
-            ldg256(p.res + o, rv[0], rv[1]);
-            ldg256(p.res + o + 8, rv[2], rv[3]);
-          }
+          const float4 (&rv)[4] = rva[k2];
           tmem_ld_wait(v);
           tmem_zero16(taddr);
           if (ok) {
