@@ -232,29 +232,57 @@ wgrad3x3_x3_kernel(const float* __restrict__ A, const float* __restrict__ G, flo
     const float* a_b = A + (long long)b * h * wd * C;
     const float* g_b = G + (long long)b * h * wd * C;
     __syncthreads();
-    for (int i = tid; i < RH * RW * 2; i += NT) {      // activations with the one-pixel halo
-      const int hf = i & 1, pix = i >> 1;
-      const int r = pix / RW, c = pix % RW;
-      const int gy = oy + r, gx = ox + c;
-      float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
-      if (gy >= 0 && gy < h && gx >= 0 && gx < wd) {
-        const float4* s = reinterpret_cast<const float4*>(a_b + ((long long)gy * wd + gx) * C + 8 * hf);
-        u = s[0]; v = s[1];
-        u.x *= 64.f; u.y *= 64.f; u.z *= 64.f; u.w *= 64.f; v.x *= 64.f; v.y *= 64.f; v.z *= 64.f; v.w *= 64.f;
+    // Staging in batches of 4 iterations: all global loads of a batch first, then the splits and shared-memory stores.
+    // (split_store is inline asm with a memory clobber, so a load placed after it cannot move above it: one load per
+    // iteration meant 13 serial global-load latencies per tile, most of the kernel's time.)
+    constexpr int SB = 4;
+    for (int i0 = tid; i0 < RH * RW * 2; i0 += NT * SB) {      // activations with the one-pixel halo
+      float4 u[SB], v[SB];
+#pragma unroll
+      for (int k = 0; k < SB; ++k) {
+        const int i = i0 + k * NT;
+        const int hf = i & 1, pix = i >> 1;
+        const int r = pix / RW, c = pix % RW;
+        const int gy = oy + r, gx = ox + c;
+        u[k] = make_float4(0.f, 0.f, 0.f, 0.f); v[k] = u[k];
+        if (i < RH * RW * 2 && gy >= 0 && gy < h && gx >= 0 && gx < wd) {
+          const float4* s = reinterpret_cast<const float4*>(a_b + ((long long)gy * wd + gx) * C + 8 * hf);
+          u[k] = s[0]; v[k] = s[1];
+        }
       }
-      split_store(aH + px_off(pix, hf), aL + px_off(pix, hf), u, v);
+#pragma unroll
+      for (int k = 0; k < SB; ++k) {
+        const int i = i0 + k * NT;
+        if (i >= RH * RW * 2) break;
+        const int hf = i & 1, pix = i >> 1;
+        float4 a = u[k], bq = v[k];
+        a.x *= 64.f; a.y *= 64.f; a.z *= 64.f; a.w *= 64.f; bq.x *= 64.f; bq.y *= 64.f; bq.z *= 64.f; bq.w *= 64.f;
+        split_store(aH + px_off(pix, hf), aL + px_off(pix, hf), a, bq);
+      }
     }
-    for (int i = tid; i < WG_TH * RW * 2; i += NT) {   // output gradients: zero on the halo columns and outside the image
-      const int hf = i & 1, pix = i >> 1;
-      const int r = pix / RW, c = pix % RW;
-      const int gy = oy + 1 + r, gx = ox + c;
-      float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
-      if (c >= 1 && c < RW - 1 && gy < h && gx < wd) {
-        const float4* s = reinterpret_cast<const float4*>(g_b + ((long long)gy * wd + gx) * C + 8 * hf);
-        u = s[0]; v = s[1];
-        u.x *= g_scale; u.y *= g_scale; u.z *= g_scale; u.w *= g_scale; v.x *= g_scale; v.y *= g_scale; v.z *= g_scale; v.w *= g_scale;
+    for (int i0 = tid; i0 < WG_TH * RW * 2; i0 += NT * SB) {   // output gradients: zero on the halo columns and outside the image
+      float4 u[SB], v[SB];
+#pragma unroll
+      for (int k = 0; k < SB; ++k) {
+        const int i = i0 + k * NT;
+        const int hf = i & 1, pix = i >> 1;
+        const int r = pix / RW, c = pix % RW;
+        const int gy = oy + 1 + r, gx = ox + c;
+        u[k] = make_float4(0.f, 0.f, 0.f, 0.f); v[k] = u[k];
+        if (i < WG_TH * RW * 2 && c >= 1 && c < RW - 1 && gy < h && gx < wd) {
+          const float4* s = reinterpret_cast<const float4*>(g_b + ((long long)gy * wd + gx) * C + 8 * hf);
+          u[k] = s[0]; v[k] = s[1];
+        }
       }
-      split_store(gH + px_off(pix, hf), gL + px_off(pix, hf), u, v);
+#pragma unroll
+      for (int k = 0; k < SB; ++k) {
+        const int i = i0 + k * NT;
+        if (i >= WG_TH * RW * 2) break;
+        const int hf = i & 1, pix = i >> 1;
+        float4 a = u[k], bq = v[k];
+        a.x *= g_scale; a.y *= g_scale; a.z *= g_scale; a.w *= g_scale; bq.x *= g_scale; bq.y *= g_scale; bq.z *= g_scale; bq.w *= g_scale;
+        split_store(gH + px_off(pix, hf), gL + px_off(pix, hf), a, bq);
+      }
     }
     __syncthreads();
     for (int r = warp; r < WG_TH; r += NT / 32) {
