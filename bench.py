@@ -284,7 +284,7 @@ def main():
         "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
         "kernel": {"f16": "ustream::stream_pass_kernel (tcgen05 row-streaming stack; + one base_conv3_mma_kernel launch inside the timed stack)",
                    "f16_mma_sync": "fused_pass_kernel<1>",
-                   "f16x3": "umma3::umma_pass_kernel<P=2> (tcgen05, fp16 hi/lo operand parts)",
+                   "f16x3": "ustream3::stream_pass_kernel (tcgen05 row-streaming stack, fp16 hi/lo operand parts)",
                    "f16x3_mma_sync": "fused_pass_kernel<2>",
                    "fp32": "conv3x3_c16_kernel"}[args.precision],
         "launches_per_step": passes, "avg_launch_ms": r["stack_ms"] / passes,

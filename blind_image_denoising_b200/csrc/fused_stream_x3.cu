@@ -1,0 +1,602 @@
+// fused_stream_x3.cu -- the row-streaming tcgen05 stack of fused_stream.cu in the F16X3 arithmetic (FP32-grade results).
+//
+// Same pipeline (column strips streamed top to bottom, layer l+1 trailing layer l by LAG = 3 row groups, rings in shared
+// memory, the 32 TMEM blocks as one ring, barrier-helper warp, per-layer mma_done), with activations and weights split into
+// fp16 hi + lo parts: every product is issued as lo*hi + hi*lo + hi*hi (9 MMAs per row and conv), the rings carry both
+// parts (four channel-half planes), the feature map between passes carries both parts (lo images after the hi images).
+// One residual block (two convs) per pass: the rings of two blocks with both parts do not fit in shared memory.
+// It replaces the region kernel of fused_umma_x3.cu as the engine of precision "f16x3" (BFCNN_X3_REGIONS=1 selects the
+// region kernel); kept in its own translation unit so that the F16 kernel's code generation is untouched.
+//
+// Reference arithmetic: module_denoiser.py:53-73, backbone_blocks.py:167-246 (block), model.py:297-342 (head),
+// utilities.py:435-443 (denormalise).
+#include "kernels.cuh"
+#include "umma_ptx.cuh"
+
+namespace bfcnn {
+namespace ustream3 {
+
+using namespace tc5;
+
+constexpr int RW = 128;                 // strip width == UMMA M
+constexpr int SLACK_PX = 8;             // pixels of slack before/after every plane (tap shift -1/+1)
+constexpr int EPI_WARPS = 16;           // 4 sets x 4 TMEM lane quarters
+constexpr int WARP_MMA = 16;            // warp 16 issues the MMAs, warp 17 waits on its barriers, warp 18 is the TMA producer
+constexpr int NTHREADS = 32 * 19;
+constexpr int LAG = 3;                  // steps between consecutive layers
+constexpr int K0 = 9;                   // X0 ring: groups of 2 rows (TMA prefetch depth)
+constexpr int KT = 3;                   // T rings: written by the epilogue of layer l at step w+1 (which has only seen layer l's
+                                        // MMAs of that step), read by the MMAs of layer l+1 at step w+3: three groups
+constexpr int ROW_BYTES = RW * 16;      // one row of one channel-half plane
+constexpr int GROUP_BYTES = 2 * ROW_BYTES;
+constexpr int W_LAYER_BYTES = 3 * 48 * 16 * 2;   // B operand of one conv: [dx 3][N 48][K 16] fp16
+constexpr int MAX_SMEM = 232448;
+constexpr int MAX_NL = 4;
+constexpr int MIN_SHARE = 24;           // rows per CTA below which fewer CTAs are launched
+
+// barriers (8 B each)
+// mma_done[l][s & 1] (per layer: the epilogue of layer l starts while the later layers of the step are still being
+// multiplied), epi_done[s & 1], x_full[k], x_free[k]
+constexpr uint32_t BAR_MMA = 0, BAR_EPI = 2 * 4, BAR_XFULL = BAR_EPI + 2, BAR_XFREE = BAR_XFULL + K0, NBARS = BAR_XFREE + K0;
+constexpr uint32_t SM_BARS = 0, SM_TMEM = 512, SM_HEAD = 528, SM_BIAS = 784, SM_WTS = 1152;
+
+__host__ __device__ inline uint32_t plane_bytes_of(int rows) { return (uint32_t)(rows * RW + 2 * SLACK_PX) * 16u; }
+// weights: [layer][hi / lo part][W_LAYER_BYTES]; rings: X0 and T0, each hi half 0, hi half 1, lo half 0, lo half 1
+__host__ __device__ inline uint32_t rings_offset(int nl) { return (SM_WTS + (uint32_t)nl * 2 * W_LAYER_BYTES + 127u) & ~127u; }
+__host__ __device__ inline uint32_t smem_bytes(int nl) { return rings_offset(nl) + 4 * plane_bytes_of(2 * K0) + 4 * plane_bytes_of(2 * KT); }
+
+struct Params {
+  long long plane_halves;  // halves between the hi and the lo part of a feature map (n * he * we * 16)
+  const __half* fin;       // [2 parts][n][he][we][16]  input feature map of this pass
+  __half* fout;            // [n][he][we][16]
+  void* out;               // [n][h][w][3] uint8 or float
+  const uint8_t* wumma;    // [2N][W_LAYER_BYTES]
+  const float* bias;       // [2N][16]
+  const float* whead;      // [16][4]
+  int n, h, w, he, we;
+  int blk0, nblk;
+  int out_u8;
+  int tw, tiles_x, rows_needed;   // output columns per strip, strips per image, output rows per strip
+  long long total_rows, share;    // linearised (image, strip, row) space; COST units each CTA owns (see cost_to_row)
+  int seg_overhead;               // cost of starting a segment at a strip start, in rows (halo rows + pipeline fill / drain)
+  long long* trace;               // debug timeline (BFCNN_STREAM_TRACE=1) of CTA trace_block, steps [TRACE_S0, TRACE_S0 + 32)
+  int trace_block;
+};
+constexpr uint32_t TRACE_S0 = 100;
+#ifdef BFCNN_STREAM_TRACE_BUILD   // compile-time: the timeline costs the issuer ~5 % even when it is switched off at run time
+#define STREAM_TRACE(slot) do { if (tr && S >= TRACE_S0 && S < TRACE_S0 + 32) p.trace[(S - TRACE_S0) * 8 + (slot)] = clock64(); } while (0)
+#define STREAM_TRACE_PTR(cond) ((tr && (cond) && S >= TRACE_S0 && S < TRACE_S0 + 32) ? p.trace + (S - TRACE_S0) * 8 + 4 : nullptr)
+#else
+#define STREAM_TRACE(slot) do { } while (0)
+#define STREAM_TRACE_PTR(cond) nullptr
+#endif
+
+// Work is split in COST space: every strip costs rows_needed + seg_overhead units, the first seg_overhead of which stand
+// for the halo rows and the pipeline fill / drain a CTA pays when it starts a new segment at a strip boundary.  Equal
+// cost ranges instead of equal row ranges keep CTAs whose range spans two strips from running ~28 rows longer than the
+// others (6 % at one 4K frame per pass).
+__device__ __forceinline__ long long cost_to_row(const Params& p, long long c) {
+  const long long per = (long long)p.rows_needed + p.seg_overhead;
+  const long long s = c / per, off = c - s * per;
+  return s * p.rows_needed + max(0ll, min((long long)p.rows_needed, off - p.seg_overhead));
+}
+struct Seg { int b, j, ya, yb; };
+// the next segment of the linear row range [a, r1): rows [ya, yb) of strip j of image b
+__device__ __forceinline__ Seg seg_at(const Params& p, long long a, long long r1) {
+  Seg s;
+  const long long strip = a / p.rows_needed;
+  s.ya = (int)(a - strip * p.rows_needed);
+  s.yb = (int)min((long long)p.rows_needed, (long long)s.ya + (r1 - a));
+  s.b = (int)(strip / p.tiles_x);
+  s.j = (int)(strip - (long long)s.b * p.tiles_x);
+  return s;
+}
+
+// rings: byte address of pixel 0, row slot 0, channel half 0; the other half is +plane
+struct Rings {
+  uint32_t x0, t0;             // hi part; the lo part is + 2 planes
+  uint32_t x0_plane, t_plane;
+};
+
+enum Kind { KIND_A = 0, KIND_B_TO_X = 1, KIND_B_OUT = 2 };
+
+// Every shared-memory descriptor of this kernel has SBO = 128 B, version 1, SWIZZLE_NONE: the high word is one constant
+// and the issuer's arithmetic (tap shifts, ring rows, weight blocks) touches the 14-bit start-address field of the low
+// word only -- 32-bit adds instead of 64-bit ones on the issuing thread.
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ void mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc)
+      : "memory");
+}
+
+// model.py:342 tanh(2y)*0.51, then utilities.py:435-443 (clip(+-0.5)+0.5)*255, with tanh(z) = 1 - 2/(exp(2z)+1) on the
+// fast exp / divide units (absolute error ~1e-6 of the +-1 range, 1e-4 on the 0-255 scale): the head sits on the
+// epilogue's critical path in the last pass
+__device__ __forceinline__ float head_activation_fast(float y) {
+  const float e = __expf(4.0f * y);
+  float t = (1.0f - __fdividef(2.0f, e + 1.0f)) * 0.51f;
+  t = fminf(fmaxf(t, -0.5f), 0.5f);
+  return (t + 0.5f) * 255.0f;
+}
+
+struct EpiCtx {
+  uint32_t tq;             // TMEM address of this warp's lane quarter, column 0
+  uint32_t pix;            // byte offset of this thread's pixel inside a ring row
+  int y00, he, h_img;      // row rho of the segment is image row y00 + rho
+  int P, nl;
+  bool col_ok, col_out;
+  __half* fout_col;        // feature-map address of (b, y00, gx); row rho adds rho * row_halves
+  uint8_t* out_col;        // output address of (b, y00, gx)
+  long long row_halves, row_out;
+  int gb0;                 // X0 ring group slot of the segment's group 0
+};
+
+// one (layer, row) task of one warp: 32 pixels of output row rho of layer l
+template <int KIND, bool LAST_PASS>
+__device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const EpiCtx& E, uint32_t bars, const float (&bias)[16],
+                                         const float* s_head, const float* s_bias_l, int l, int rho, long long* tp = nullptr) {
+  const uint32_t taddr = E.tq + (uint32_t)((rho + 14 * l) & 31) * 16u;
+  uint32_t v[16];
+  if (tp) tp[0] = clock64();
+  tmem_ld16_issue(taddr, v);
+  const bool inside = E.col_ok && ((unsigned)(E.y00 + rho) < (unsigned)E.he);
+  if (KIND == KIND_A) {
+    tmem_ld_wait(v);
+    if (tp) tp[1] = clock64();
+    tmem_zero16(taddr);
+    if (tp) tp[2] = clock64();
+    const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
+    // T = ReLU(acc), split into the hi part and the lo part (the rounding error of the hi part), per channel half
+    uint32_t hp[8], lp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float r0 = fmaxf(__uint_as_float(v[2 * i]), 0.f), r1 = fmaxf(__uint_as_float(v[2 * i + 1]), 0.f);
+      const uint32_t hh = pack_h2(r0, r1);
+      const float2 hf = unpack_h2(hh);
+      hp[i] = hh & m;
+      lp[i] = pack_h2(r0 - hf.x, r1 - hf.y) & m;
+    }
+    const uint32_t dst = R.t0 + ((uint32_t)rho % (2 * KT)) * ROW_BYTES + E.pix;
+    sts128(dst, make_uint4(hp[0], hp[1], hp[2], hp[3]));
+    sts128(dst + R.t_plane, make_uint4(hp[4], hp[5], hp[6], hp[7]));
+    sts128(dst + 2 * R.t_plane, make_uint4(lp[0], lp[1], lp[2], lp[3]));
+    sts128(dst + 3 * R.t_plane, make_uint4(lp[4], lp[5], lp[6], lp[7]));
+    if (tp) tp[3] = clock64();
+  } else {
+    // residual: X of this block (fp16) + the BN constant b' + the accumulator
+    const uint32_t xsrc = R.x0 + (uint32_t)(((E.gb0 + (rho >> 1)) % K0) * 2 + (rho & 1)) * ROW_BYTES + E.pix;
+    const uint4 xa = lds128(xsrc), xb = lds128(xsrc + R.x0_plane);
+    const uint4 xla = lds128(xsrc + 2 * R.x0_plane), xlb = lds128(xsrc + 3 * R.x0_plane);
+    tmem_ld_wait(v);
+    tmem_zero16(taddr);
+    float xf[16];   // X = hi + lo
+    {
+      const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+      const uint32_t xl[8] = {xla.x, xla.y, xla.z, xla.w, xlb.x, xlb.y, xlb.z, xlb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 a2 = unpack_h2(xs[i]), b2 = unpack_h2(xl[i]);
+        xf[2 * i] = a2.x + b2.x; xf[2 * i + 1] = a2.y + b2.y;
+      }
+    }
+    if (KIND == KIND_B_OUT && LAST_PASS) {
+      // collapsed 1x1 head + tanh(2y)*0.51 + denormalise (+ round + uint8), accumulated channel pair by channel pair
+      // (the 19-warp CTA caps the kernel at 96 registers; bias and head weights stay in shared memory)
+      if (E.col_out && inside && rho >= E.nl && rho < E.P - E.nl && (E.y00 + rho) < E.h_img) {
+        // s_head is packed [16 ch][3] here (12 broadcast LDS.128 per thread) and the BN constant b' of the last conv_b
+        // enters as bias[0..2] = sum_ch b'[ch] w[ch][j], folded once per thread
+        float s0 = bias[0], s1 = bias[1], s2 = bias[2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {   // 4 channels = 12 weights = 3 float4 per iteration
+          const float4 wa = *reinterpret_cast<const float4*>(s_head + 12 * q), wb = *reinterpret_cast<const float4*>(s_head + 12 * q + 4);
+          const float4 wc = *reinterpret_cast<const float4*>(s_head + 12 * q + 8);
+          const float f0 = __uint_as_float(v[4 * q]) + xf[4 * q], f1 = __uint_as_float(v[4 * q + 1]) + xf[4 * q + 1];
+          const float f2 = __uint_as_float(v[4 * q + 2]) + xf[4 * q + 2], f3 = __uint_as_float(v[4 * q + 3]) + xf[4 * q + 3];
+          s0 = fmaf(f0, wa.x, s0); s1 = fmaf(f0, wa.y, s1); s2 = fmaf(f0, wa.z, s2);
+          s0 = fmaf(f1, wa.w, s0); s1 = fmaf(f1, wb.x, s1); s2 = fmaf(f1, wb.y, s2);
+          s0 = fmaf(f2, wb.z, s0); s1 = fmaf(f2, wb.w, s1); s2 = fmaf(f2, wc.x, s2);
+          s0 = fmaf(f3, wc.y, s0); s1 = fmaf(f3, wc.z, s1); s2 = fmaf(f3, wc.w, s2);
+        }
+        const float r0o = head_activation_fast(s0), r1o = head_activation_fast(s1), r2o = head_activation_fast(s2);
+        if (p.out_u8) {
+          uint8_t* d = E.out_col + (long long)rho * E.row_out;
+          d[0] = (uint8_t)__float2int_rn(r0o); d[1] = (uint8_t)__float2int_rn(r1o); d[2] = (uint8_t)__float2int_rn(r2o);
+        } else {
+          float* d = reinterpret_cast<float*>(E.out_col) + (long long)rho * E.row_out;
+          d[0] = r0o; d[1] = r1o; d[2] = r2o;
+        }
+      }
+      if (l == 1) {
+        fence_async_smem();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + (BAR_XFREE + (uint32_t)((E.gb0 + (rho >> 1)) % K0)) * 8);
+      }
+      return;
+    }
+    // X_new = acc + X + b', split into hi + lo and written to the next pass's feature map (lo images follow the hi images)
+    if (E.col_out && inside && rho >= E.nl && rho < E.P - E.nl) {
+      uint32_t hp[8], lp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float b0, b1;
+        if (LAST_PASS) {
+          const float2 bb = *reinterpret_cast<const float2*>(s_bias_l + 2 * i);
+          b0 = bb.x; b1 = bb.y;
+        } else {
+          b0 = bias[2 * i]; b1 = bias[2 * i + 1];
+        }
+        const float f0 = __uint_as_float(v[2 * i]) + (xf[2 * i] + b0), f1 = __uint_as_float(v[2 * i + 1]) + (xf[2 * i + 1] + b1);
+        const uint32_t hh = pack_h2(f0, f1);
+        const float2 hf = unpack_h2(hh);
+        hp[i] = hh;
+        lp[i] = pack_h2(f0 - hf.x, f1 - hf.y);
+      }
+      __half* o = E.fout_col + (long long)rho * E.row_halves;
+      stg256(o, make_uint4(hp[0], hp[1], hp[2], hp[3]), make_uint4(hp[4], hp[5], hp[6], hp[7]));
+      stg256(o + p.plane_halves, make_uint4(lp[0], lp[1], lp[2], lp[3]), make_uint4(lp[4], lp[5], lp[6], lp[7]));
+    }
+    if (l == 1) {
+      // this warp's X0 pixels of the row are consumed: (generic read -> async-proxy TMA overwrite)
+      fence_async_smem();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(bars + (BAR_XFREE + (uint32_t)((E.gb0 + (rho >> 1)) % K0)) * 8);
+    }
+  }
+}
+
+template <bool LAST_PASS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
+  const int nl = 2 * p.nblk, halo = nl;
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t bars = s0 + SM_BARS;
+  float* s_head = reinterpret_cast<float*>(smem + SM_HEAD);
+  float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
+  Rings R;
+  {
+    uint32_t o = s0 + rings_offset(nl);
+    R.x0_plane = plane_bytes_of(2 * K0); R.t_plane = plane_bytes_of(2 * KT);
+    R.x0 = o + SLACK_PX * 16; o += 4 * R.x0_plane;
+    R.t0 = o + SLACK_PX * 16;
+  }
+  const long long r0 = min(p.total_rows, cost_to_row(p, (long long)blockIdx.x * p.share));
+  const long long r1 = min(p.total_rows, cost_to_row(p, ((long long)blockIdx.x + 1) * p.share));
+  const bool tr = (p.trace != nullptr) && ((int)blockIdx.x == p.trace_block);
+  if (tr && tid == 0) p.trace[256] = clock64();
+
+  // ---------------- one-time setup: barriers, TMEM, weights, zeroed rings
+  if (tid < (int)NBARS) {
+    // epi_done: one arrival per epilogue warp; x_free: one per warp of the 2 rows x 4 quarters that read the group
+    // (32 same-address arrivals per warp showed up as ~200 extra shared-memory wavefronts per step)
+    const uint32_t cnt = tid < (int)BAR_EPI ? 1u : (tid < (int)BAR_XFULL ? (uint32_t)EPI_WARPS : (tid < (int)BAR_XFREE ? 1u : 8u));
+    mbar_init(bars + tid * 8, cnt);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(s0 + SM_TMEM) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  for (int i = tid; i < nl * 2 * (W_LAYER_BYTES / 16); i += NTHREADS)   // [layer][hi / lo][W_LAYER_BYTES], as host_pack.cu lays them out
+    reinterpret_cast<uint4*>(smem + SM_WTS)[i] = reinterpret_cast<const uint4*>(p.wumma + (size_t)(2 * p.blk0) * 2 * W_LAYER_BYTES)[i];
+  for (int i = tid; i < nl * C; i += NTHREADS) s_bias[i] = p.bias[(size_t)(2 * p.blk0) * C + i];
+  if (LAST_PASS) {
+    if (tid < C * 3) s_head[tid] = p.whead[(tid / 3) * 4 + (tid % 3)];   // packed [16][3]
+  } else if (tid < C * 4) {
+    s_head[tid] = p.whead[tid];
+  }
+  {
+    // stale shared memory may hold NaN patterns; rows outside the valid cone are multiplied (and ignored), so start clean
+    const uint32_t ro = rings_offset(nl), n16 = (smem_bytes(nl) - ro) / 16;
+    for (uint32_t i = tid; i < n16; i += NTHREADS) reinterpret_cast<uint4*>(smem + ro)[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_async_smem();   // barrier inits + zeros -> async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+  if (tr && tid == 0) p.trace[257] = clock64();
+
+  if (warp < EPI_WARPS) {
+    // ================= epilogue warps =================
+    const int quarter = warp & 3, set = warp >> 2;
+    const int c = quarter * 32 + lane;
+    EpiCtx E;
+    E.tq = tmem + ((uint32_t)(quarter * 32) << 16);
+    E.pix = (uint32_t)c * 16u;
+    E.he = p.he; E.h_img = p.h; E.nl = nl;
+    E.row_halves = (long long)p.we * 16; E.row_out = (long long)p.w * 3;
+    // this warp's tasks of a step: t = set, set + 4 (< 2 nl): row parity t / nl of layer (t + parity) % nl
+    int tl[2], tpar[2], ntask = 0;
+    for (int t = set; t < 2 * nl && ntask < 2; t += 4) { tpar[ntask] = t / nl; tl[ntask] = (t + tpar[ntask]) % nl; ++ntask; }
+    // the layer whose MMAs are issued first in a step (order 3, 1, 2, 0) comes first
+    auto issue_rank = [](int l) { return l == 3 ? 0 : (l == 1 ? 1 : (l == 2 ? 2 : 3)); };
+    if (ntask == 2 && issue_rank(tl[1]) < issue_rank(tl[0])) {
+      const int a_ = tl[0], b_ = tpar[0];
+      tl[0] = tl[1]; tpar[0] = tpar[1]; tl[1] = a_; tpar[1] = b_;
+    }
+    float bias[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bias[i] = 0.f;
+    for (int k = 0; k < ntask && !LAST_PASS; ++k)
+      if (tl[k] & 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bias[i] = s_bias[tl[k] * C + i];   // at most one conv_b layer per warp (nl = 2, 4)
+      }
+    if (LAST_PASS) {   // the head's share of the last conv_b's BN constant (the other conv_b layers read s_bias per task)
+      for (int ch = 0; ch < C; ++ch) {
+        const float bv = p.bias[(size_t)(2 * p.blk0 + nl - 1) * C + ch];
+        bias[0] = fmaf(bv, p.whead[ch * 4 + 0], bias[0]);
+        bias[1] = fmaf(bv, p.whead[ch * 4 + 1], bias[1]);
+        bias[2] = fmaf(bv, p.whead[ch * 4 + 2], bias[2]);
+      }
+    }
+    for (int blk = set; blk < 32; blk += 4) tmem_zero16(E.tq + blk * 16);
+    tmem_wait_st();
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;\n" ::"r"(32 * (EPI_WARPS + 1)) : "memory");   // accumulators are zero -> MMA issuer
+    uint32_t S = 0;
+    long long gg = 0;
+    for (long long a = r0; a < r1;) {
+      const Seg sg = seg_at(p, a, r1);
+      a += sg.yb - sg.ya;
+      const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
+      {
+        const int gx = sg.j * p.tw - halo + c;
+        E.y00 = sg.ya - nl; E.P = P;
+        E.col_ok = (gx >= 0) && (gx < p.we);
+        E.col_out = E.col_ok && (c >= halo) && (c < RW - halo) && (!LAST_PASS || gx < p.w);
+        E.fout_col = p.fout + ((((long long)sg.b * p.he + E.y00) * p.we + gx) << 4);
+        E.out_col = reinterpret_cast<uint8_t*>(p.out) + ((((long long)sg.b * p.h + E.y00) * p.w + gx) * 3) * (p.out_u8 ? 1 : 4);
+        E.gb0 = (int)(gg % K0);
+      }
+      for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        for (int k = 0; k < ntask; ++k) {
+          const int l = tl[k], w = sr - LAG * l - 1;
+          mbar_wait_sleep(bars + (BAR_MMA + 2u * (uint32_t)l + (S & 1u)) * 8, (S >> 1) & 1u);
+          tc_fence_after();
+          if (w < 0 || w >= Gm) continue;
+          const int rho = 2 * w + tpar[k];
+          if ((l & 1) == 0) epi_task<KIND_A, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho,
+                                                        STREAM_TRACE_PTR(warp == 0 && lane == 0));
+          else if (l + 1 < nl) epi_task<KIND_B_TO_X, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
+          else epi_task<KIND_B_OUT, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
+        }
+        fence_async_smem();   // T / X stores of this step -> async proxy (tensor core reads)
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + (BAR_EPI + (S & 1u)) * 8);
+      }
+      gg += Gm;
+    }
+  } else if (warp == WARP_MMA) {
+    // ================= MMA issuer =================
+    // The issuing thread never touches shared memory: a completed mbarrier.try_wait on it costs ~360 cycles of tensor-pipe
+    // bubble (tools/umma_probe3.cu: the load queues behind the operand fetches, and the MMA queue is shallow).  The waits
+    // of step S are done by the helper warp, which then releases the issuer through a named barrier (bar.arrive /
+    // bar.sync 2 + (S & 1): hardware barrier, no shared-memory traffic).
+    asm volatile("bar.sync 1, %0;\n" ::"r"(32 * (EPI_WARPS + 1)) : "memory");   // accumulators are zero
+    const uint32_t idesc0 = make_idesc_f16(128, 0);   // + (blocks * 2) << 17: N = 16 per accumulator block
+    const uint32_t adesc_x0 = desc_lo(R.x0, R.x0_plane), adesc_t0 = desc_lo(R.t0, R.t_plane);
+    const uint32_t alo_x0 = (2 * R.x0_plane) >> 4, alo_t0 = (2 * R.t_plane) >> 4;   // hi -> lo part of a ring, 16-byte units
+    constexpr uint32_t BDX = 48 * 16 * 2 / 16, BLO = W_LAYER_BYTES / 16;                // next dx block / the lo weights
+    const uint32_t bdesc0 = desc_lo(s0 + SM_WTS, 48 * 16);
+    uint32_t S = 0;
+    long long gg = 0;
+    for (long long a = r0; a < r1;) {
+      const Seg sg = seg_at(p, a, r1);
+      a += sg.yb - sg.ya;
+      const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
+      const int gb0 = (int)(gg % K0);
+      // per-layer issue state at the layer's group 0: A descriptor of input row 0 (pixel -1), its ring row, TMEM block of row -1
+      uint32_t st_ad[MAX_NL];
+      int st_slot[MAX_NL], st_blk[MAX_NL];
+#pragma unroll
+      for (int l = 0; l < MAX_NL; ++l) {
+        const uint32_t adl = (l == 0) ? adesc_x0 : adesc_t0;
+        st_slot[l] = (l == 0) ? 2 * gb0 : 0;
+        st_ad[l] = adl + (uint32_t)(st_slot[l] * RW - 1);
+        st_blk[l] = (14 * l - 1) & 31;
+      }
+      for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        if (lane == 0) STREAM_TRACE(0);
+        asm volatile("bar.sync %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");   // the helper has seen this step's barriers
+        tc_fence_after();
+        if (elect_one_sync()) {
+          STREAM_TRACE(1);
+          // issue order inside a step: conv_b layers first (3, 1, 2, 0) -- the layers of a step are independent of each
+          // other, and the conv_b epilogues (residual load, global / head stores) are the long ones
+#pragma unroll
+          for (int li = 0; li < MAX_NL; ++li) {
+            const int l = (li == 0) ? 3 : ((li == 1) ? 1 : ((li == 2) ? 2 : 0));
+            if (l >= nl) continue;
+            const int g = sr - LAG * l;
+            const uint32_t mbar_l = bars + (BAR_MMA + 2u * (uint32_t)l + (S & 1u)) * 8;
+            if (g < 0 || g >= Gm) { umma_commit(mbar_l); continue; }
+            const uint32_t bd = bdesc0 + (uint32_t)(l * 2 * (W_LAYER_BYTES / 16));
+            const uint32_t alo = (l == 0) ? alo_x0 : alo_t0;
+            // one input row: lo*hi + hi*lo + hi*hi for each dx (the F16X3 arithmetic, FP32-grade products)
+            auto row9 = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t id) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                mma_lo(d, a + alo + dx, b + dx * BDX, id);
+                mma_lo(d, a + dx, b + BLO + dx * BDX, id);
+                mma_lo(d, a + dx, b + dx * BDX, id);
+              }
+            };
+            // incremental state of the layer (the issuing thread must not fall behind the shallow MMA queue: descriptor
+            // arithmetic from scratch cost ~200 cycles per group of six MMAs, 40 % of the issue time)
+            const uint32_t ad = st_ad[l];
+            const int blk0 = st_blk[l];   // accumulator block of output row 2g - 1
+            const int rho0 = 2 * g;
+            // advance the state AFTER the MMAs are queued (the thread would otherwise block on the full queue anyway)
+            auto advance = [&]() {
+              st_blk[l] = (blk0 + 2) & 31;
+              const int rows = (l == 0) ? 2 * K0 : 2 * KT;
+              st_slot[l] += 2;
+              st_ad[l] = ad + 2 * RW;
+              if (st_slot[l] >= rows) { st_slot[l] -= rows; st_ad[l] -= (uint32_t)(rows * RW); }
+            };
+            if (rho0 >= 1 && rho0 + 2 < P && blk0 <= 28) {
+              // fast path (7 groups in 8): both rows are interior rows of the segment and their four accumulator blocks
+              // do not wrap around the TMEM ring -> six N = 48 MMAs, straight-line
+              const uint32_t d = tmem + (uint32_t)blk0 * 16u;
+              const uint32_t id = idesc0 + (6u << 17);
+              row9(d, ad, bd, id);
+              row9(d + 16, ad + RW, bd, id);
+              umma_commit(mbar_l);
+              advance();
+              continue;
+            }
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+              const int rho = rho0 + par;
+              if (rho >= P) break;
+              const uint32_t adr = ad + (uint32_t)(par * RW);
+              // accumulator blocks of output rows rho-1, rho, rho+1 (B blocks 0, 1, 2); the segment's first / last input
+              // row has no row above / below
+              const int jlo = (rho == 0) ? 1 : 0, jhi = (rho == P - 1) ? 1 : 2;
+              const int blk_lo = (blk0 + par + jlo) & 31, nb = jhi - jlo + 1;
+              const int n1 = min(nb, 32 - blk_lo);
+              {
+                const uint32_t d = tmem + (uint32_t)blk_lo * 16u;
+                const uint32_t b = bd + (uint32_t)(jlo * 16);
+                const uint32_t id = idesc0 + ((uint32_t)(2 * n1) << 17);
+                row9(d, adr, b, id);
+              }
+              if (n1 < nb) {   // the blocks wrap around the TMEM ring: second part at column 0
+                const uint32_t b = bd + (uint32_t)((jlo + n1) * 16);
+                const uint32_t id = idesc0 + ((uint32_t)(2 * (nb - n1)) << 17);
+                row9(tmem, adr, b, id);
+              }
+            }
+            umma_commit(mbar_l);
+            advance();
+          }
+          STREAM_TRACE(2);
+          STREAM_TRACE(3);
+        }
+        __syncwarp();
+      }
+      gg += Gm;
+    }
+    if (tr && lane == 0) { p.trace[258] = clock64(); p.trace[259] = S; }
+  } else if (warp == WARP_MMA + 1) {
+    // ================= barrier helper of the MMA issuer =================
+    // step S needs: epi_done(S-2) (lane 0: input rows written, accumulator blocks drained), x_full of layer 0's group
+    // (lane 1), and at a segment start epi_done(S-1) too (lane 2: every accumulator block drained before the ring
+    // restarts at row 0).  One barrier per lane, in parallel.
+    uint32_t S = 0;
+    long long gg = 0;
+    for (long long a = r0; a < r1;) {
+      const Seg sg = seg_at(p, a, r1);
+      a += sg.yb - sg.ya;
+      const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
+      for (int sr = 0; sr < nsteps; ++sr, ++S) {
+        if (lane == 0 && S >= 2) mbar_wait_sleep(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
+        if (lane == 1 && sr < Gm) {
+          const long long k = gg + sr;
+          mbar_wait_sleep(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (uint32_t)(k / K0) & 1u);
+        }
+        if (lane == 2 && sr == 0 && S >= 1) mbar_wait_sleep(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
+        __syncwarp();
+        tc_fence_before();
+        asm volatile("bar.arrive %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");
+      }
+      gg += Gm;
+    }
+  } else {
+    // ================= TMA producer =================
+    if (elect_one_sync()) {
+      long long gg = 0;
+      for (long long a = r0; a < r1;) {
+        const Seg sg = seg_at(p, a, r1);
+        a += sg.yb - sg.ya;
+        const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1;
+        const int gx0 = sg.j * p.tw - halo, y00 = sg.ya - nl;
+        for (int g = 0; g < Gm; ++g, ++gg) {
+          const uint32_t k = (uint32_t)(gg % K0), n = (uint32_t)(gg / K0);
+          if (n >= 1) mbar_wait_sleep(bars + (BAR_XFREE + k) * 8, (n - 1) & 1u);
+          const uint32_t bar = bars + (BAR_XFULL + k) * 8;
+          mbar_arrive_expect_tx(bar, 4 * GROUP_BYTES);
+          const uint32_t dst = R.x0 + k * GROUP_BYTES;
+          tma_load_q(dst, &tmap, 0, gx0, y00 + 2 * g, sg.b, bar);
+          tma_load_q(dst + R.x0_plane, &tmap, 1, gx0, y00 + 2 * g, sg.b, bar);
+          tma_load_q(dst + 2 * R.x0_plane, &tmap, 0, gx0, y00 + 2 * g, sg.b + p.n, bar);   // lo part: images n .. 2n-1
+          tma_load_q(dst + 3 * R.x0_plane, &tmap, 1, gx0, y00 + 2 * g, sg.b + p.n, bar);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tr && tid == 0) p.trace[260] = clock64();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+}  // namespace ustream3
+
+int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e, cudaStream_t st) {
+  using namespace ustream3;
+  const int N = h->arch.no_layers;
+  BF_REQUIRE(N >= 1, "the fused tensor-core stack needs no_layers >= 1 (use BFCNN_PREC_FP32)");
+  static bool attr_set = false;
+  if (!attr_set) {
+    BF_CUDA(cudaFuncSetAttribute((const void*)stream_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    BF_CUDA(cudaFuncSetAttribute((const void*)stream_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    attr_set = true;
+  }
+  const int passes = N;   // one residual block per pass
+  const size_t feat_halves = (size_t)e.n * e.he * e.we * C;
+  BF_CHECK(h->ws_feat[1].reserve(feat_halves * 2 * sizeof(__half)));   // hi part, then lo part
+  if (passes > 1) BF_CHECK(h->ws_feat[0].reserve(feat_halves * 2 * sizeof(__half)));
+  // pass "-1": base conv (hi + lo) into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
+  BF_CHECK(launch_base_conv_f16_x3(h, d_in, h->ws_feat[1].as<__half>(), h->ws_feat[1].as<__half>() + feat_halves, e, st));
+  Extent e2 = e;
+  e2.n = 2 * e.n;   // the tensor map sees the lo images behind the hi images
+  for (int ps = 0; ps < passes; ++ps) {
+    Params p;
+    const bool last = (ps + 1 == passes);
+    p.out = d_out;
+    p.fin = h->ws_feat[(ps + 1) & 1].as<__half>();
+    p.fout = last ? nullptr : h->ws_feat[ps & 1].as<__half>();
+    p.plane_halves = (long long)feat_halves;
+    p.wumma = h->d_conv_umma_x3.as<uint8_t>();
+    p.bias = h->d_bias_f32.as<float>();
+    p.whead = h->d_head_f32.as<float>();
+    p.n = e.n; p.h = e.h; p.w = e.w; p.he = e.he; p.we = e.we;
+    p.blk0 = ps;
+    p.nblk = 1;
+    p.out_u8 = out_u8 ? 1 : 0;
+    const int nl = 2;
+    p.tw = RW - 2 * nl;
+    p.rows_needed = last ? e.h : e.he;
+    const int cols_needed = last ? e.w : e.we;
+    p.tiles_x = (cols_needed + p.tw - 1) / p.tw;
+    p.total_rows = (long long)e.n * p.tiles_x * p.rows_needed;
+    p.seg_overhead = 2 * nl + 2 * (LAG * (nl - 1) + 1);
+    const long long total_cost = (long long)e.n * p.tiles_x * ((long long)p.rows_needed + p.seg_overhead);
+    int grid = (int)std::min<long long>(h->sm_count, std::max<long long>(1, p.total_rows / MIN_SHARE));
+    p.share = (total_cost + grid - 1) / grid;
+    grid = (int)((total_cost + p.share - 1) / p.share);
+    const size_t smem = smem_bytes(nl);
+    BF_REQUIRE(smem <= (size_t)MAX_SMEM, "internal: streaming pass does not fit in shared memory");
+    p.trace = nullptr; p.trace_block = 0;
+    CUtensorMap tmap;
+    BF_CHECK(make_feature_tmap(&tmap, p.fin, e2, RW, 2));
+    if (last) stream_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
+    else stream_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
+    h->launches++;
+    BF_CUDA(cudaGetLastError());
+  }
+  return BFCNN_OK;
+}
+
+}  // namespace bfcnn

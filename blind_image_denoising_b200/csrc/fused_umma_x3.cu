@@ -743,8 +743,22 @@ static int env_int_u3(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
+int launch_base_conv_f16_x3(bfcnn_handle* h, const uint8_t* d_in, __half* hi, __half* lo, const Extent& e, cudaStream_t st) {
+  using namespace umma3;
+  const int k0 = h->arch.base_kernel, r0 = (k0 - 1) / 2;
+  const size_t bsm = (size_t)(k0 * k0 * 3 * C + (BC_H + 2 * r0) * (BC_W + 2 * r0) * 3) * sizeof(float);
+  dim3 grid((e.we + BC_W - 1) / BC_W, (e.he + BC_H - 1) / BC_H, e.n);
+  BF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "image too large for the base conv grid");
+  base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, hi, lo, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, k0);
+  h->launches++;
+  BF_CUDA(cudaGetLastError());
+  return BFCNN_OK;
+}
+
 int run_fused_stack_umma_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e, cudaStream_t st) {
   using namespace umma3;
+  if (!env_int_u3("BFCNN_X3_REGIONS", 0) && h->arch.no_layers >= 1)   // default engine: the row-streaming kernel
+    return run_fused_stack_stream_x3(h, d_in, d_out, out_u8, e, st);
   constexpr int P = 2;   // 1: fp16 operands (F16); 2: fp16 hi + lo operands, 3 MMAs per product (F16X3, FP32-grade)
   const int N = h->arch.no_layers, k0 = h->arch.base_kernel;
   if (N < 1) {

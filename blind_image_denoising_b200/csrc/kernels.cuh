@@ -51,6 +51,11 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
 int run_fused_stack_umma_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                             cudaStream_t st);
 
+// ---- fused_stream_x3.cu: the row-streaming pipeline in the F16X3 arithmetic (default engine of precision f16x3)
+int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
+                              cudaStream_t st);
+int launch_base_conv_f16_x3(bfcnn_handle* h, const uint8_t* d_in, __half* hi, __half* lo, const Extent& e, cudaStream_t st);
+
 // ---- train.cu
 int run_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, float* noisy_f32, int n,
                 int height, int width, uint64_t seed, uint64_t sample_offset,

@@ -262,3 +262,23 @@ def test_random_shapes_streaming_vs_mma_sync(native_lib):
         assert np.array_equal(ya, a(x, pad_pow2=pad))
     for a, b in models.values():
         a.close(); b.close()
+
+
+def test_f16x3_streaming_matches_region_engine_and_fp32(native_lib, monkeypatch):
+    """Precision f16x3 runs on the row-streaming kernel (fused_stream_x3.cu); BFCNN_X3_REGIONS=1 selects the region kernel.
+    Both are FP32-grade: uint8 equal to the FP32 FFMA path up to 1 LSB on < 1 % of the values, also across segment
+    hand-overs (many small images) and odd shapes."""
+    rng = np.random.default_rng(31)
+    for n_layers, shape in [(6, (40, 24, 40, 3)), (3, (2, 333, 217, 3)), (18, (1, 150, 300, 3))]:
+        x = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        m = _model(n_layers, precision="f16x3")
+        a = m(x)
+        monkeypatch.setenv("BFCNN_X3_REGIONS", "1")
+        b = m(x)
+        monkeypatch.delenv("BFCNN_X3_REGIONS")
+        f = m(x, precision="fp32")
+        for y in (a, b):
+            d = np.abs(y.astype(np.int32) - f.astype(np.int32))
+            assert d.max() <= 1 and (d > 0).mean() < 0.01, (n_layers, shape, int(d.max()), float((d > 0).mean()))
+        assert np.array_equal(a, m(x))
+        m.close()
