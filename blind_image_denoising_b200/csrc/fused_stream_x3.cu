@@ -558,7 +558,10 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
   BF_CHECK(h->ws_feat[1].reserve(feat_halves * 2 * sizeof(__half)));   // hi part, then lo part
   if (passes > 1) BF_CHECK(h->ws_feat[0].reserve(feat_halves * 2 * sizeof(__half)));
   // pass "-1": base conv (hi + lo) into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
-  BF_CHECK(launch_base_conv_f16_x3(h, d_in, h->ws_feat[1].as<__half>(), h->ws_feat[1].as<__half>() + feat_halves, e, st));
+  if (h->arch.base_kernel == 3 && !getenv("BFCNN_BASE_FFMA"))   // tensor-core base conv (fused_umma.cu), hi + lo outputs
+    BF_CHECK(launch_base_conv_f16(h, d_in, h->ws_feat[1].as<__half>(), e, st, h->ws_feat[1].as<__half>() + feat_halves));
+  else
+    BF_CHECK(launch_base_conv_f16_x3(h, d_in, h->ws_feat[1].as<__half>(), h->ws_feat[1].as<__half>() + feat_halves, e, st));
   Extent e2 = e;
   e2.n = 2 * e.n;   // the tensor map sees the lo images behind the hi images
   for (int ps = 0; ps < passes; ++ps) {

@@ -489,8 +489,8 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __global__ void __launch_bounds__(256, 4)
-base_conv3_mma_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, const float* __restrict__ w,
-                      int h, int wd, int he, int we, int tiles_x, int tiles_y, int tiles) {
+base_conv3_mma_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, __half* __restrict__ out_lo /* or nullptr */,
+                      const float* __restrict__ w, int h, int wd, int he, int we, int tiles_x, int tiles_y, int tiles) {
   __shared__ __align__(16) __half s_in[BM_TH * BM_TW * 4];
   __shared__ __align__(16) __half s_out[8][16 * 16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -578,18 +578,29 @@ base_conv3_mma_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out,
         mma16816(acc[nt], a, bh[ks][nt][0], bh[ks][nt][1]);
       }
     }
-    // stage [16 px][16 ch] fp16, then 32 lanes x 16 B = the 512 contiguous bytes of the 16 pixels
-    __syncwarp();
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      *reinterpret_cast<uint32_t*>(so + g * 16 + nt * 8 + 2 * t) = pack_h2(acc[nt][0], acc[nt][1]);
-      *reinterpret_cast<uint32_t*>(so + (g + 8) * 16 + nt * 8 + 2 * t) = pack_h2(acc[nt][2], acc[nt][3]);
-    }
-    __syncwarp();
+    // stage [16 px][16 ch] fp16, then 32 lanes x 16 B = the 512 contiguous bytes of the 16 pixels; for the F16X3 stacks
+    // a second round stores the lo part (the rounding error of the fp16 value) into the lo feature map
     const int gy = y0 + ry, gx = x0 + px0 + (lane >> 1);
-    if (gy < he && gx < we) {
-      const uint4 v = *reinterpret_cast<const uint4*>(so + lane * 8);
-      *reinterpret_cast<uint4*>(out + ((((long long)b * he + gy) * we + gx) << 4) + (lane & 1) * 8) = v;
+    const long long o = ((((long long)b * he + gy) * we + gx) << 4) + (lane & 1) * 8;
+    for (int part = 0; part < (out_lo ? 2 : 1); ++part) {
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const uint32_t h01 = pack_h2(acc[nt][0], acc[nt][1]), h23 = pack_h2(acc[nt][2], acc[nt][3]);
+        if (part == 0) {
+          *reinterpret_cast<uint32_t*>(so + g * 16 + nt * 8 + 2 * t) = h01;
+          *reinterpret_cast<uint32_t*>(so + (g + 8) * 16 + nt * 8 + 2 * t) = h23;
+        } else {
+          const float2 f01 = unpack_h2(h01), f23 = unpack_h2(h23);
+          *reinterpret_cast<uint32_t*>(so + g * 16 + nt * 8 + 2 * t) = pack_h2(acc[nt][0] - f01.x, acc[nt][1] - f01.y);
+          *reinterpret_cast<uint32_t*>(so + (g + 8) * 16 + nt * 8 + 2 * t) = pack_h2(acc[nt][2] - f23.x, acc[nt][3] - f23.y);
+        }
+      }
+      __syncwarp();
+      if (gy < he && gx < we) {
+        const uint4 v = *reinterpret_cast<const uint4*>(so + lane * 8);
+        *reinterpret_cast<uint4*>((part == 0 ? out : out_lo) + o) = v;
+      }
     }
   }
   }
@@ -637,7 +648,7 @@ static int env_int_u(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, const Extent& e, cudaStream_t st) {
+int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, const Extent& e, cudaStream_t st, __half* feat_lo) {
   using namespace umma;
   const int k0 = h->arch.base_kernel, r0 = (k0 - 1) / 2;
   const size_t bsm = (size_t)(k0 * k0 * 3 * C + (BC_H + 2 * r0) * (BC_W + 2 * r0) * 3) * sizeof(float);
@@ -649,7 +660,7 @@ int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, con
     const long long tiles = (long long)tx * ty * e.n;
     BF_REQUIRE(tiles < (1ll << 31), "too many base-conv tiles");
     const int g3 = (int)std::min<long long>(tiles, 4ll * h->sm_count);
-    base_conv3_mma_kernel<<<g3, 256, 0, st>>>(d_in, feat, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, tx, ty, (int)tiles);
+    base_conv3_mma_kernel<<<g3, 256, 0, st>>>(d_in, feat, feat_lo, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, tx, ty, (int)tiles);
   } else {
     base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, feat, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, k0);
   }
