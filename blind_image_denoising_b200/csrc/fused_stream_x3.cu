@@ -32,7 +32,7 @@ constexpr int GROUP_BYTES = 2 * ROW_BYTES;
 constexpr int W_LAYER_BYTES = 3 * 48 * 16 * 2;   // B operand of one conv: [dx 3][N 48][K 16] fp16
 constexpr int MAX_SMEM = 232448;
 constexpr int MAX_NL = 4;
-constexpr int MIN_SHARE = 24;           // rows per CTA below which fewer CTAs are launched
+constexpr int MIN_SHARE = 8;            // rows per CTA below which fewer CTAs are launched
 
 // barriers (8 B each)
 // mma_done[l][s & 1] (per layer: the epilogue of layer l starts while the later layers of the step are still being
