@@ -59,17 +59,7 @@ struct Params {
   int tw, tiles_x, rows_needed;   // output columns per strip, strips per image, output rows per strip
   long long total_rows, share;    // linearised (image, strip, row) space; COST units each CTA owns (see cost_to_row)
   int seg_overhead;               // cost of starting a segment at a strip start, in rows (halo rows + pipeline fill / drain)
-  long long* trace;               // debug timeline (BFCNN_STREAM_TRACE=1) of CTA trace_block, steps [TRACE_S0, TRACE_S0 + 32)
-  int trace_block;
 };
-constexpr uint32_t TRACE_S0 = 100;
-#ifdef BFCNN_STREAM_TRACE_BUILD   // compile-time: the timeline costs the issuer ~5 % even when it is switched off at run time
-#define STREAM_TRACE(slot) do { if (tr && S >= TRACE_S0 && S < TRACE_S0 + 32) p.trace[(S - TRACE_S0) * 8 + (slot)] = clock64(); } while (0)
-#define STREAM_TRACE_PTR(cond) ((tr && (cond) && S >= TRACE_S0 && S < TRACE_S0 + 32) ? p.trace + (S - TRACE_S0) * 8 + 4 : nullptr)
-#else
-#define STREAM_TRACE(slot) do { } while (0)
-#define STREAM_TRACE_PTR(cond) nullptr
-#endif
 
 // Work is split in COST space: every strip costs rows_needed + seg_overhead units, the first seg_overhead of which stand
 // for the halo rows and the pipeline fill / drain a CTA pays when it starts a new segment at a strip boundary.  Equal
@@ -137,17 +127,14 @@ struct EpiCtx {
 // one (layer, row) task of one warp: 32 pixels of output row rho of layer l
 template <int KIND, bool LAST_PASS>
 __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const EpiCtx& E, uint32_t bars, const float (&bias)[16],
-                                         const float* s_head, const float* s_bias_l, int l, int rho, long long* tp = nullptr) {
+                                         const float* s_head, const float* s_bias_l, int l, int rho) {
   const uint32_t taddr = E.tq + (uint32_t)((rho + 14 * l) & 31) * 16u;
   uint32_t v[16];
-  if (tp) tp[0] = clock64();
   tmem_ld16_issue(taddr, v);
   const bool inside = E.col_ok && ((unsigned)(E.y00 + rho) < (unsigned)E.he);
   if (KIND == KIND_A) {
     tmem_ld_wait(v);
-    if (tp) tp[1] = clock64();
     tmem_zero16(taddr);
-    if (tp) tp[2] = clock64();
     const uint32_t m = inside ? 0xFFFFFFFFu : 0u;
     // T = ReLU(acc), split into the hi part and the lo part (the rounding error of the hi part), per channel half
     uint32_t hp[8], lp[8];
@@ -164,7 +151,6 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
     sts128(dst + R.t_plane, make_uint4(hp[4], hp[5], hp[6], hp[7]));
     sts128(dst + 2 * R.t_plane, make_uint4(lp[0], lp[1], lp[2], lp[3]));
     sts128(dst + 3 * R.t_plane, make_uint4(lp[4], lp[5], lp[6], lp[7]));
-    if (tp) tp[3] = clock64();
   } else {
     // residual: X of this block (fp16) + the BN constant b' + the accumulator
     const uint32_t xsrc = R.x0 + (uint32_t)(((E.gb0 + (rho >> 1)) % K0) * 2 + (rho & 1)) * ROW_BYTES + E.pix;
@@ -267,8 +253,6 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
   }
   const long long r0 = min(p.total_rows, cost_to_row(p, (long long)blockIdx.x * p.share));
   const long long r1 = min(p.total_rows, cost_to_row(p, ((long long)blockIdx.x + 1) * p.share));
-  const bool tr = (p.trace != nullptr) && ((int)blockIdx.x == p.trace_block);
-  if (tr && tid == 0) p.trace[256] = clock64();
 
   // ---------------- one-time setup: barriers, TMEM, weights, zeroed rings
   if (tid < (int)NBARS) {
@@ -300,7 +284,6 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
-  if (tr && tid == 0) p.trace[257] = clock64();
 
   if (warp < EPI_WARPS) {
     // ================= epilogue warps =================
@@ -362,8 +345,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
           tc_fence_after();
           if (w < 0 || w >= Gm) continue;
           const int rho = 2 * w + tpar[k];
-          if ((l & 1) == 0) epi_task<KIND_A, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho,
-                                                        STREAM_TRACE_PTR(warp == 0 && lane == 0));
+          if ((l & 1) == 0) epi_task<KIND_A, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
           else if (l + 1 < nl) epi_task<KIND_B_TO_X, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
           else epi_task<KIND_B_OUT, LAST_PASS>(p, R, E, bars, bias, s_head, s_bias + l * C, l, rho);
         }
@@ -405,11 +387,9 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         st_blk[l] = (14 * l - 1) & 31;
       }
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
-        if (lane == 0) STREAM_TRACE(0);
         asm volatile("bar.sync %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");   // the helper has seen this step's barriers
         tc_fence_after();
         if (elect_one_sync()) {
-          STREAM_TRACE(1);
           // issue order inside a step: conv_b layers first (3, 1, 2, 0) -- the layers of a step are independent of each
           // other, and the conv_b epilogues (residual load, global / head stores) are the long ones
 #pragma unroll
@@ -479,14 +459,11 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             umma_commit(mbar_l);
             advance();
           }
-          STREAM_TRACE(2);
-          STREAM_TRACE(3);
         }
         __syncwarp();
       }
       gg += Gm;
     }
-    if (tr && lane == 0) { p.trace[258] = clock64(); p.trace[259] = S; }
   } else if (warp == WARP_MMA + 1) {
     // ================= barrier helper of the MMA issuer =================
     // step S needs: epi_done(S-2) (lane 0: input rows written, accumulator blocks drained), x_full of layer 0's group
@@ -537,7 +514,6 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
   }
   tc_fence_before();
   __syncthreads();
-  if (tr && tid == 0) p.trace[260] = clock64();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
 }
 
@@ -591,7 +567,6 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
     grid = (int)((total_cost + p.share - 1) / p.share);
     const size_t smem = smem_bytes(nl);
     BF_REQUIRE(smem <= (size_t)MAX_SMEM, "internal: streaming pass does not fit in shared memory");
-    p.trace = nullptr; p.trace_block = 0;
     CUtensorMap tmap;
     BF_CHECK(make_feature_tmap(&tmap, p.fin, e2, RW, 2));
     if (last) stream_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
