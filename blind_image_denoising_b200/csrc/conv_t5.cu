@@ -167,9 +167,11 @@ conv3x3_t5_kernel(const Params p) {
       const Seg sg = seg_at(p, a, r1);
       a += sg.yb - sg.ya;
       const int P = (sg.yb - sg.ya) + 2, Gm = (P + G - 1) / G, nsteps = Gm + 1;
-      const int y00 = sg.ya - 1, gx = sg.j * (RW - 2) - 1 + c;
-      const bool col_out = (c >= 1) && (c < RW - 1) && (gx < p.wd);
-      const long long px0 = ((long long)sg.b * p.h + y00) * p.wd + gx;   // pixel index of (b, y00, gx)
+      // column of the VIRTUAL row (all images side by side, one zero column between them): image vb, column gx
+      const int y00 = sg.ya - 1, vx = sg.j * (RW - 2) - 1 + c;
+      const int vb = vx >= 0 ? vx / (p.wd + 1) : -1, gx = vx - vb * (p.wd + 1);
+      const bool col_out = (c >= 1) && (c < RW - 1) && (vb >= 0) && (vb < p.n) && (gx < p.wd);
+      const long long px0 = ((long long)vb * p.h + y00) * p.wd + gx;   // pixel index of (vb, y00, gx)
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
         const int w = sr - 1;
         // the residual / mask operand of BOTH rows of this step is fetched before the wait for the MMAs (its address does
@@ -318,9 +320,10 @@ conv3x3_t5_kernel(const Params p) {
       const Seg sg = seg_at(p, a, r1);
       a += sg.yb - sg.ya;
       const int P = (sg.yb - sg.ya) + 2, Gm = (P + G - 1) / G, nsteps = Gm + 1;
-      const int y00 = sg.ya - 1, gx = sg.j * (RW - 2) - 1 + c;
-      const bool col_in = (gx >= 0) && (gx < p.wd);
-      const float* in_b = p.in + (long long)sg.b * p.h * p.wd * C + 8 * hf;
+      const int y00 = sg.ya - 1, vx = sg.j * (RW - 2) - 1 + c;
+      const int vb = vx >= 0 ? vx / (p.wd + 1) : -1, gx = vx - vb * (p.wd + 1);
+      const bool col_in = (vb >= 0) && (vb < p.n) && (gx < p.wd);   // separator columns and the outside are zero ("same" padding)
+      const float* in_b = p.in + (long long)vb * p.h * p.wd * C + 8 * hf;
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
         if ((int)(S % CVT_GROUPS) != cgrp) continue;   // the other converter group's step
         const uint32_t slot = S % KIN;
@@ -378,9 +381,14 @@ int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float*
   Params p;
   p.in = in; p.out = out; p.w = w; p.res = res; p.stats = stats;
   p.n = e.n; p.h = e.he; p.wd = e.we;
-  p.tiles_x = (e.we + (RW - 2) - 1) / (RW - 2);
-  p.total_rows = (long long)e.n * p.tiles_x * e.he;
-  const long long total_cost = (long long)e.n * p.tiles_x * ((long long)e.he + SEG_OVERHEAD);
+  // The images of the batch are laid side by side in one VIRTUAL row with a zero column between neighbours (which is the
+  // zero padding of both): strips of 126 output columns run across image boundaries, so a 256-pixel-wide crop does not
+  // waste a third of the lanes of its third strip.
+  const long long vwidth = (long long)e.n * (e.we + 1) - 1;
+  BF_REQUIRE(vwidth < (1ll << 30), "batch too wide for the virtual row");
+  p.tiles_x = (int)((vwidth + (RW - 2) - 1) / (RW - 2));
+  p.total_rows = (long long)p.tiles_x * e.he;
+  const long long total_cost = (long long)p.tiles_x * ((long long)e.he + SEG_OVERHEAD);
   int grid = (int)std::min<long long>(h->sm_count, std::max<long long>(1, p.total_rows / MIN_SHARE));
   p.share = (total_cost + grid - 1) / grid;
   grid = (int)((total_cost + p.share - 1) / p.share);
