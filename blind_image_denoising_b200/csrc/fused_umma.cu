@@ -400,7 +400,7 @@ umma_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
 constexpr int BC_W = 64, BC_H = 16;
 __global__ void __launch_bounds__(256, 2)
 base_conv_f16_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, const float* __restrict__ w,
-                     int h, int wd, int he, int we, int k0) {
+                     int h, int wd, int he, int we, int k0, long long img_stride, long long row_stride) {
   extern __shared__ __align__(16) float bsm[];
   const int r0 = (k0 - 1) >> 1;
   const int tw = BC_W + 2 * r0, th = BC_H + 2 * r0;
@@ -462,7 +462,7 @@ base_conv_f16_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, 
     uint4 lo, hi;
     lo.x = pack_h2(acc[p][0], acc[p][1]); lo.y = pack_h2(acc[p][2], acc[p][3]); lo.z = pack_h2(acc[p][4], acc[p][5]); lo.w = pack_h2(acc[p][6], acc[p][7]);
     hi.x = pack_h2(acc[p][8], acc[p][9]); hi.y = pack_h2(acc[p][10], acc[p][11]); hi.z = pack_h2(acc[p][12], acc[p][13]); hi.w = pack_h2(acc[p][14], acc[p][15]);
-    uint4* o = reinterpret_cast<uint4*>(out + ((((long long)b * he + gy) * we + gx) << 4));
+    uint4* o = reinterpret_cast<uint4*>(out + (((long long)b * img_stride + (long long)gy * row_stride + gx) << 4));
     o[0] = lo;
     o[1] = hi;
   }
@@ -490,7 +490,8 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 }
 __global__ void __launch_bounds__(256, 4)
 base_conv3_mma_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, __half* __restrict__ out_lo /* or nullptr */,
-                      const float* __restrict__ w, int h, int wd, int he, int we, int tiles_x, int tiles_y, int tiles) {
+                      const float* __restrict__ w, int h, int wd, int he, int we, int tiles_x, int tiles_y, int tiles,
+                      long long img_stride, long long row_stride) {
   __shared__ __align__(16) __half s_in[BM_TH * BM_TW * 4];
   __shared__ __align__(16) __half s_out[8][16 * 16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -581,7 +582,7 @@ base_conv3_mma_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out,
     // stage [16 px][16 ch] fp16, then 32 lanes x 16 B = the 512 contiguous bytes of the 16 pixels; for the F16X3 stacks
     // a second round stores the lo part (the rounding error of the fp16 value) into the lo feature map
     const int gy = y0 + ry, gx = x0 + px0 + (lane >> 1);
-    const long long o = ((((long long)b * he + gy) * we + gx) << 4) + (lane & 1) * 8;
+    const long long o = (((long long)b * img_stride + (long long)gy * row_stride + gx) << 4) + (lane & 1) * 8;
     for (int part = 0; part < (out_lo ? 2 : 1); ++part) {
       __syncwarp();
 #pragma unroll
@@ -648,8 +649,10 @@ static int env_int_u(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, const Extent& e, cudaStream_t st, __half* feat_lo) {
+int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, const Extent& e, cudaStream_t st, __half* feat_lo,
+                         long long img_stride, long long row_stride) {
   using namespace umma;
+  if (img_stride == 0) { img_stride = (long long)e.he * e.we; row_stride = e.we; }   // [n][he][we][16]
   const int k0 = h->arch.base_kernel, r0 = (k0 - 1) / 2;
   const size_t bsm = (size_t)(k0 * k0 * 3 * C + (BC_H + 2 * r0) * (BC_W + 2 * r0) * 3) * sizeof(float);
   dim3 grid((e.we + BC_W - 1) / BC_W, (e.he + BC_H - 1) / BC_H, e.n);
@@ -660,9 +663,10 @@ int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, con
     const long long tiles = (long long)tx * ty * e.n;
     BF_REQUIRE(tiles < (1ll << 31), "too many base-conv tiles");
     const int g3 = (int)std::min<long long>(tiles, 4ll * h->sm_count);
-    base_conv3_mma_kernel<<<g3, 256, 0, st>>>(d_in, feat, feat_lo, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, tx, ty, (int)tiles);
+    base_conv3_mma_kernel<<<g3, 256, 0, st>>>(d_in, feat, feat_lo, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, tx, ty, (int)tiles,
+                                              img_stride, row_stride);
   } else {
-    base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, feat, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, k0);
+    base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, feat, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, k0, img_stride, row_stride);
   }
   h->launches++;
   BF_CUDA(cudaGetLastError());

@@ -44,8 +44,9 @@ int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool
 // fp16 NHWC16 feature map as a 5-D TMA tensor {ch8, half, x, y, n}, box = box_x pixels x box_y rows of one channel half
 int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e, int box_x, int box_y);
 // feat_lo != nullptr (F16X3 stacks, k0 = 3 only): also the lo part of the hi/lo split
+// img_stride / row_stride (pixels; 0 = the plain [n][he][we] map): where pixel (b, y, x) goes, b * img_stride + y * row_stride + x
 int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, const Extent& e, cudaStream_t st,
-                         __half* feat_lo = nullptr);
+                         __half* feat_lo = nullptr, long long img_stride = 0, long long row_stride = 0);
 // ---- fused_stream.cu: the same arithmetic as a row-streaming pipeline (no vertical halo recompute); default F16 engine
 int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                            cudaStream_t st);
