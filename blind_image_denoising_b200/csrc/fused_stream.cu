@@ -87,8 +87,8 @@ struct Params {
   int n, h, w, he, we;
   int blk0, nblk;
   int out_u8;
-  int tw, tiles_x, rows_needed;   // output columns per strip, strips per image, output rows per strip
-  long long total_rows, share;    // linearised (image, strip, row) space; COST units each CTA owns (see cost_to_row)
+  int tw, tiles_x, rows_needed;   // output columns per strip, strips per virtual row, output rows per strip
+  long long total_rows, share;    // linearised (strip, row) space; COST units each CTA owns (see cost_to_row)
   int seg_overhead;               // cost of starting a segment at a strip start, in rows (halo rows + pipeline fill / drain)
   long long* trace;               // debug timeline (BFCNN_STREAM_TRACE=1) of CTA trace_block, steps [TRACE_S0, TRACE_S0 + 32)
   int trace_block;
