@@ -46,9 +46,12 @@ __host__ __device__ inline uint32_t rings_offset(int nl) { return (SM_WTS + (uin
 __host__ __device__ inline uint32_t smem_bytes(int nl) { return rings_offset(nl) + 4 * plane_bytes_of(2 * K0) + 4 * plane_bytes_of(2 * KT); }
 
 struct Params {
-  long long plane_halves;  // halves between the hi and the lo part of a feature map (n * he * we * 16)
-  const __half* fin;       // [2 parts][n][he][we][16]  input feature map of this pass
-  __half* fout;            // [n][he][we][16]
+  // Feature maps between passes: ONE virtual row per image row, the n images side by side, each followed by a zero column
+  // (the "same" padding of both neighbours), hi part then lo part: [2 parts][he][vw = n (we + 1)][16] (see fused_stream.cu).
+  long long plane_halves;  // halves between the hi and the lo part of a feature map (he * vw * 16)
+  const __half* fin;       // [2 parts][he][vw][16]  input feature map of this pass
+  __half* fout;            // [2 parts][he][vw][16]
+  int vw;                  // n * (we + 1)
   void* out;               // [n][h][w][3] uint8 or float
   const uint8_t* wumma;    // [2N][W_LAYER_BYTES]
   const float* bias;       // [2N][16]
@@ -56,8 +59,8 @@ struct Params {
   int n, h, w, he, we;
   int blk0, nblk;
   int out_u8;
-  int tw, tiles_x, rows_needed;   // output columns per strip, strips per image, output rows per strip
-  long long total_rows, share;    // linearised (image, strip, row) space; COST units each CTA owns (see cost_to_row)
+  int tw, tiles_x, rows_needed;   // output columns per strip, strips per virtual row, output rows per strip
+  long long total_rows, share;    // linearised (strip, row) space; COST units each CTA owns (see cost_to_row)
   int seg_overhead;               // cost of starting a segment at a strip start, in rows (halo rows + pipeline fill / drain)
 };
 
@@ -293,7 +296,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     E.tq = tmem + ((uint32_t)(quarter * 32) << 16);
     E.pix = (uint32_t)c * 16u;
     E.he = p.he; E.h_img = p.h; E.nl = nl;
-    E.row_halves = (long long)p.we * 16; E.row_out = (long long)p.w * 3;
+    E.row_halves = (long long)p.vw * 16; E.row_out = (long long)p.w * 3;
     // this warp's tasks of a step: t = set, set + 4 (< 2 nl): row parity t / nl of layer (t + parity) % nl
     int tl[2], tpar[2], ntask = 0;
     for (int t = set; t < 2 * nl && ntask < 2; t += 4) { tpar[ntask] = t / nl; tl[ntask] = (t + tpar[ntask]) % nl; ++ntask; }
@@ -330,12 +333,13 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
       a += sg.yb - sg.ya;
       const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
       {
-        const int gx = sg.j * p.tw - halo + c;
+        const int vx = sg.j * p.tw - halo + c;                     // column of the virtual row
+        const int vb = vx >= 0 ? vx / (p.we + 1) : -1, gx = vx - vb * (p.we + 1);   // image, column inside the image
         E.y00 = sg.ya - nl; E.P = P;
-        E.col_ok = (gx >= 0) && (gx < p.we);
+        E.col_ok = (vb >= 0) && (vb < p.n) && (gx < p.we);           // separator columns and the outside stay zero
         E.col_out = E.col_ok && (c >= halo) && (c < RW - halo) && (!LAST_PASS || gx < p.w);
-        E.fout_col = p.fout + ((((long long)sg.b * p.he + E.y00) * p.we + gx) << 4);
-        E.out_col = reinterpret_cast<uint8_t*>(p.out) + ((((long long)sg.b * p.h + E.y00) * p.w + gx) * 3) * (p.out_u8 ? 1 : 4);
+        E.fout_col = p.fout + (((long long)E.y00 * p.vw + vx) << 4);
+        E.out_col = reinterpret_cast<uint8_t*>(p.out) + ((((long long)vb * p.h + E.y00) * p.w + gx) * 3) * (p.out_u8 ? 1 : 4);
         E.gb0 = (int)(gg % K0);
       }
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
@@ -503,10 +507,10 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
           const uint32_t bar = bars + (BAR_XFULL + k) * 8;
           mbar_arrive_expect_tx(bar, 4 * GROUP_BYTES);
           const uint32_t dst = R.x0 + k * GROUP_BYTES;
-          tma_load_q(dst, &tmap, 0, gx0, y00 + 2 * g, sg.b, bar);
-          tma_load_q(dst + R.x0_plane, &tmap, 1, gx0, y00 + 2 * g, sg.b, bar);
-          tma_load_q(dst + 2 * R.x0_plane, &tmap, 0, gx0, y00 + 2 * g, sg.b + p.n, bar);   // lo part: images n .. 2n-1
-          tma_load_q(dst + 3 * R.x0_plane, &tmap, 1, gx0, y00 + 2 * g, sg.b + p.n, bar);
+          tma_load_q(dst, &tmap, 0, gx0, y00 + 2 * g, 0, bar);   // gx0: column of the virtual row
+          tma_load_q(dst + R.x0_plane, &tmap, 1, gx0, y00 + 2 * g, 0, bar);
+          tma_load_q(dst + 2 * R.x0_plane, &tmap, 0, gx0, y00 + 2 * g, 1, bar);   // lo part: "image" 1 of the tensor map
+          tma_load_q(dst + 3 * R.x0_plane, &tmap, 1, gx0, y00 + 2 * g, 1, bar);
         }
       }
     }
@@ -530,16 +534,24 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
     attr_set = true;
   }
   const int passes = N;   // one residual block per pass
-  const size_t feat_halves = (size_t)e.n * e.he * e.we * C;
+  const long long vw = (long long)e.n * (e.we + 1);   // virtual row: the images side by side, a zero column after each
+  BF_REQUIRE(vw < (1ll << 30), "batch too wide for the virtual row");
+  const size_t feat_halves = (size_t)e.he * vw * C;
   BF_CHECK(h->ws_feat[1].reserve(feat_halves * 2 * sizeof(__half)));   // hi part, then lo part
   if (passes > 1) BF_CHECK(h->ws_feat[0].reserve(feat_halves * 2 * sizeof(__half)));
+  // the separator columns sit at a regular stride of (we + 1) pixels, in the hi and in the lo part: zero them in both maps
+  // (nothing else writes them)
+  for (int k = (passes > 1 ? 0 : 1); k < 2; ++k)
+    for (int part = 0; part < 2; ++part)
+      BF_CUDA(cudaMemset2DAsync(h->ws_feat[k].as<__half>() + part * feat_halves + (size_t)e.we * C, (size_t)(e.we + 1) * C * sizeof(__half), 0,
+                                C * sizeof(__half), (size_t)e.he * e.n, st));
   // pass "-1": base conv (hi + lo) into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
   if (h->arch.base_kernel == 3 && !getenv("BFCNN_BASE_FFMA"))   // tensor-core base conv (fused_umma.cu), hi + lo outputs
-    BF_CHECK(launch_base_conv_f16(h, d_in, h->ws_feat[1].as<__half>(), e, st, h->ws_feat[1].as<__half>() + feat_halves));
+    BF_CHECK(launch_base_conv_f16(h, d_in, h->ws_feat[1].as<__half>(), e, st, h->ws_feat[1].as<__half>() + feat_halves, e.we + 1, vw));
   else
-    BF_CHECK(launch_base_conv_f16_x3(h, d_in, h->ws_feat[1].as<__half>(), h->ws_feat[1].as<__half>() + feat_halves, e, st));
-  Extent e2 = e;
-  e2.n = 2 * e.n;   // the tensor map sees the lo images behind the hi images
+    BF_CHECK(launch_base_conv_f16_x3(h, d_in, h->ws_feat[1].as<__half>(), h->ws_feat[1].as<__half>() + feat_halves, e, st, e.we + 1, vw));
+  Extent e2 = e;   // what the TMA sees: two "images" (hi part, lo part) of he rows and vw columns
+  e2.n = 2; e2.we = (int)vw;
   for (int ps = 0; ps < passes; ++ps) {
     Params p;
     const bool last = (ps + 1 == passes);
@@ -550,18 +562,19 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
     p.wumma = h->d_conv_umma_x3.as<uint8_t>();
     p.bias = h->d_bias_f32.as<float>();
     p.whead = h->d_head_f32.as<float>();
-    p.n = e.n; p.h = e.h; p.w = e.w; p.he = e.he; p.we = e.we;
+    p.n = e.n; p.h = e.h; p.w = e.w; p.he = e.he; p.we = e.we; p.vw = (int)vw;
     p.blk0 = ps;
     p.nblk = 1;
     p.out_u8 = out_u8 ? 1 : 0;
     const int nl = 2;
     p.tw = RW - 2 * nl;
     p.rows_needed = last ? e.h : e.he;
-    const int cols_needed = last ? e.w : e.we;
-    p.tiles_x = (cols_needed + p.tw - 1) / p.tw;
-    p.total_rows = (long long)e.n * p.tiles_x * p.rows_needed;
+    // columns of the virtual row that need an output: up to the last needed column of the last image
+    const long long cols_needed = (long long)(e.n - 1) * (e.we + 1) + (last ? e.w : e.we);
+    p.tiles_x = (int)((cols_needed + p.tw - 1) / p.tw);
+    p.total_rows = (long long)p.tiles_x * p.rows_needed;
     p.seg_overhead = 2 * nl + 2 * (LAG * (nl - 1) + 1);
-    const long long total_cost = (long long)e.n * p.tiles_x * ((long long)p.rows_needed + p.seg_overhead);
+    const long long total_cost = (long long)p.tiles_x * ((long long)p.rows_needed + p.seg_overhead);
     int grid = (int)std::min<long long>(h->sm_count, std::max<long long>(1, p.total_rows / MIN_SHARE));
     p.share = (total_cost + grid - 1) / grid;
     grid = (int)((total_cost + p.share - 1) / p.share);

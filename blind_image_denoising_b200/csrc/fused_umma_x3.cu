@@ -618,7 +618,8 @@ umma_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
 constexpr int BC_W = 64, BC_H = 16;
 __global__ void __launch_bounds__(256, 2)
 base_conv_f16_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, __half* __restrict__ out_lo /* or nullptr */,
-                     const float* __restrict__ w, int h, int wd, int he, int we, int k0) {
+                     const float* __restrict__ w, int h, int wd, int he, int we, int k0,
+                     long long img_stride /* pixels between images */, long long row_stride /* pixels between rows */) {
   extern __shared__ __align__(16) float bsm[];
   const int r0 = (k0 - 1) >> 1;
   const int tw = BC_W + 2 * r0, th = BC_H + 2 * r0;
@@ -680,7 +681,7 @@ base_conv_f16_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, 
     uint4 lo, hi;
     lo.x = pack_h2(acc[p][0], acc[p][1]); lo.y = pack_h2(acc[p][2], acc[p][3]); lo.z = pack_h2(acc[p][4], acc[p][5]); lo.w = pack_h2(acc[p][6], acc[p][7]);
     hi.x = pack_h2(acc[p][8], acc[p][9]); hi.y = pack_h2(acc[p][10], acc[p][11]); hi.z = pack_h2(acc[p][12], acc[p][13]); hi.w = pack_h2(acc[p][14], acc[p][15]);
-    const long long oo = (((long long)b * he + gy) * we + gx) << 4;
+    const long long oo = ((long long)b * img_stride + (long long)gy * row_stride + gx) << 4;
     uint4* o = reinterpret_cast<uint4*>(out + oo);
     o[0] = lo;
     o[1] = hi;
@@ -743,13 +744,15 @@ static int env_int_u3(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-int launch_base_conv_f16_x3(bfcnn_handle* h, const uint8_t* d_in, __half* hi, __half* lo, const Extent& e, cudaStream_t st) {
+int launch_base_conv_f16_x3(bfcnn_handle* h, const uint8_t* d_in, __half* hi, __half* lo, const Extent& e, cudaStream_t st,
+                            long long img_stride, long long row_stride) {
   using namespace umma3;
+  if (img_stride == 0) { img_stride = (long long)e.he * e.we; row_stride = e.we; }   // [n][he][we][16]
   const int k0 = h->arch.base_kernel, r0 = (k0 - 1) / 2;
   const size_t bsm = (size_t)(k0 * k0 * 3 * C + (BC_H + 2 * r0) * (BC_W + 2 * r0) * 3) * sizeof(float);
   dim3 grid((e.we + BC_W - 1) / BC_W, (e.he + BC_H - 1) / BC_H, e.n);
   BF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "image too large for the base conv grid");
-  base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, hi, lo, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, k0);
+  base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, hi, lo, h->d_base_f32.as<float>(), e.h, e.w, e.he, e.we, k0, img_stride, row_stride);
   h->launches++;
   BF_CUDA(cudaGetLastError());
   return BFCNN_OK;
@@ -786,7 +789,7 @@ int run_fused_stack_umma_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, b
     BF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "image too large for the base conv grid");
     __half* b_hi = h->ws_feat[1].as<__half>();
     base_conv_f16_kernel<<<grid, 256, bsm, st>>>(d_in, b_hi, P == 2 ? b_hi + feat_halves : nullptr, h->d_base_f32.as<float>(), e.h, e.w,
-                                                 e.he, e.we, k0);
+                                                 e.he, e.we, k0, (long long)e.he * e.we, e.we);
     h->launches++;
     BF_CUDA(cudaGetLastError());
   }

@@ -57,7 +57,8 @@ int run_fused_stack_umma_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, b
 // ---- fused_stream_x3.cu: the row-streaming pipeline in the F16X3 arithmetic (default engine of precision f16x3)
 int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                               cudaStream_t st);
-int launch_base_conv_f16_x3(bfcnn_handle* h, const uint8_t* d_in, __half* hi, __half* lo, const Extent& e, cudaStream_t st);
+int launch_base_conv_f16_x3(bfcnn_handle* h, const uint8_t* d_in, __half* hi, __half* lo, const Extent& e, cudaStream_t st,
+                            long long img_stride = 0, long long row_stride = 0);
 
 // ---- train.cu
 int run_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, float* noisy_f32, int n,
