@@ -590,14 +590,15 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
   const size_t feat_halves = (size_t)e.he * vw * C;
   BF_CHECK(h->ws_feat[1].reserve(feat_halves * sizeof(__half)));
   if (passes > 1) BF_CHECK(h->ws_feat[0].reserve(feat_halves * sizeof(__half)));
-  // the separator columns sit at a regular stride of (we + 1) pixels: zero them in both maps (nothing else writes them)
-  for (int k = (passes > 1 ? 0 : 1); k < 2; ++k)
+  // the separator columns sit at a regular stride of (we + 1) pixels: zero them in both maps (nothing else writes
+  // them); the last one lies outside the tensor map, where the TMA fills in zeros, so one image needs no memset
+  for (int k = (passes > 1 ? 0 : 1); k < 2 && e.n > 1; ++k)
     BF_CUDA(cudaMemset2DAsync(h->ws_feat[k].as<__half>() + (size_t)e.we * C, (size_t)(e.we + 1) * C * sizeof(__half), 0, C * sizeof(__half),
                               (size_t)e.he * e.n, st));
   // pass "-1": base conv into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
   BF_CHECK(launch_base_conv_f16(h, d_in, h->ws_feat[1].as<__half>(), e, st, nullptr, e.we + 1, vw));
   Extent ev = e;   // what the TMA sees: one "image" of he rows and vw columns
-  ev.n = 1; ev.we = (int)vw;
+  ev.n = 1; ev.we = (int)vw - 1;
   for (int ps = 0; ps < passes; ++ps) {
     Params p;
     const bool last = (ps + 1 == passes);
@@ -633,7 +634,7 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
       p.trace = h->ws_feat[2].as<long long>(); p.trace_block = grid / 2;
     }
     CUtensorMap tmap;
-    BF_CHECK(make_feature_tmap(&tmap, p.fin, ev, RW, 2));
+    BF_CHECK(make_feature_tmap(&tmap, p.fin, ev, RW, 2, vw));
     if (last) stream_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     else stream_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     h->launches++;

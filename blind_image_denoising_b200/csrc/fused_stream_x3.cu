@@ -540,8 +540,9 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
   BF_CHECK(h->ws_feat[1].reserve(feat_halves * 2 * sizeof(__half)));   // hi part, then lo part
   if (passes > 1) BF_CHECK(h->ws_feat[0].reserve(feat_halves * 2 * sizeof(__half)));
   // the separator columns sit at a regular stride of (we + 1) pixels, in the hi and in the lo part: zero them in both maps
-  // (nothing else writes them)
-  for (int k = (passes > 1 ? 0 : 1); k < 2; ++k)
+  // (nothing else writes
+  // them); the last one lies outside the tensor map, where the TMA fills in zeros, so one image needs no memset
+  for (int k = (passes > 1 ? 0 : 1); k < 2 && e.n > 1; ++k)
     for (int part = 0; part < 2; ++part)
       BF_CUDA(cudaMemset2DAsync(h->ws_feat[k].as<__half>() + part * feat_halves + (size_t)e.we * C, (size_t)(e.we + 1) * C * sizeof(__half), 0,
                                 C * sizeof(__half), (size_t)e.he * e.n, st));
@@ -551,7 +552,7 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
   else
     BF_CHECK(launch_base_conv_f16_x3(h, d_in, h->ws_feat[1].as<__half>(), h->ws_feat[1].as<__half>() + feat_halves, e, st, e.we + 1, vw));
   Extent e2 = e;   // what the TMA sees: two "images" (hi part, lo part) of he rows and vw columns
-  e2.n = 2; e2.we = (int)vw;
+  e2.n = 2; e2.we = (int)vw - 1;
   for (int ps = 0; ps < passes; ++ps) {
     Params p;
     const bool last = (ps + 1 == passes);
@@ -581,7 +582,7 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
     const size_t smem = smem_bytes(nl);
     BF_REQUIRE(smem <= (size_t)MAX_SMEM, "internal: streaming pass does not fit in shared memory");
     CUtensorMap tmap;
-    BF_CHECK(make_feature_tmap(&tmap, p.fin, e2, RW, 2));
+    BF_CHECK(make_feature_tmap(&tmap, p.fin, e2, RW, 2, vw));
     if (last) stream_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     else stream_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     h->launches++;

@@ -616,7 +616,8 @@ base_conv3_mma_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out,
 typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e, int box_x, int box_y) {
+int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e, int box_x, int box_y, long long row_px) {
+  if (row_px == 0) row_px = e.we;   // pixels between rows (>= e.we)
   static tmap_encode_fn enc = nullptr;
   if (!enc) {
     void* fn = nullptr;
@@ -630,7 +631,7 @@ int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e, int
   }
   // fp16 NHWC16 viewed as {ch8, half, x, y, n}
   const cuuint64_t dims[5] = {8, 2, (cuuint64_t)e.we, (cuuint64_t)e.he, (cuuint64_t)e.n};
-  const cuuint64_t strides[4] = {16, 32, (cuuint64_t)e.we * 32, (cuuint64_t)e.he * e.we * 32};
+  const cuuint64_t strides[4] = {16, 32, (cuuint64_t)row_px * 32, (cuuint64_t)e.he * row_px * 32};
   const cuuint32_t box[5] = {8, 1, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr,

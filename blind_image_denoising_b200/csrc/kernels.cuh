@@ -42,7 +42,7 @@ int run_fused_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_
 int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                          cudaStream_t st);
 // fp16 NHWC16 feature map as a 5-D TMA tensor {ch8, half, x, y, n}, box = box_x pixels x box_y rows of one channel half
-int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e, int box_x, int box_y);
+int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e, int box_x, int box_y, long long row_px = 0);
 // feat_lo != nullptr (F16X3 stacks, k0 = 3 only): also the lo part of the hi/lo split
 // img_stride / row_stride (pixels; 0 = the plain [n][he][we] map): where pixel (b, y, x) goes, b * img_stride + y * row_stride + x
 int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, const Extent& e, cudaStream_t st,
