@@ -225,12 +225,20 @@ wgrad3x3_x3_kernel(const float* __restrict__ A, const float* __restrict__ G, flo
     const uint32_t off = k < 2 * SLACK_PX ? (uint32_t)k * 16u : (uint32_t)(A_PLANE - (4 * SLACK_PX - k) * 16);
     sts128(base + off, make_uint4(0u, 0u, 0u, 0u));
   }
-  const int ntiles = tiles_x * tiles_y * n;
+  const int ntiles = tiles_x * tiles_y;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    // Tiles walk the VIRTUAL row of the batch: the n images side by side, one zero column between neighbours (it is the
+    // zero padding both of them see), so a 256-pixel-wide image does not pay for a fifth, nearly empty 62-column tile.
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int oy = ty * WG_TH - 1, ox = tx * (RW - 2) - 1;
-    const float* a_b = A + (long long)b * h * wd * C;
-    const float* g_b = G + (long long)b * h * wd * C;
+    // a thread stages the same column and channel half in every iteration (NT / 2 is a multiple of RW)
+    static_assert((NT / 2) % RW == 0, "staging assumes a fixed column per thread");
+    const int c_t = (tid >> 1) % RW, hf_t = tid & 1;
+    const int vx = ox + c_t, vb = vx >= 0 ? vx / (wd + 1) : -1, gx_t = vx - vb * (wd + 1);
+    const bool col_ok = vb >= 0 && vb < n && gx_t < wd;
+    const long long col_off = col_ok ? (((long long)vb * h * wd + gx_t) * C + 8 * hf_t) : 0;
+    const float* a_b = A + col_off;
+    const float* g_b = G + col_off;
     __syncthreads();
     // Staging in batches of 4 iterations: all global loads of a batch first, then the splits and shared-memory stores.
     // (split_store is inline asm with a memory clobber, so a load placed after it cannot move above it: one load per
@@ -241,12 +249,11 @@ wgrad3x3_x3_kernel(const float* __restrict__ A, const float* __restrict__ G, flo
 #pragma unroll
       for (int k = 0; k < SB; ++k) {
         const int i = i0 + k * NT;
-        const int hf = i & 1, pix = i >> 1;
-        const int r = pix / RW, c = pix % RW;
-        const int gy = oy + r, gx = ox + c;
+        const int r = (i >> 1) / RW;
+        const int gy = oy + r;
         u[k] = make_float4(0.f, 0.f, 0.f, 0.f); v[k] = u[k];
-        if (i < RH * RW * 2 && gy >= 0 && gy < h && gx >= 0 && gx < wd) {
-          const float4* s = reinterpret_cast<const float4*>(a_b + ((long long)gy * wd + gx) * C + 8 * hf);
+        if (i < RH * RW * 2 && col_ok && gy >= 0 && gy < h) {
+          const float4* s = reinterpret_cast<const float4*>(a_b + (long long)gy * wd * C);
           u[k] = s[0]; v[k] = s[1];
         }
       }
@@ -265,12 +272,11 @@ wgrad3x3_x3_kernel(const float* __restrict__ A, const float* __restrict__ G, flo
 #pragma unroll
       for (int k = 0; k < SB; ++k) {
         const int i = i0 + k * NT;
-        const int hf = i & 1, pix = i >> 1;
-        const int r = pix / RW, c = pix % RW;
-        const int gy = oy + 1 + r, gx = ox + c;
+        const int r = (i >> 1) / RW;
+        const int gy = oy + 1 + r;
         u[k] = make_float4(0.f, 0.f, 0.f, 0.f); v[k] = u[k];
-        if (i < WG_TH * RW * 2 && c >= 1 && c < RW - 1 && gy < h && gx < wd) {
-          const float4* s = reinterpret_cast<const float4*>(g_b + ((long long)gy * wd + gx) * C + 8 * hf);
+        if (i < WG_TH * RW * 2 && col_ok && c_t >= 1 && c_t < RW - 1 && gy < h) {
+          const float4* s = reinterpret_cast<const float4*>(g_b + (long long)gy * wd * C);
           u[k] = s[0]; v[k] = s[1];
         }
       }
@@ -385,8 +391,10 @@ int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, flo
   }
   static_assert((size_t)8 * 2304 * 4 <= (size_t)2 * ((WG_TH + 2) * RW + 2 * SLACK_PX) * PX_BYTES + (size_t)2 * (WG_TH * RW + 2 * SLACK_PX) * PX_BYTES,
                 "cross-warp reduction buffer does not fit");
-  const int tiles_x = (e.we + (RW - 2) - 1) / (RW - 2), tiles_y = (e.he + WG_TH - 1) / WG_TH;
-  const long long ntiles = (long long)tiles_x * tiles_y * e.n;
+  const long long vcols = (long long)e.n * (e.we + 1) - 1;   // virtual row: the images side by side, a zero column between them
+  BF_REQUIRE(vcols < (1ll << 30), "batch too wide for the virtual row");
+  const int tiles_x = (int)((vcols + (RW - 2) - 1) / (RW - 2)), tiles_y = (e.he + WG_TH - 1) / WG_TH;
+  const long long ntiles = (long long)tiles_x * tiles_y;
   BF_REQUIRE(ntiles < (1ll << 31), "too many tiles");
   const int grid = (int)std::min<long long>(ntiles, std::min(max_parts, 2 * h->sm_count));
   wgrad3x3_x3_kernel<<<grid, NT, smem, st>>>(act, grad, partial, e.n, e.he, e.we, tiles_x, tiles_y, g_scale, 1.0f / (64.f * g_scale));
