@@ -291,9 +291,12 @@ wgrad3x3_x3_kernel(const float* __restrict__ A, const float* __restrict__ G, flo
       }
     }
     __syncthreads();
-    for (int r = warp; r < WG_TH; r += NT / 32) {
+    // work unit = half a tile row (two K steps of 16 pixels): 24 units over 8 warps, 3 each (whole rows: 2 / 2 / 2 / 2 / 1 / 1 / 1 / 1)
+    static_assert((RW / 16) % 2 == 0 && (WG_TH * 2) % (NT / 32) == 0, "units must divide evenly over the warps");
+    for (int u = warp; u < WG_TH * 2; u += NT / 32) {
+      const int r = u >> 1;
 #pragma unroll 1
-      for (int ks = 0; ks < RW / 16; ++ks) {
+      for (int ks = (u & 1) * (RW / 32); ks < ((u & 1) + 1) * (RW / 32); ++ks) {
         uint32_t bh[4], bl[4];
         const int gpix = r * RW + ks * 16 + gp;
         ldsm4t(bh, gH + px_off(gpix, gh));
