@@ -194,16 +194,155 @@ __device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
+// Staging of one wgrad tile by NTH threads: activations with the one-pixel halo and output gradients (zero on the halo
+// columns and outside the image) from fp32 NHWC16 into the fp16 hi / lo planes.  Tiles walk the VIRTUAL row of the batch:
+// the n images side by side, one zero column between neighbours (it is the zero padding both of them see), so a
+// 256-pixel-wide image does not pay for a fifth, nearly empty 62-column tile.  All global loads of a batch of SB
+// iterations are issued first, then the splits and shared-memory stores (split_store is inline asm with a memory
+// clobber, so a load placed after it cannot move above it: one load per iteration meant 13 serial global-load
+// latencies per tile).
+template <int NTH, int SBA, int SBG>
+__device__ __forceinline__ void wgrad_stage_tile(int lt, uint32_t aH, uint32_t aL, uint32_t gH, uint32_t gL, const float* __restrict__ A,
+                                                 const float* __restrict__ G, int n, int h, int wd, int oy, int ox, float g_scale) {
+  constexpr int RH = WG_TH + 2;
+  // a thread stages the same column and channel half in every iteration (NTH / 2 is a multiple of RW)
+  static_assert((NTH / 2) % RW == 0, "staging assumes a fixed column per thread");
+  const int c_t = (lt >> 1) % RW, hf_t = lt & 1;
+  const int vx = ox + c_t, vb = vx >= 0 ? vx / (wd + 1) : -1, gx_t = vx - vb * (wd + 1);
+  const bool col_ok = vb >= 0 && vb < n && gx_t < wd;
+  const long long col_off = col_ok ? (((long long)vb * h * wd + gx_t) * C + 8 * hf_t) : 0;
+  const float* a_b = A + col_off;
+  const float* g_b = G + col_off;
+  for (int i0 = lt; i0 < RH * RW * 2; i0 += NTH * SBA) {
+    float4 u[SBA], v[SBA];
+#pragma unroll
+    for (int k = 0; k < SBA; ++k) {
+      const int i = i0 + k * NTH;
+      const int gy = oy + (i >> 1) / RW;
+      u[k] = make_float4(0.f, 0.f, 0.f, 0.f); v[k] = u[k];
+      if (i < RH * RW * 2 && col_ok && gy >= 0 && gy < h) {
+        const float4* sp = reinterpret_cast<const float4*>(a_b + (long long)gy * wd * C);
+        u[k] = sp[0]; v[k] = sp[1];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SBA; ++k) {
+      const int i = i0 + k * NTH;
+      if (i >= RH * RW * 2) break;
+      const int hf = i & 1, pix = i >> 1;
+      float4 a = u[k], bq = v[k];
+      a.x *= 64.f; a.y *= 64.f; a.z *= 64.f; a.w *= 64.f; bq.x *= 64.f; bq.y *= 64.f; bq.z *= 64.f; bq.w *= 64.f;
+      split_store(aH + px_off(pix, hf), aL + px_off(pix, hf), a, bq);
+    }
+  }
+  for (int i0 = lt; i0 < WG_TH * RW * 2; i0 += NTH * SBG) {
+    float4 u[SBG], v[SBG];
+#pragma unroll
+    for (int k = 0; k < SBG; ++k) {
+      const int i = i0 + k * NTH;
+      const int gy = oy + 1 + (i >> 1) / RW;
+      u[k] = make_float4(0.f, 0.f, 0.f, 0.f); v[k] = u[k];
+      if (i < WG_TH * RW * 2 && col_ok && c_t >= 1 && c_t < RW - 1 && gy < h) {
+        const float4* sp = reinterpret_cast<const float4*>(g_b + (long long)gy * wd * C);
+        u[k] = sp[0]; v[k] = sp[1];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SBG; ++k) {
+      const int i = i0 + k * NTH;
+      if (i >= WG_TH * RW * 2) break;
+      const int hf = i & 1, pix = i >> 1;
+      float4 a = u[k], bq = v[k];
+      a.x *= g_scale; a.y *= g_scale; a.z *= g_scale; a.w *= g_scale; bq.x *= g_scale; bq.y *= g_scale; bq.z *= g_scale; bq.w *= g_scale;
+      split_store(gH + px_off(pix, hf), gL + px_off(pix, hf), a, bq);
+    }
+  }
+}
+
+// The MMA phase of one tile for one of 8 warps.  Work unit = half a tile row (two K steps of 16 pixels): 24 units, 3 per
+// warp.  The two accumulators of a tap form two independent HMMA chains (each still receives lo*hi, hi*lo, hi*hi in order).
+__device__ __forceinline__ void wgrad_mma_tile(float (&acc)[9][2][4], int warp, int lane, uint32_t aH, uint32_t aL, uint32_t gH, uint32_t gL) {
+  // ldmatrix.trans row addresses: lanes 0-7 / 8-15 / 16-23 / 24-31 give the rows of the four 8x8 matrices
+  //   (pixels 0-7, ch 0-7), (pixels 0-7, ch 8-15), (pixels 8-15, ch 0-7), (pixels 8-15, ch 8-15)
+  const int lp = (lane & 7) + ((lane >> 4) & 1) * 8, lh = (lane >> 3) & 1;
+  // for the B operand (G) the x4 order is (px 0-7, co 0-7), (px 8-15, co 0-7), (px 0-7, co 8-15), (px 8-15, co 8-15)
+  const int gp = (lane & 7) + ((lane >> 3) & 1) * 8, gh = (lane >> 4) & 1;
+  static_assert((RW / 16) % 2 == 0 && (WG_TH * 2) % 8 == 0, "units must divide evenly over the warps");
+  for (int u = warp; u < WG_TH * 2; u += 8) {
+    const int r = u >> 1;
+#pragma unroll 1
+    for (int ks = (u & 1) * (RW / 32); ks < ((u & 1) + 1) * (RW / 32); ++ks) {
+      uint32_t bh[4], bl[4];
+      const int gpix = r * RW + ks * 16 + gp;
+      ldsm4t(bh, gH + px_off(gpix, gh));
+      ldsm4t(bl, gL + px_off(gpix, gh));
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          uint32_t ah[4], al[4];
+          const int apix = (r + dy) * RW + ks * 16 + dx - 1 + lp;
+          ldsm4t(ah, aH + px_off(apix, lh));
+          ldsm4t(al, aL + px_off(apix, lh));
+          const int t = dy * 3 + dx;
+          // A fragment order of mma (a0: m 0-7 k 0-7, a1: m 8-15 k 0-7, a2: m 0-7 k 8-15, a3: m 8-15 k 8-15) == load order
+          mma16816(acc[t][0], al, make_uint2(bh[0], bh[1]));
+          mma16816(acc[t][1], al, make_uint2(bh[2], bh[3]));
+          mma16816(acc[t][0], ah, make_uint2(bl[0], bl[1]));
+          mma16816(acc[t][1], ah, make_uint2(bl[2], bl[3]));
+          mma16816(acc[t][0], ah, make_uint2(bh[0], bh[1]));
+          mma16816(acc[t][1], ah, make_uint2(bh[2], bh[3]));
+        }
+    }
+  }
+}
+
+// the 8 MMA warps' accumulators in fixed order through shared memory, then one partial per CTA
+__device__ __forceinline__ void wgrad_store_acc(const float (&acc)[9][2][4], int warp, int lane, uint8_t* smem) {
+  float* s_red = reinterpret_cast<float*>(smem);   // [8][2304]
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      float* d = s_red + warp * 2304 + t * C * C + nt * 8 + 2 * q;
+      d[g * C] = acc[t][nt][0]; d[g * C + 1] = acc[t][nt][1];
+      d[(g + 8) * C] = acc[t][nt][2]; d[(g + 8) * C + 1] = acc[t][nt][3];
+    }
+}
+template <int NTH>
+__device__ __forceinline__ void wgrad_sum_cta(int tid, const uint8_t* smem, float* __restrict__ partial, float out_scale) {
+  const float* s_red = reinterpret_cast<const float*>(smem);
+  float* dst = partial + (size_t)blockIdx.x * 2304;
+  for (int i = tid; i < 2304; i += NTH) {
+    float a = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) a += s_red[w8 * 2304 + i];
+    dst[i] = a * out_scale;
+  }
+}
+
+// the tap shifts read one pixel before / after the activation planes: those products meet a zero gradient, but
+// 0 * (NaN bit pattern left in shared memory) would still poison the sum, so the slack is zeroed once
+__device__ __forceinline__ void wgrad_zero_slack(int t /* 0 .. 63 */, uint32_t buf, int a_plane) {
+  const int pl = t / (4 * SLACK_PX), k = t % (4 * SLACK_PX);   // 16-byte chunks: 2 per pixel
+  const uint32_t base = buf + pl * a_plane;
+  const uint32_t off = k < 2 * SLACK_PX ? (uint32_t)k * 16u : (uint32_t)(a_plane - (4 * SLACK_PX - k) * 16);
+  sts128(base + off, make_uint4(0u, 0u, 0u, 0u));
+}
+
+constexpr int WG_A_PLANE = ((WG_TH + 2) * RW + 2 * SLACK_PX) * PX_BYTES, WG_G_PLANE = (WG_TH * RW + 2 * SLACK_PX) * PX_BYTES;
+constexpr int WG_BUF = 2 * WG_A_PLANE + 2 * WG_G_PLANE;   // hi + lo planes of A and of G: 108.5 KB
+
+// Version 1 (BFCNN_WGRAD_V1=1, kept for A/B): two 8-warp CTAs per SM, each stage / barrier / MMA / barrier per tile.
 __global__ void __launch_bounds__(NT, 2)
 wgrad3x3_x3_kernel(const float* __restrict__ A, const float* __restrict__ G, float* __restrict__ partial, int n, int h, int wd,
                    int tiles_x, int tiles_y, float g_scale, float out_scale) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int RH = WG_TH + 2;
-  constexpr int A_PLANE = (RH * RW + 2 * SLACK_PX) * PX_BYTES, G_PLANE = (WG_TH * RW + 2 * SLACK_PX) * PX_BYTES;
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
-  const uint32_t aH = s0 + SLACK_PX * PX_BYTES, aL = aH + A_PLANE;
-  const uint32_t gH = s0 + 2 * A_PLANE + SLACK_PX * PX_BYTES, gL = gH + G_PLANE;
+  const uint32_t aH = s0 + SLACK_PX * PX_BYTES, aL = aH + WG_A_PLANE;
+  const uint32_t gH = s0 + 2 * WG_A_PLANE + SLACK_PX * PX_BYTES, gL = gH + WG_G_PLANE;
   float acc[9][2][4];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
@@ -211,138 +350,77 @@ wgrad3x3_x3_kernel(const float* __restrict__ A, const float* __restrict__ G, flo
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[t][nt][k] = 0.f;
-  // ldmatrix.trans row addresses: lanes 0-7 / 8-15 / 16-23 / 24-31 give the rows of the four 8x8 matrices
-  //   (pixels 0-7, ch 0-7), (pixels 0-7, ch 8-15), (pixels 8-15, ch 0-7), (pixels 8-15, ch 8-15)
-  const int lp = (lane & 7) + ((lane >> 4) & 1) * 8, lh = (lane >> 3) & 1;
-  // for the B operand (G) the x4 order is (px 0-7, co 0-7), (px 8-15, co 0-7), (px 0-7, co 8-15), (px 8-15, co 8-15)
-  const int gp = (lane & 7) + ((lane >> 3) & 1) * 8, gh = (lane >> 4) & 1;
-
-  // the tap shifts read one pixel before / after the activation planes: those products meet a zero gradient, but
-  // 0 * (NaN bit pattern left in shared memory) would still poison the sum, so the slack is zeroed once
-  if (tid < 2 * 2 * SLACK_PX * 2) {
-    const int pl = tid / (4 * SLACK_PX), k = tid % (4 * SLACK_PX);   // 16-byte chunks: 2 per pixel
-    const uint32_t base = s0 + pl * A_PLANE;
-    const uint32_t off = k < 2 * SLACK_PX ? (uint32_t)k * 16u : (uint32_t)(A_PLANE - (4 * SLACK_PX - k) * 16);
-    sts128(base + off, make_uint4(0u, 0u, 0u, 0u));
-  }
+  if (tid < 2 * 2 * SLACK_PX * 2) wgrad_zero_slack(tid, s0, WG_A_PLANE);
   const int ntiles = tiles_x * tiles_y;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    // Tiles walk the VIRTUAL row of the batch: the n images side by side, one zero column between neighbours (it is the
-    // zero padding both of them see), so a 256-pixel-wide image does not pay for a fifth, nearly empty 62-column tile.
     const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const int oy = ty * WG_TH - 1, ox = tx * (RW - 2) - 1;
-    // a thread stages the same column and channel half in every iteration (NT / 2 is a multiple of RW)
-    static_assert((NT / 2) % RW == 0, "staging assumes a fixed column per thread");
-    const int c_t = (tid >> 1) % RW, hf_t = tid & 1;
-    const int vx = ox + c_t, vb = vx >= 0 ? vx / (wd + 1) : -1, gx_t = vx - vb * (wd + 1);
-    const bool col_ok = vb >= 0 && vb < n && gx_t < wd;
-    const long long col_off = col_ok ? (((long long)vb * h * wd + gx_t) * C + 8 * hf_t) : 0;
-    const float* a_b = A + col_off;
-    const float* g_b = G + col_off;
     __syncthreads();
-    // Staging in batches of 4 iterations: all global loads of a batch first, then the splits and shared-memory stores.
-    // (split_store is inline asm with a memory clobber, so a load placed after it cannot move above it: one load per
-    // iteration meant 13 serial global-load latencies per tile, most of the kernel's time.)
-    constexpr int SB = 4;
-    for (int i0 = tid; i0 < RH * RW * 2; i0 += NT * SB) {      // activations with the one-pixel halo
-      float4 u[SB], v[SB];
-#pragma unroll
-      for (int k = 0; k < SB; ++k) {
-        const int i = i0 + k * NT;
-        const int r = (i >> 1) / RW;
-        const int gy = oy + r;
-        u[k] = make_float4(0.f, 0.f, 0.f, 0.f); v[k] = u[k];
-        if (i < RH * RW * 2 && col_ok && gy >= 0 && gy < h) {
-          const float4* s = reinterpret_cast<const float4*>(a_b + (long long)gy * wd * C);
-          u[k] = s[0]; v[k] = s[1];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < SB; ++k) {
-        const int i = i0 + k * NT;
-        if (i >= RH * RW * 2) break;
-        const int hf = i & 1, pix = i >> 1;
-        float4 a = u[k], bq = v[k];
-        a.x *= 64.f; a.y *= 64.f; a.z *= 64.f; a.w *= 64.f; bq.x *= 64.f; bq.y *= 64.f; bq.z *= 64.f; bq.w *= 64.f;
-        split_store(aH + px_off(pix, hf), aL + px_off(pix, hf), a, bq);
-      }
-    }
-    for (int i0 = tid; i0 < WG_TH * RW * 2; i0 += NT * SB) {   // output gradients: zero on the halo columns and outside the image
-      float4 u[SB], v[SB];
-#pragma unroll
-      for (int k = 0; k < SB; ++k) {
-        const int i = i0 + k * NT;
-        const int r = (i >> 1) / RW;
-        const int gy = oy + 1 + r;
-        u[k] = make_float4(0.f, 0.f, 0.f, 0.f); v[k] = u[k];
-        if (i < WG_TH * RW * 2 && col_ok && c_t >= 1 && c_t < RW - 1 && gy < h) {
-          const float4* s = reinterpret_cast<const float4*>(g_b + (long long)gy * wd * C);
-          u[k] = s[0]; v[k] = s[1];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < SB; ++k) {
-        const int i = i0 + k * NT;
-        if (i >= WG_TH * RW * 2) break;
-        const int hf = i & 1, pix = i >> 1;
-        float4 a = u[k], bq = v[k];
-        a.x *= g_scale; a.y *= g_scale; a.z *= g_scale; a.w *= g_scale; bq.x *= g_scale; bq.y *= g_scale; bq.z *= g_scale; bq.w *= g_scale;
-        split_store(gH + px_off(pix, hf), gL + px_off(pix, hf), a, bq);
-      }
-    }
+    wgrad_stage_tile<NT, 4, 4>(tid, aH, aL, gH, gL, A, G, n, h, wd, ty * WG_TH - 1, tx * (RW - 2) - 1, g_scale);
     __syncthreads();
-    // work unit = half a tile row (two K steps of 16 pixels): 24 units over 8 warps, 3 each (whole rows: 2 / 2 / 2 / 2 / 1 / 1 / 1 / 1)
-    static_assert((RW / 16) % 2 == 0 && (WG_TH * 2) % (NT / 32) == 0, "units must divide evenly over the warps");
-    for (int u = warp; u < WG_TH * 2; u += NT / 32) {
-      const int r = u >> 1;
-#pragma unroll 1
-      for (int ks = (u & 1) * (RW / 32); ks < ((u & 1) + 1) * (RW / 32); ++ks) {
-        uint32_t bh[4], bl[4];
-        const int gpix = r * RW + ks * 16 + gp;
-        ldsm4t(bh, gH + px_off(gpix, gh));
-        ldsm4t(bl, gL + px_off(gpix, gh));
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            uint32_t ah[4], al[4];
-            const int apix = (r + dy) * RW + ks * 16 + dx - 1 + lp;
-            ldsm4t(ah, aH + px_off(apix, lh));
-            ldsm4t(al, aL + px_off(apix, lh));
-            const int t = dy * 3 + dx;
-            // A fragment order of mma (a0: m 0-7 k 0-7, a1: m 8-15 k 0-7, a2: m 0-7 k 8-15, a3: m 8-15 k 8-15) == load order
-            mma16816(acc[t][0], al, make_uint2(bh[0], bh[1]));
-            mma16816(acc[t][0], ah, make_uint2(bl[0], bl[1]));
-            mma16816(acc[t][0], ah, make_uint2(bh[0], bh[1]));
-            mma16816(acc[t][1], al, make_uint2(bh[2], bh[3]));
-            mma16816(acc[t][1], ah, make_uint2(bl[2], bl[3]));
-            mma16816(acc[t][1], ah, make_uint2(bh[2], bh[3]));
-          }
-      }
-    }
+    wgrad_mma_tile(acc, warp, lane, aH, aL, gH, gL);
   }
-  // ---- the 8 warps in fixed order through shared memory, then one partial per CTA
   __syncthreads();
-  float* s_red = reinterpret_cast<float*>(smem);   // [8][2304]
-  {
-    const int g = lane >> 2, q = lane & 3;
+  wgrad_store_acc(acc, warp, lane, smem);
+  __syncthreads();
+  wgrad_sum_cta<NT>(tid, smem, partial, out_scale);
+}
+
+// Version 2 (default): ONE 16-warp CTA per SM, warps 0-7 multiply, warps 8-15 stage the next tile into the other of two
+// shared-memory buffers, so global-load latency and the hi / lo split hide behind the MMAs of the previous tile instead of
+// alternating with them (ncu of version 1: tensor pipe 47 % active, half of the stall samples in the staging phase and at
+// its two barriers -- profiles/r01i_train_ncu.md).  Hand-over through named barriers: FULL[b] (256 loader arrivals +
+// 256 consumer waits), FREE[b] (the other way round, only when the CTA has another tile for that buffer).
+constexpr int WS_NT = 512;
+constexpr bool WGRAD_V1_DEFAULT = true;   // until the loader-warp kernel has passed tests/test_training_gpu.py on a B200
+__device__ __forceinline__ void nbar_sync(int id, int cnt) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(cnt) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int cnt) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(cnt) : "memory"); }
+
+__global__ void __launch_bounds__(WS_NT, 1)
+wgrad3x3_x3_ws_kernel(const float* __restrict__ A, const float* __restrict__ G, float* __restrict__ partial, int n, int h, int wd,
+                      int tiles_x, int tiles_y, float g_scale, float out_scale) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+  constexpr int BAR_FULL = 1, BAR_FREE = 3, BAR_MMA_WARPS = 5;
+  if (tid < 2 * (2 * 2 * SLACK_PX * 2)) wgrad_zero_slack(tid & 63, s0 + (tid >> 6) * WG_BUF, WG_A_PLANE);
+  __syncthreads();
+  const int ntiles = tiles_x * tiles_y;
+  if (warp < 8) {   // ---- consumers: the accumulators live in this branch only, the loaders keep their registers for loads
+    float acc[9][2][4];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        float* d = s_red + warp * 2304 + t * C * C + nt * 8 + 2 * q;
-        d[g * C] = acc[t][nt][0]; d[g * C + 1] = acc[t][nt][1];
-        d[(g + 8) * C] = acc[t][nt][2]; d[(g + 8) * C + 1] = acc[t][nt][3];
-      }
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[t][nt][k] = 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t sb = s0 + b * WG_BUF;
+      const uint32_t aH = sb + SLACK_PX * PX_BYTES, aL = aH + WG_A_PLANE;
+      const uint32_t gH = sb + 2 * WG_A_PLANE + SLACK_PX * PX_BYTES, gL = gH + WG_G_PLANE;
+      nbar_sync(BAR_FULL + b, WS_NT);
+      wgrad_mma_tile(acc, warp, lane, aH, aL, gH, gL);
+      if (tile + 2 * (int)gridDim.x < ntiles) nbar_arrive(BAR_FREE + b, WS_NT);   // the loaders may refill this buffer
+    }
+    nbar_sync(BAR_MMA_WARPS, WS_NT / 2);   // every consumer warp is done reading the tile buffers (all tiles are staged by then)
+    wgrad_store_acc(acc, warp, lane, smem);
+  } else {          // ---- loaders
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t sb = s0 + b * WG_BUF;
+      const uint32_t aH = sb + SLACK_PX * PX_BYTES, aL = aH + WG_A_PLANE;
+      const uint32_t gH = sb + 2 * WG_A_PLANE + SLACK_PX * PX_BYTES, gL = gH + WG_G_PLANE;
+      if (it >= 2) nbar_sync(BAR_FREE + b, WS_NT);
+      const int tx = tile % tiles_x, ty = tile / tiles_x;
+      wgrad_stage_tile<WS_NT / 2, 7, 6>(tid - WS_NT / 2, aH, aL, gH, gL, A, G, n, h, wd, ty * WG_TH - 1, tx * (RW - 2) - 1, g_scale);
+      __threadfence_block();
+      nbar_arrive(BAR_FULL + b, WS_NT);
+    }
   }
   __syncthreads();
-  float* dst = partial + (size_t)blockIdx.x * 2304;
-  for (int i = tid; i < 2304; i += NT) {
-    float a = 0.f;
-#pragma unroll
-    for (int w8 = 0; w8 < NT / 32; ++w8) a += s_red[w8 * 2304 + i];
-    dst[i] = a * out_scale;
-  }
+  wgrad_sum_cta<WS_NT>(tid, smem, partial, out_scale);
 }
 
 }  // namespace x3
@@ -385,22 +463,27 @@ int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float*
 int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, float* partial, int max_parts, const Extent& e,
                        float g_scale, int* parts_out, cudaStream_t st) {
   using namespace x3;
-  constexpr int RH = WG_TH + 2;
-  const size_t smem = (size_t)2 * (RH * RW + 2 * SLACK_PX) * PX_BYTES + (size_t)2 * (WG_TH * RW + 2 * SLACK_PX) * PX_BYTES;
+  const char* v1s = getenv("BFCNN_WGRAD_V1");
+  const bool v1 = v1s ? atoi(v1s) != 0 : WGRAD_V1_DEFAULT;   // 1: the two-CTA kernel, 0: the loader-warp kernel
+  const size_t smem = (size_t)WG_BUF * (v1 ? 1 : 2);
   static bool attr_set = false;
   if (!attr_set) {
-    BF_CUDA(cudaFuncSetAttribute((const void*)wgrad3x3_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BF_CUDA(cudaFuncSetAttribute((const void*)wgrad3x3_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_BUF));
+    BF_CUDA(cudaFuncSetAttribute((const void*)wgrad3x3_x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * WG_BUF));
     attr_set = true;
   }
-  static_assert((size_t)8 * 2304 * 4 <= (size_t)2 * ((WG_TH + 2) * RW + 2 * SLACK_PX) * PX_BYTES + (size_t)2 * (WG_TH * RW + 2 * SLACK_PX) * PX_BYTES,
-                "cross-warp reduction buffer does not fit");
+  static_assert((size_t)8 * 2304 * 4 <= (size_t)WG_BUF, "cross-warp reduction buffer does not fit");
+  static_assert(2 * WG_BUF <= 232448, "two tile buffers do not fit in shared memory");
   const long long vcols = (long long)e.n * (e.we + 1) - 1;   // virtual row: the images side by side, a zero column between them
   BF_REQUIRE(vcols < (1ll << 30), "batch too wide for the virtual row");
   const int tiles_x = (int)((vcols + (RW - 2) - 1) / (RW - 2)), tiles_y = (e.he + WG_TH - 1) / WG_TH;
   const long long ntiles = (long long)tiles_x * tiles_y;
-  BF_REQUIRE(ntiles < (1ll << 31), "too many tiles");
-  const int grid = (int)std::min<long long>(ntiles, std::min(max_parts, 2 * h->sm_count));
-  wgrad3x3_x3_kernel<<<grid, NT, smem, st>>>(act, grad, partial, e.n, e.he, e.we, tiles_x, tiles_y, g_scale, 1.0f / (64.f * g_scale));
+  BF_REQUIRE(ntiles < (1ll << 30), "too many tiles");
+  const int grid = (int)std::min<long long>(ntiles, std::min(max_parts, (v1 ? 2 : 1) * h->sm_count));
+  if (v1)
+    wgrad3x3_x3_kernel<<<grid, NT, smem, st>>>(act, grad, partial, e.n, e.he, e.we, tiles_x, tiles_y, g_scale, 1.0f / (64.f * g_scale));
+  else
+    wgrad3x3_x3_ws_kernel<<<grid, WS_NT, smem, st>>>(act, grad, partial, e.n, e.he, e.we, tiles_x, tiles_y, g_scale, 1.0f / (64.f * g_scale));
   h->launches++;
   BF_CUDA(cudaGetLastError());
   *parts_out = grid;
