@@ -371,7 +371,7 @@ wgrad3x3_x3_kernel(const float* __restrict__ A, const float* __restrict__ G, flo
 // its two barriers -- profiles/r01i_train_ncu.md).  Hand-over through named barriers: FULL[b] (256 loader arrivals +
 // 256 consumer waits), FREE[b] (the other way round, only when the CTA has another tile for that buffer).
 constexpr int WS_NT = 512;
-constexpr bool WGRAD_V1_DEFAULT = true;   // until the loader-warp kernel has passed tests/test_training_gpu.py on a B200
+constexpr bool WGRAD_V1_DEFAULT = false;  // BFCNN_WGRAD_V1=1 selects the two-CTA kernel (A/B: tools/check_wgrad.py)
 __device__ __forceinline__ void nbar_sync(int id, int cnt) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(cnt) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int cnt) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(cnt) : "memory"); }
 
