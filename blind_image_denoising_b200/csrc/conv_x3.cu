@@ -276,23 +276,28 @@ __device__ __forceinline__ void wgrad_mma_tile(float (&acc)[9][2][4], int warp, 
       const int gpix = r * RW + ks * 16 + gp;
       ldsm4t(bh, gH + px_off(gpix, gh));
       ldsm4t(bl, gL + px_off(gpix, gh));
+      // the fragments of tap t + 1 are requested before the MMAs of tap t are issued (the asm statements keep their order, so
+      // without this every group of six MMAs waited for its own ldmatrix: "short scoreboard" was the top HMMA stall)
+      uint32_t ah[2][4], al[2][4];
+      const int apix0 = r * RW + ks * 16 - 1 + lp;
+      ldsm4t(ah[0], aH + px_off(apix0, lh));
+      ldsm4t(al[0], aL + px_off(apix0, lh));
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          uint32_t ah[4], al[4];
-          const int apix = (r + dy) * RW + ks * 16 + dx - 1 + lp;
-          ldsm4t(ah, aH + px_off(apix, lh));
-          ldsm4t(al, aL + px_off(apix, lh));
-          const int t = dy * 3 + dx;
-          // A fragment order of mma (a0: m 0-7 k 0-7, a1: m 8-15 k 0-7, a2: m 0-7 k 8-15, a3: m 8-15 k 8-15) == load order
-          mma16816(acc[t][0], al, make_uint2(bh[0], bh[1]));
-          mma16816(acc[t][1], al, make_uint2(bh[2], bh[3]));
-          mma16816(acc[t][0], ah, make_uint2(bl[0], bl[1]));
-          mma16816(acc[t][1], ah, make_uint2(bl[2], bl[3]));
-          mma16816(acc[t][0], ah, make_uint2(bh[0], bh[1]));
-          mma16816(acc[t][1], ah, make_uint2(bh[2], bh[3]));
+      for (int t = 0; t < 9; ++t) {
+        const int cur = t & 1, nxt = cur ^ 1;
+        if (t + 1 < 9) {
+          const int apix = (r + (t + 1) / 3) * RW + ks * 16 + (t + 1) % 3 - 1 + lp;
+          ldsm4t(ah[nxt], aH + px_off(apix, lh));
+          ldsm4t(al[nxt], aL + px_off(apix, lh));
         }
+        // A fragment order of mma (a0: m 0-7 k 0-7, a1: m 8-15 k 0-7, a2: m 0-7 k 8-15, a3: m 8-15 k 8-15) == load order
+        mma16816(acc[t][0], al[cur], make_uint2(bh[0], bh[1]));
+        mma16816(acc[t][1], al[cur], make_uint2(bh[2], bh[3]));
+        mma16816(acc[t][0], ah[cur], make_uint2(bl[0], bl[1]));
+        mma16816(acc[t][1], ah[cur], make_uint2(bl[2], bl[3]));
+        mma16816(acc[t][0], ah[cur], make_uint2(bh[0], bh[1]));
+        mma16816(acc[t][1], ah[cur], make_uint2(bh[2], bh[3]));
+      }
     }
   }
 }
