@@ -3,7 +3,8 @@
 // Same pipeline (column strips streamed top to bottom, layer l+1 trailing layer l by LAG = 3 row groups, rings in shared
 // memory, the 32 TMEM blocks as one ring, barrier-helper warp, per-layer mma_done), with activations and weights split into
 // fp16 hi + lo parts: every product is issued as lo*hi + hi*lo + hi*hi (9 MMAs per row and conv), the rings carry both
-// parts (four channel-half planes), the feature map between passes carries both parts (lo images after the hi images).
+// parts (four channel-half planes), the feature map between passes carries both parts (the virtual-row map of
+// fused_stream.cu twice: the lo map behind the hi map, a second "image" to the tensor map).
 // One residual block (two convs) per pass: the rings of two blocks with both parts do not fit in shared memory.
 // It replaces the region kernel of fused_umma_x3.cu as the engine of precision "f16x3" (BFCNN_X3_REGIONS=1 selects the
 // region kernel); kept in its own translation unit so that the F16 kernel's code generation is untouched.
