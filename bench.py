@@ -295,7 +295,11 @@ def main():
     if os.path.exists(prof):
         try:
             with open(prof) as f:
-                roofline["traffic"] = json.load(f).get(args.precision)
+                per_frame = json.load(f).get(args.precision)   # ncu --set full capture of a ONE-frame launch
+            if per_frame is not None:   # the feature map goes once in and once out per pass: linear in the frames of a launch
+                roofline["traffic"] = per_frame * F
+                roofline["traffic_note"] = (f"dram bytes read + written per launch = {per_frame} B measured by ncu on a 1-frame launch "
+                                            f"x {F} frames per launch (algorithmic: {F * 2160 * 3840 * 64} B, the fp16 NHWC16 map in and out)")
         except Exception:
             pass
 
