@@ -225,7 +225,8 @@ conv3x3_c16_kernel(const float* __restrict__ in, float* __restrict__ out,
 
 int launch_conv3x3_f32(bfcnn_handle* h, const float* in, float* out, const float* w, const float* bias,
                        const float* res, double* stats, ConvEpi epi, const Extent& e, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
+  bool& attr_set = attr_set_dev[h->device & 63];
   auto set_attr = [](const void* f) {
     return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM);
   };

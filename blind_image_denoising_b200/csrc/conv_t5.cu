@@ -369,7 +369,8 @@ int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float*
                       ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st) {
   using namespace t5;
   BF_REQUIRE(in_scale > 0.f, "in_scale must be a positive power of two");
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
+  bool& attr_set = attr_set_dev[h->device & 63];
   if (!attr_set) {
     BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

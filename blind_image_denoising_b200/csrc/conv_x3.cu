@@ -437,7 +437,8 @@ int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float*
   const int th = (e.he + tiles_y - 1) / tiles_y;
   const int tiles_x = (e.we + (RW - 2) - 1) / (RW - 2);
   const size_t smem = (size_t)2 * ((th + 2) * RW + 2 * SLACK_PX) * PX_BYTES;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
+  bool& attr_set = attr_set_dev[h->device & 63];
   if (!attr_set) {
     const int mx = 2 * ((TH_MAX + 2) * RW + 2 * SLACK_PX) * PX_BYTES;
     BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_x3_kernel<CONV_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -471,7 +472,8 @@ int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, flo
   const char* v1s = getenv("BFCNN_WGRAD_V1");
   const bool v1 = v1s ? atoi(v1s) != 0 : WGRAD_V1_DEFAULT;   // 1: the two-CTA kernel, 0: the loader-warp kernel
   const size_t smem = (size_t)WG_BUF * (v1 ? 1 : 2);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
+  bool& attr_set = attr_set_dev[h->device & 63];
   if (!attr_set) {
     BF_CUDA(cudaFuncSetAttribute((const void*)wgrad3x3_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_BUF));
     BF_CUDA(cudaFuncSetAttribute((const void*)wgrad3x3_x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * WG_BUF));

@@ -577,7 +577,8 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
   using namespace ustream;
   const int N = h->arch.no_layers;
   BF_REQUIRE(N >= 1, "the fused tensor-core stack needs no_layers >= 1 (use BFCNN_PREC_FP32)");
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
+  bool& attr_set = attr_set_dev[h->device & 63];
   if (!attr_set) {
     BF_CUDA(cudaFuncSetAttribute((const void*)stream_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     BF_CUDA(cudaFuncSetAttribute((const void*)stream_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));

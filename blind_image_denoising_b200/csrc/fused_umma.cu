@@ -683,7 +683,8 @@ int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool
     set_error("the fused tensor-core stack needs no_layers >= 1 (use BFCNN_PREC_FP32)");
     return BFCNN_ERR_UNSUPPORTED;
   }
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
+  bool& attr_set = attr_set_dev[h->device & 63];
   if (!attr_set) {
     BF_CUDA(cudaFuncSetAttribute((const void*)umma_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     BF_CUDA(cudaFuncSetAttribute((const void*)umma_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));

@@ -768,7 +768,8 @@ int run_fused_stack_umma_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, b
     set_error("the fused tensor-core stack needs no_layers >= 1 (use BFCNN_PREC_FP32)");
     return BFCNN_ERR_UNSUPPORTED;
   }
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
+  bool& attr_set = attr_set_dev[h->device & 63];
   if (!attr_set) {
     BF_CUDA(cudaFuncSetAttribute((const void*)umma_pass_kernel<false, 2, GROUP_X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     BF_CUDA(cudaFuncSetAttribute((const void*)umma_pass_kernel<true, 2, GROUP_X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));

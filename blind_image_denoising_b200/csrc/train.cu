@@ -937,7 +937,8 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   const size_t map_floats = npx * C;
   const long long n4 = (long long)(map_floats / 4);
   const double cnt = (double)npx;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
+  bool& attr_set = attr_set_dev[h->device & 63];
   if (!attr_set) {
     BF_CUDA(cudaFuncSetAttribute((const void*)wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
     BF_CUDA(cudaFuncSetAttribute((const void*)wgrad_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
