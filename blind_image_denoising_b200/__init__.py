@@ -18,8 +18,13 @@ from . import _native
 from .arch import (Arch, arch_from_config, arch_from_name, arch_from_variable_shapes,
                    default_pipeline_config)
 from .denoiser import Denoiser, PipelinedDenoiser
+from .model import BuilderResults, model_builder
+from .optimizer import deep_supervision_schedule_builder, optimizer_builder, schedule_builder
 from .tensorbundle import read_model_variables, write_model_variables
-from .weights import synthetic_variables
+from .train_loop import create_checkpoint, train_loop
+from .training import (DatasetResults, Trainer, dataset_builder, load_image, loss_function_builder,
+                       trainer_from_config)
+from .weights import initial_variables, synthetic_variables
 
 __version__ = "0.1.0"
 DENOISER_STR = "denoiser"  # reference bfcnn/constants.py (DENOISER_STR)
@@ -78,10 +83,20 @@ def _build_denoiser(path, name: str = "", **kwargs) -> Denoiser:
     variables = load_variables(path)
     arch = arch_from_variable_shapes([v.shape for v in variables])
     cfg_path = _find_config(path if path.is_dir() else path.parent)
+    allow_synthetic = bool(kwargs.pop("allow_synthetic", False))
     if cfg_path is not None:
-        cfg_arch = arch_from_config(load_config(cfg_path))
+        cfg = load_config(cfg_path)
+        cfg_arch = arch_from_config(cfg)
         if cfg_arch != arch:
             raise ValueError(f"pipeline.json describes {cfg_arch} but the checkpoint holds {arch}")
+        marker = str(cfg.get("weights", ""))
+        if marker.upper().startswith("SYNTHETIC") and not allow_synthetic:
+            # the reference snapshot ships no resnet blobs: the directories under pretrained/ hold seed-0
+            # random weights of the right shapes -- say so at every load instead of pretending to denoise
+            import warnings
+            warnings.warn(f"model [{name or path}] holds SYNTHETIC (random, untrained) weights: {marker}. It reproduces the "
+                          "reference arithmetic but does not denoise; copy real `saved_model/variables/` files over "
+                          f"[{path}] or pass allow_synthetic=True to silence this.", UserWarning, stacklevel=3)
     return Denoiser(arch, variables, name=name, **kwargs)
 
 
@@ -107,7 +122,8 @@ def load_model(model_path: str, **kwargs) -> Denoiser:
     """reference bfcnn/__init__.py:81-97 (same argument checks and messages).
 
     Returns a callable mapping uint8 [N,H,W,3] to the denoised uint8 tensor.
-    Keyword-only extras: device=0, precision="f16x3"|"f16"|"fp32", pad_pow2=True."""
+    Keyword-only extras: device=0, precision="f16x3"|"f16"|"fp32", pad_pow2=True, allow_synthetic=False (the shipped
+    model directories hold synthetic weights, SURVEY F2: loading them warns unless this is set)."""
     if model_path is None or len(model_path) <= 0:
         raise ValueError("model_path cannot be empty")
     if model_path in models:
@@ -136,9 +152,13 @@ def synthetic_model(no_layers: int, seed: int = 0, **kwargs) -> Denoiser:
     return Denoiser(arch, synthetic_variables(arch, seed), name=f"synthetic_1x{no_layers}", **kwargs)
 
 
+# reference bfcnn/__init__.py:129-143 (__all__) for the hot path, plus this package's own names
 __all__ = [
-    "models", "configs", "CONFIGS_DICT", "load_model", "load_denoiser_model",
-    "load_default_denoiser", "load_config", "load_variables", "synthetic_model", "Denoiser", "PipelinedDenoiser", "Arch",
-    "arch_from_config", "arch_from_name", "default_pipeline_config", "synthetic_variables",
+    "models", "configs", "CONFIGS_DICT", "train_loop", "load_model", "load_image", "model_builder", "schedule_builder",
+    "optimizer_builder", "load_denoiser_model", "load_default_denoiser", "load_config",
+    "dataset_builder", "loss_function_builder", "deep_supervision_schedule_builder", "create_checkpoint",
+    "BuilderResults", "DatasetResults", "Trainer", "trainer_from_config",
+    "load_variables", "synthetic_model", "Denoiser", "PipelinedDenoiser", "Arch",
+    "arch_from_config", "arch_from_name", "default_pipeline_config", "synthetic_variables", "initial_variables",
     "read_model_variables", "write_model_variables",
 ]

@@ -15,17 +15,19 @@ from .arch import CArch
 _LIB_PATH = Path(__file__).resolve().parent / "libbfcnn_b200.so"
 
 PREC_FP32, PREC_F16, PREC_F16X3, PREC_F16_MMA_SYNC, PREC_F16X3_MMA_SYNC = 0, 1, 2, 3, 4
-PRECISIONS = {"fp32": PREC_FP32, "f16": PREC_F16, "fp16": PREC_F16, "bf16": PREC_F16,
+# no "bf16" alias: the tensor-core arm computes with fp16 operands (10 mantissa bits, not bf16's 7)
+PRECISIONS = {"fp32": PREC_FP32, "f16": PREC_F16, "fp16": PREC_F16,
               "f16x3": PREC_F16X3, "fp16x3": PREC_F16X3, "f16_mma_sync": PREC_F16_MMA_SYNC,
               "f16x3_mma_sync": PREC_F16X3_MMA_SYNC}
-FLAG_IN_DEVICE, FLAG_OUT_DEVICE, FLAG_NO_PAD_POW2 = 1, 2, 4
+FLAG_IN_DEVICE, FLAG_OUT_DEVICE, FLAG_NO_PAD_POW2, FLAG_IN_F32 = 1, 2, 4, 8
 
 # every symbol include/bfcnn_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "bfcnn_abi_version", "bfcnn_last_error", "bfcnn_device_count", "bfcnn_num_weights",
     "bfcnn_num_trainable", "bfcnn_create", "bfcnn_destroy", "bfcnn_set_weights",
     "bfcnn_get_weights", "bfcnn_denoise_u8", "bfcnn_denoise_f32", "bfcnn_launch_count",
-    "bfcnn_last_stack_ms", "bfcnn_corrupt", "bfcnn_loss", "bfcnn_train_step", "bfcnn_adam_step", "bfcnn_conv3x3", "bfcnn_set_train_engine",
+    "bfcnn_last_stack_ms", "bfcnn_corrupt", "bfcnn_loss", "bfcnn_train_step", "bfcnn_train_losses", "bfcnn_saved_activation", "bfcnn_downscale2x",
+    "bfcnn_adam_step", "bfcnn_conv3x3", "bfcnn_set_train_engine",
 ]
 
 
@@ -33,7 +35,7 @@ class NoiseCfg(ctypes.Structure):
     _fields_ = [("additive_min", c_float), ("additive_max", c_float),
                 ("multiplicative_min", c_float), ("multiplicative_max", c_float),
                 ("random_left_right", c_int32), ("random_up_down", c_int32),
-                ("subsample", c_int32), ("round_values", c_int32)]
+                ("subsample", c_int32), ("round_values", c_int32), ("draw_group", c_int32)]
 
 
 class LossCfg(ctypes.Structure):
@@ -99,15 +101,21 @@ def load_library() -> ctypes.CDLL:
                                POINTER(c_float), c_void_p]
     lib.bfcnn_loss.restype = c_int
     lib.bfcnn_train_step.argtypes = [H, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(LossCfg),
-                                     c_void_p, POINTER(c_float), c_int, c_void_p]
+                                     c_void_p, c_void_p, c_int, c_void_p]
     lib.bfcnn_train_step.restype = c_int
+    lib.bfcnn_downscale2x.argtypes = [H, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.bfcnn_downscale2x.restype = c_int
+    lib.bfcnn_train_losses.argtypes = [H, POINTER(c_float), c_void_p]
+    lib.bfcnn_train_losses.restype = c_int
+    lib.bfcnn_saved_activation.argtypes = [H, c_int, c_int, c_void_p, c_void_p]
+    lib.bfcnn_saved_activation.restype = c_int
     lib.bfcnn_set_train_engine.argtypes = [H, c_int]
     lib.bfcnn_set_train_engine.restype = c_int
     lib.bfcnn_conv3x3.argtypes = [H, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.bfcnn_conv3x3.restype = c_int
     lib.bfcnn_adam_step.argtypes = [H, c_void_p, c_float, POINTER(AdamCfg), c_int64, c_void_p]
     lib.bfcnn_adam_step.restype = c_int
-    if lib.bfcnn_abi_version() != 2:
+    if lib.bfcnn_abi_version() != 3:
         raise ImportError("libbfcnn_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -156,6 +156,43 @@ def arch_from_config(config: Dict) -> Arch:
         raise ValueError("bias terms are not on the hot path (bias-free models only)")
     if not bb.get("use_bn", True):
         raise ValueError("use_bn=False is not on the hot path")
+    # Keys that change the arithmetic the kernels hard-code.  Most of them leave every variable SHAPE unchanged, so the
+    # checkpoint/shape cross-check of load_model cannot catch them: reject anything but the reference defaults
+    # (backbone_resnet.py:19-49, model.py:267-275) instead of computing something else silently.
+    def _same(v, allowed):
+        return (v.strip().lower() if isinstance(v, str) else v) in allowed
+
+    def _need(section, cfg, key, allowed, default):
+        v = cfg.get(key, default)
+        if not _same(v, allowed):
+            raise ValueError(f"{section} option {key}={v!r} is not on the hot path (the kernels implement {sorted(map(str, allowed))[0]!s})")
+
+    _need("backbone", bb, "activation", {"relu"}, "relu")                  # ReLU after conv_a (backbone_blocks.py:174-178)
+    _need("backbone", bb, "base_activation", {"linear"}, "linear")         # base conv and block outputs are linear (:178)
+    _need("backbone", bb, "kernel_regularizer", {"l1"}, "l1")              # train.cu: L1(0.01) on every backbone kernel
+    _need("backbone", bb, "dropout_rate", {-1, -1.0}, -1)
+    _need("backbone", bb, "add_gradient_dropout", {False}, False)
+    v = bb.get("block_activation", None)   # the last entry is overridden by base_activation (backbone_resnet.py:178)
+    if v and (len(v) != len(bk) or [str(a).strip().lower() for a in v[:-1]] != ["relu"] * (len(bk) - 1)):
+        raise ValueError(f"backbone option block_activation={v!r} is not on the hot path")
+    v = bb.get("block_regularizer", None)
+    if v and [str(a).strip().lower() for a in v] != ["l1"] * len(bk):
+        raise ValueError(f"backbone option block_regularizer={v!r} is not on the hot path")
+    v = bb.get("block_groups", None)
+    if v and list(v) != [1] * len(bk):
+        raise ValueError(f"backbone option block_groups={v!r} is not on the hot path")
+    v = bb.get("block_depthwise", None)
+    if v and list(v) != [-1] * len(bk):
+        raise ValueError(f"backbone option block_depthwise={v!r} is not on the hot path")
+    if bb.get("selector_params", None):
+        raise ValueError("backbone option selector_params is not on the hot path")
+    if list(bb.get("value_range", [0, 255])) != [0, 255]:
+        raise ValueError("backbone option value_range must be [0, 255] (the normaliser is fused into the base conv)")
+    # denoiser head (model.py:267-275): two LINEAR 1x1 convs without normalisation collapse into one [16,3] matrix
+    _need("denoiser", dn, "activation", {"linear"}, "linear")
+    _need("denoiser", dn, "kernel_regularizer", {"l2"}, "l2")              # train.cu: L2(0.01) on the head kernels
+    _need("denoiser", dn, "use_bn", {False}, False)
+    _need("denoiser", dn, "use_ln", {False}, False)
     ishape = bb.get("input_shape", ["?", "?", 3])
     return Arch(no_layers=int(bb["no_layers"]),
                 base_kernel=int(bb.get("kernel_size", 3)),

@@ -47,14 +47,14 @@ int check_images(int n, int height, int width) {
 }
 
 // the conv stack of one batch (device pointers)
-int run_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e, int precision, cudaStream_t st) {
+int run_stack(bfcnn_handle* h, const uint8_t* d_in, bool in_u8, void* d_out, bool out_u8, const Extent& e, int precision, cudaStream_t st) {
   if (precision == BFCNN_PREC_FP32) {
     const size_t feat = (size_t)e.n * e.he * e.we * C * sizeof(float);
     BF_CHECK(h->ws_feat[0].reserve(feat));
     BF_CHECK(h->ws_feat[1].reserve(feat));
     float* X = h->ws_feat[0].as<float>();
     float* T = h->ws_feat[1].as<float>();
-    BF_CHECK(launch_base_conv(h, d_in, true, X, h->d_base_f32.as<float>(), e, st));
+    BF_CHECK(launch_base_conv(h, d_in, in_u8, X, h->d_base_f32.as<float>(), e, st));
     for (int i = 0; i < h->arch.no_layers; ++i) {
       const float* wa = h->d_conv_f32.as<float>() + (size_t)(2 * i) * 9 * C * C;
       const float* wb = h->d_conv_f32.as<float>() + (size_t)(2 * i + 1) * 9 * C * C;
@@ -78,11 +78,16 @@ int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int
              "unknown precision");
   const size_t npx = (size_t)n * height * width;
   if (npx == 0) return BFCNN_OK;  // empty batch / empty image: nothing to do
+  // float32 input (the hydra model's own signature, model.py:100-102: the normaliser clips to [0,255]) runs on the
+  // reference-grade FP32 path only: the tensor-core stacks rely on uint8 pixels being exact in fp16
+  const bool in_u8 = !(flags & BFCNN_FLAG_IN_F32);
+  BF_REQUIRE(in_u8 || precision == BFCNN_PREC_FP32, "float32 input needs precision BFCNN_PREC_FP32");
+  const size_t isz = in_u8 ? 1 : sizeof(float);
   BF_REQUIRE(in != nullptr && out != nullptr, "in/out is NULL");
   BF_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t px_img = (size_t)height * width;
-  const size_t in_bytes = npx * 3, osz = out_u8 ? 1 : sizeof(float), out_bytes = npx * 3 * osz;
+  const size_t in_bytes = npx * 3 * isz, osz = out_u8 ? 1 : sizeof(float), out_bytes = npx * 3 * osz;
   if (!h->packed_valid) {
     // a training / optimiser step changed the variables on the device: fold and pack them again
     BF_CUDA(cudaDeviceSynchronize());
@@ -122,18 +127,18 @@ int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int
   BF_CUDA(cudaEventRecord(h->ev0, st));
   for (int c = 0; c < chunks; ++c) {
     const int i0 = c * per_chunk, nc = std::min(per_chunk, n - i0);
-    const size_t off_in = (size_t)i0 * px_img * 3, off_out = off_in * osz;
-    const size_t cin = (size_t)nc * px_img * 3, cout = cin * osz;
+    const size_t off_px = (size_t)i0 * px_img * 3, off_in = off_px * isz, off_out = off_px * osz;
+    const size_t cin = (size_t)nc * px_img * 3 * isz, cout = (size_t)nc * px_img * 3 * osz;
     if (in_host) {
       cudaStream_t sc = chunks > 1 ? h->s_h2d : st;
-      BF_CUDA(cudaMemcpyAsync(h->ws_in.as<uint8_t>() + off_in, in + off_in, cin, cudaMemcpyHostToDevice, sc));
+      BF_CUDA(cudaMemcpyAsync(h->ws_in.as<uint8_t>() + off_in, reinterpret_cast<const uint8_t*>(in) + off_in, cin, cudaMemcpyHostToDevice, sc));
       if (chunks > 1) {
         BF_CUDA(cudaEventRecord(h->ev_pool[2 * c], sc));
         BF_CUDA(cudaStreamWaitEvent(st, h->ev_pool[2 * c], 0));
       }
     }
     const Extent e = make_extent(h, nc, height, width, flags);
-    BF_CHECK(run_stack(h, d_in + off_in, d_out + off_out, out_u8, e, precision, st));
+    BF_CHECK(run_stack(h, d_in + off_in, in_u8, d_out + off_out, out_u8, e, precision, st));
     if (out_host) {
       cudaStream_t sc = chunks > 1 ? h->s_d2h : st;
       if (chunks > 1) {
@@ -146,8 +151,16 @@ int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int
   BF_CUDA(cudaEventRecord(h->ev1, st));
   h->ev_valid = true;
   if (out_host) {
-    if (chunks > 1) BF_CUDA(cudaStreamSynchronize(h->s_d2h));
-    BF_CUDA(cudaStreamSynchronize(st));
+    // Wait for the result with a BLOCKING event: cudaStreamSynchronize spins, and with one spinning worker thread per
+    // model instance and rank (PipelinedDenoiser: two per GPU) eight ranks keep sixteen host cores busy doing nothing
+    // while the threads that have to issue the next copies wait for a core.
+    if (!h->ev_done) BF_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
+    if (chunks > 1) {
+      BF_CUDA(cudaEventRecord(h->ev_done, h->s_d2h));
+      BF_CUDA(cudaEventSynchronize(h->ev_done));
+    }
+    BF_CUDA(cudaEventRecord(h->ev_done, st));
+    BF_CUDA(cudaEventSynchronize(h->ev_done));
   }
   return BFCNN_OK;
 }
@@ -238,6 +251,8 @@ void bfcnn_destroy(bfcnn_handle* h) {
   if (h->s_compute) cudaStreamDestroy(h->s_compute);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
+  h->d_train_tables.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -316,7 +331,7 @@ int bfcnn_loss(bfcnn_handle* h, const float* gt, const float* pred, int n, int h
 int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int n, int height, int width,
                      const bfcnn_loss_cfg* cfg, float* flat_grads, float* losses4, int update_moving,
                      void* stream) {
-  BF_REQUIRE(h != nullptr && cfg != nullptr && losses4 != nullptr, "NULL argument");
+  BF_REQUIRE(h != nullptr && cfg != nullptr, "NULL argument");   // losses4 may be NULL: asynchronous step
   BF_CHECK(check_images(n, height, width));
   BF_REQUIRE((size_t)n * height * width > 0, "train step on an empty batch is undefined");
   BF_REQUIRE(clean != nullptr && noisy != nullptr && flat_grads != nullptr, "NULL pointer");
@@ -324,6 +339,28 @@ int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, in
   BF_CUDA(cudaSetDevice(h->device));
   return run_train_step(h, clean, noisy, n, height, width, cfg, flat_grads, losses4, update_moving,
                         (cudaStream_t)stream);
+}
+
+int bfcnn_downscale2x(bfcnn_handle* h, const float* in, float* out, int n, int height, int width, int clip_values,
+                      int round_values, void* stream) {
+  BF_REQUIRE(h != nullptr, "handle is NULL");
+  BF_CHECK(check_images(n, height, width));
+  if ((size_t)n * (height / 2) * (width / 2) == 0) return BFCNN_OK;
+  BF_REQUIRE(in != nullptr && out != nullptr, "NULL image pointer");
+  BF_CUDA(cudaSetDevice(h->device));
+  return run_downscale2x(h, in, out, n, height, width, clip_values, round_values, (cudaStream_t)stream);
+}
+
+int bfcnn_train_losses(bfcnn_handle* h, float* losses5, void* stream) {
+  BF_REQUIRE(h != nullptr && losses5 != nullptr, "NULL argument");
+  BF_CUDA(cudaSetDevice(h->device));
+  return run_train_losses(h, losses5, (cudaStream_t)stream);
+}
+
+int bfcnn_saved_activation(bfcnn_handle* h, int which, int index, float* out, void* stream) {
+  BF_REQUIRE(h != nullptr && out != nullptr, "NULL argument");
+  BF_CUDA(cudaSetDevice(h->device));
+  return run_saved_activation(h, which, index, out, (cudaStream_t)stream);
 }
 
 int bfcnn_set_train_engine(bfcnn_handle* h, int engine) {

@@ -99,9 +99,13 @@ struct bfcnn_handle {
   bfcnn::DevBuf ws_grads;               // scratch gradients
   bfcnn::DevBuf adam_m, adam_v;         // Adam moments over the trainable vector
 
+  bfcnn::DevBuf d_train_tables;         // conv offsets / regulariser segments of the training step (uploaded once)
+  int tr_n = 0, tr_h = 0, tr_w = 0;     // shape of the last training step (its saved activations sit in ws_train)
+  size_t tr_out5_off = 0;               // byte offset of the last step's five loss scalars inside ws_stats
   int train_engine = 2;   // convs of the training step: 2 = tcgen05, fp16 hi/lo split (conv_t5.cu), 1 = the same on mma.sync (conv_x3.cu), 0 = FP32 FFMA
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_done = nullptr;                   // blocking-sync event: host-buffer calls sleep on it instead of spinning
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the host-buffer pipeline (api.cu)
   cudaStream_t s_compute = nullptr;               // compute stream of host-to-host calls without a caller stream (api.cu)
   std::vector<cudaEvent_t> ev_pool;

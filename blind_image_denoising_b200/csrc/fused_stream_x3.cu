@@ -571,9 +571,14 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
     p.out_u8 = out_u8 ? 1 : 0;
     const int nl = 2;
     p.tw = RW - 2 * nl;
-    p.rows_needed = last ? e.h : e.he;
+    // Rows / columns this pass has to produce: the layers that are still to come (rem) shrink the cone of influence by one
+    // pixel each, so beyond h + rem (w + rem) nothing can reach the cropped output any more (the band of the
+    // pow2 canvas is only as wide as the receptive field that is LEFT).  What lies beyond keeps stale values: never read
+    // by a valid output.
+    const int rem = 2 * (N - p.blk0 - p.nblk);
+    p.rows_needed = std::min(e.he, e.h + rem);
     // columns of the virtual row that need an output: up to the last needed column of the last image
-    const long long cols_needed = (long long)(e.n - 1) * (e.we + 1) + (last ? e.w : e.we);
+    const long long cols_needed = (long long)(e.n - 1) * (e.we + 1) + std::min(e.we, e.w + rem);
     p.tiles_x = (int)((cols_needed + p.tw - 1) / p.tw);
     p.total_rows = (long long)p.tiles_x * p.rows_needed;
     p.seg_overhead = 2 * nl + 2 * (LAG * (nl - 1) + 1);

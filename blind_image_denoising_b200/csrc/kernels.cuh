@@ -69,6 +69,10 @@ int run_loss(bfcnn_handle* h, const float* gt, const float* pred, int n, int hei
 int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int n, int height,
                    int width, const bfcnn_loss_cfg* cfg, float* flat_grads, float* losses4,
                    int update_moving, cudaStream_t st);
+int run_downscale2x(bfcnn_handle* h, const float* in, float* out, int n, int height, int width, int clip_values, int round_values,
+                    cudaStream_t st);
+int run_train_losses(bfcnn_handle* h, float* losses5, cudaStream_t st);
+int run_saved_activation(bfcnn_handle* h, int which, int index, float* out, cudaStream_t st);
 int run_adam_step(bfcnn_handle* h, const float* flat_grads, float grad_scale, const bfcnn_adam_cfg* cfg,
                   int64_t step, cudaStream_t st);
 

@@ -120,9 +120,17 @@ corrupt_kernel(const uint8_t* __restrict__ clean_u8, float* __restrict__ clean_f
   const uint64_t g = sample_offset + (uint64_t)s;
   const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  // per-sample draws (dataset.py:141-142,170-187)
-  const U4 ra = philox4x32_10(0u, 0xFFFFFFFFu, g_lo, g_hi, k0, k1);
-  const U4 rb = philox4x32_10(1u, 0xFFFFFFFFu, g_lo, g_hi, k0, k1);
+  // The decisions of dataset.py:141-142,170-187 (flips, noise on/off, sigmas) are drawn once per CALL of prepare_data_fn in
+  // the reference, and a call sees the no_crops_per_image crops of ONE image (dataset.py:276-297: load + random_crops ->
+  // prepare -> unbatch -> shuffle -> batch).  draw_group = k > 1: runs of k consecutive global sample indices (the crops of
+  // one image) share the draws of the run's first index; 0 / 1: every sample draws for itself (k = 1 crop per image, the
+  // reference default); < 0: the whole call shares the draws of sample_offset.  The per-pixel noise is always per sample.
+  uint64_t gd = g;
+  if (cfg.draw_group > 1) gd = g - g % (uint64_t)cfg.draw_group;
+  else if (cfg.draw_group < 0) gd = sample_offset;
+  const uint32_t d_lo = (uint32_t)gd, d_hi = (uint32_t)(gd >> 32);
+  const U4 ra = philox4x32_10(0u, 0xFFFFFFFFu, d_lo, d_hi, k0, k1);
+  const U4 rb = philox4x32_10(1u, 0xFFFFFFFFu, d_lo, d_hi, k0, k1);
   const bool add_on = cfg.additive_max > 0.f, mul_on = cfg.multiplicative_max > 0.f;
   const bool flip_lr = cfg.random_left_right && (u01(ra.x) > 0.5f);
   const bool flip_ud = cfg.random_up_down && (u01(ra.y) > 0.5f);
@@ -174,6 +182,40 @@ int run_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, floa
   const int npx = height * width;
   dim3 grid((unsigned)std::min((npx + 255) / 256, 4 * h->sm_count), (unsigned)n);
   corrupt_kernel<<<grid, 256, 0, st>>>(clean_u8, clean_f32, noisy_f32, n, height, width, seed, sample_offset, *cfg);
+  h->launches++;
+  BF_CUDA(cudaGetLastError());
+  return BFCNN_OK;
+}
+
+// =====================================================================================
+// multi-scale ground truth (utilities.py:625-685 multiscales_generator_fn; train_loop.py:239-247): one level =
+// tf.nn.avg_pool2d(ksize 2x2, strides 2, VALID) -> clip [0,255] -> tf.round.  HBM-bound: 48 B read, 12 B written per
+// output pixel; one thread per output pixel, the two input rows are read as 6 contiguous floats each.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+downscale2x_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int h, int w, int clip_values, int round_values) {
+  const int ho = h >> 1, wo = w >> 1;
+  const long long total = (long long)n * ho * wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % wo), y = (int)((i / wo) % ho), b = (int)(i / ((long long)wo * ho));
+    const float* r0 = in + (((size_t)b * h + 2 * y) * w + 2 * x) * 3;
+    const float* r1 = r0 + (size_t)w * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = __fmul_rn(__fadd_rn(__fadd_rn(r0[c], r0[3 + c]), __fadd_rn(r1[c], r1[3 + c])), 0.25f);
+      if (clip_values) v = fminf(fmaxf(v, 0.f), 255.f);
+      if (round_values) v = rintf(v);
+      out[(size_t)i * 3 + c] = v;
+    }
+  }
+}
+
+int run_downscale2x(bfcnn_handle* h, const float* in, float* out, int n, int height, int width, int clip_values, int round_values,
+                    cudaStream_t st) {
+  const long long total = (long long)n * (height / 2) * (width / 2);
+  if (total == 0) return BFCNN_OK;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
+  downscale2x_kernel<<<blocks, 256, 0, st>>>(in, out, n, height, width, clip_values, round_values);
   h->launches++;
   BF_CUDA(cudaGetLastError());
   return BFCNN_OK;
@@ -283,27 +325,25 @@ static int loss_grid_x(const bfcnn_handle* h, int per_sample, int n) {
 // =====================================================================================
 constexpr int SS_F = 7;                       // filter size
 constexpr int SS_TW = 32, SS_TH = 8;          // windows (forward) / pixels (backward) per CTA
-__constant__ float c_gauss[SS_F * SS_F];
 constexpr float SS_C1 = (0.01f * 255.f) * (0.01f * 255.f), SS_C2 = (0.03f * 255.f) * (0.03f * 255.f);
 
-static int ssim_upload_filter() {
-  static bool done = false;
-  if (done) return BFCNN_OK;
+// The 49 taps travel as a kernel argument (the constant bank of the launch): a __constant__ symbol is per DEVICE, and a
+// process-wide "uploaded" flag left handles on a second GPU of the same process with an all-zero filter.
+struct GaussTaps { float g[SS_F * SS_F]; };
+static GaussTaps ssim_taps() {
+  GaussTaps t;
   double g1[SS_F], sum = 0;
   for (int i = 0; i < SS_F; ++i) { const double c = i - (SS_F - 1) / 2.0; g1[i] = exp(-0.5 * c * c / (1.5 * 1.5)); sum += g1[i]; }
-  float g2[SS_F * SS_F];
   for (int i = 0; i < SS_F; ++i)
-    for (int j = 0; j < SS_F; ++j) g2[i * SS_F + j] = (float)((g1[i] / sum) * (g1[j] / sum));   // softmax of the sum of exponents
-  BF_CUDA(cudaMemcpyToSymbol(c_gauss, g2, sizeof(g2)));
-  done = true;
-  return BFCNN_OK;
+    for (int j = 0; j < SS_F; ++j) t.g[i * SS_F + j] = (float)((g1[i] / sum) * (g1[j] / sum));   // softmax of the sum of exponents
+  return t;
 }
 
 // per window and channel: S = l*cs and its partial derivatives w.r.t. (mean_y, E[xy], E[x^2+y^2]) -> maps [n][hv][wv][3][3];
 // per-image sum of S -> ssum[n]
 __global__ void __launch_bounds__(SS_TW * SS_TH)
 ssim_forward_kernel(const float* __restrict__ gt, const float* __restrict__ pred, float* __restrict__ maps,
-                    double* __restrict__ ssum, int h, int w, int hv, int wv) {
+                    double* __restrict__ ssum, int h, int w, int hv, int wv, const GaussTaps taps) {
   __shared__ float s_x[(SS_TH + SS_F - 1) * (SS_TW + SS_F - 1) * 3];
   __shared__ float s_y[(SS_TH + SS_F - 1) * (SS_TW + SS_F - 1) * 3];
   __shared__ float s_red[1];
@@ -331,7 +371,7 @@ ssim_forward_kernel(const float* __restrict__ gt, const float* __restrict__ pred
       for (int dy = 0; dy < SS_F; ++dy)
 #pragma unroll
         for (int dx = 0; dx < SS_F; ++dx) {
-          const float g = c_gauss[dy * SS_F + dx];
+          const float g = taps.g[dy * SS_F + dx];
           const int o = ((ly + dy) * PW + lx + dx) * 3 + c;
           const float xv = s_x[o], yv = s_y[o];
           mx = fmaf(g, xv, mx); my = fmaf(g, yv, my);
@@ -361,7 +401,7 @@ ssim_forward_kernel(const float* __restrict__ gt, const float* __restrict__ pred
 // dpred[p][c] = coef * sum_{windows containing p} g * (dS/dmy + dS/dExy * x_p + dS/dE2 * 2 y_p)
 __global__ void __launch_bounds__(SS_TW * SS_TH)
 ssim_backward_kernel(const float* __restrict__ gt, const float* __restrict__ pred, const float* __restrict__ maps,
-                     float* __restrict__ dpred, int h, int w, int hv, int wv, float coef) {
+                     float* __restrict__ dpred, int h, int w, int hv, int wv, float coef, const GaussTaps taps) {
   __shared__ float s_m[(SS_TH + SS_F - 1) * (SS_TW + SS_F - 1) * 9];
   constexpr int PW = SS_TW + SS_F - 1, PH = SS_TH + SS_F - 1;
   const int tid = threadIdx.x;
@@ -386,7 +426,7 @@ ssim_backward_kernel(const float* __restrict__ gt, const float* __restrict__ pre
 #pragma unroll
       for (int dx = 0; dx < SS_F; ++dx) {
         // pixel p sits at offset (dy, dx) inside window (gy - dy, gx - dx)
-        const float g = c_gauss[dy * SS_F + dx];
+        const float g = taps.g[dy * SS_F + dx];
         const float* m = s_m + (((ly + (SS_F - 1) - dy) * PW + lx + (SS_F - 1) - dx) * 3 + c) * 3;
         sa = fmaf(g, m[0], sa); sb = fmaf(g, m[1], sb); sc = fmaf(g, m[2], sc);
       }
@@ -399,11 +439,10 @@ ssim_backward_kernel(const float* __restrict__ gt, const float* __restrict__ pre
 static int run_ssim(bfcnn_handle* h, const float* gt, const float* pred, int n, int height, int width, float* maps,
                     double* ssim_sums, cudaStream_t st) {
   BF_REQUIRE(height >= SS_F && width >= SS_F, "SSIM needs height and width >= 7 (tf.image.ssim, filter_size=7)");
-  BF_CHECK(ssim_upload_filter());
   const int hv = height - SS_F + 1, wv = width - SS_F + 1;
   dim3 grid((wv + SS_TW - 1) / SS_TW, (hv + SS_TH - 1) / SS_TH, n);
   BF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "image too large for the SSIM grid");
-  ssim_forward_kernel<<<grid, SS_TW * SS_TH, 0, st>>>(gt, pred, maps, ssim_sums, height, width, hv, wv);
+  ssim_forward_kernel<<<grid, SS_TW * SS_TH, 0, st>>>(gt, pred, maps, ssim_sums, height, width, hv, wv, ssim_taps());
   h->launches++;
   BF_CUDA(cudaGetLastError());
   return BFCNN_OK;
@@ -904,7 +943,7 @@ __global__ void step_scalars_kernel(const float* __restrict__ loss_scal, const d
 // =====================================================================================
 struct TrainWs {
   // offsets into ws_stats (bytes)
-  size_t bn_stats, bn_params, bwd_sums, loss_sums, ssim_sums, loss_scal, loss_coef, G, reg, tables, out4, end;
+  size_t bn_stats, bn_params, bwd_sums, loss_sums, ssim_sums, loss_scal, loss_coef, G, reg, out4, end;
 };
 
 static TrainWs plan_stats(int N, int n) {
@@ -921,7 +960,6 @@ static TrainWs plan_stats(int N, int n) {
   w.loss_scal = take(8 * sizeof(float));
   w.loss_coef = take((size_t)(1 + n) * sizeof(float));
   w.out4 = take(8 * sizeof(float));
-  w.tables = take((size_t)(2 * N + 8) * (sizeof(long long) + 2 * sizeof(int)) + 64);
   w.end = o;
   return w;
 }
@@ -969,9 +1007,6 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   float* loss_scal = reinterpret_cast<float*>(sb + W.loss_scal);
   float* loss_coef = reinterpret_cast<float*>(sb + W.loss_coef);
   float* out4_d = reinterpret_cast<float*>(sb + W.out4);
-  long long* tab_off = reinterpret_cast<long long*>(sb + W.tables);
-  int* tab_len = reinterpret_cast<int*>(tab_off + (2 * N + 8));
-  int* tab_kind = tab_len + (2 * N + 8);
   BF_CUDA(cudaMemsetAsync(sb, 0, W.bn_params, st));   // all double accumulators
 
   float* saved = h->ws_train.as<float>();
@@ -986,8 +1021,9 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   float* head_c = dgrad_w + (size_t)2 * std::max(N, 1) * 9 * C * C;  // [16][4]
   float* vars = h->d_vars.as<float>();
 
-  // ---- tables: conv offsets (for the prep kernel) and regulariser segments
-  {
+  // ---- tables: conv offsets (for the prep kernel) and regulariser segments; they depend on the architecture only and are
+  // uploaded once per handle (a per-step upload needed a stream synchronisation: the host vectors die with their scope)
+  if (!h->d_train_tables.p) {
     std::vector<long long> off(2 * N + 8, 0);
     std::vector<int> len(2 * N + 8, 0), kind(2 * N + 8, 0);
     int ns = 0;
@@ -996,11 +1032,16 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
     off[ns] = (long long)L.base; len[ns] = (int)nbase; kind[ns++] = 1;
     off[ns] = (long long)L.h0; len[ns] = C * F; kind[ns++] = 2;
     off[ns] = (long long)L.h1; len[ns] = F * 3; kind[ns++] = 2;
-    BF_CUDA(cudaMemcpyAsync(tab_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
-    BF_CUDA(cudaMemcpyAsync(tab_len, len.data(), len.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    BF_CUDA(cudaMemcpyAsync(tab_kind, kind.data(), kind.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    BF_CUDA(cudaStreamSynchronize(st));  // the host vectors die at the end of this scope
+    const size_t nt = (size_t)(2 * N + 8);
+    BF_CHECK(h->d_train_tables.reserve(nt * (sizeof(long long) + 2 * sizeof(int))));
+    uint8_t* tb = h->d_train_tables.as<uint8_t>();
+    BF_CUDA(cudaMemcpy(tb, off.data(), nt * sizeof(long long), cudaMemcpyHostToDevice));
+    BF_CUDA(cudaMemcpy(tb + nt * sizeof(long long), len.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+    BF_CUDA(cudaMemcpy(tb + nt * (sizeof(long long) + sizeof(int)), kind.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
   }
+  const long long* tab_off = h->d_train_tables.as<long long>();
+  const int* tab_len = reinterpret_cast<const int*>(tab_off + (2 * N + 8));
+  const int* tab_kind = tab_len + (2 * N + 8);
   const int nseg = 2 * N + 3;
   train_prep_kernel<<<2 * N + 1, 256, 0, st>>>(vars, tab_off, 2 * N, (long long)L.h0, (long long)L.h1, F, dgrad_w, head_c);
   reg_loss_kernel<<<8, 256, 0, st>>>(vars, tab_off, tab_len, tab_kind, nseg, regd);
@@ -1047,7 +1088,7 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
     // d(total)/d(pred) of  m * (1 - mean_b mean_{c,w} S)
     const float coef = -cfg->ssim_multiplier / (float)((double)n * ssim_cnt);
     dim3 bgrid((width + SS_TW - 1) / SS_TW, (height + SS_TH - 1) / SS_TH, n);
-    ssim_backward_kernel<<<bgrid, SS_TW * SS_TH, 0, st>>>(clean, ss_pred, ss_maps, ss_dpred, height, width, hv, wv, coef);
+    ssim_backward_kernel<<<bgrid, SS_TW * SS_TH, 0, st>>>(clean, ss_pred, ss_maps, ss_dpred, height, width, hv, wv, coef, ssim_taps());
     h->launches++;
   }
   loss_finalize_kernel<<<1, 32, 0, st>>>(loss_sums, use_ssim ? ssim_sums : nullptr, ssim_cnt, n, px_per_sample * 3, *cfg, loss_scal,
@@ -1106,8 +1147,33 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
     h->launches += 2;
   }
   BF_CUDA(cudaGetLastError());
-  BF_CUDA(cudaMemcpyAsync(losses4, out4_d, 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  h->tr_n = n; h->tr_h = height; h->tr_w = width;
+  h->tr_out5_off = W.out4;
+  // losses4 == nullptr: the step stays asynchronous (no device-to-host copy, no synchronisation); the scalars stay on the
+  // device until bfcnn_train_losses() fetches them, so steps chain without a host round trip
+  if (losses4) {
+    BF_CUDA(cudaMemcpyAsync(losses4, out4_d, 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BF_CUDA(cudaStreamSynchronize(st));
+  }
+  return BFCNN_OK;
+}
+
+int run_train_losses(bfcnn_handle* h, float* losses5, cudaStream_t st) {
+  BF_REQUIRE(h->tr_n > 0 && h->ws_stats.p != nullptr, "no training step has run on this handle");
+  BF_CUDA(cudaMemcpyAsync(losses5, h->ws_stats.as<uint8_t>() + h->tr_out5_off, 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
   BF_CUDA(cudaStreamSynchronize(st));
+  return BFCNN_OK;
+}
+
+// which: 0 = X_i (input of block i; i = N is the stack output), 1 = T_i = ReLU(conv_a), 2 = U_i = conv_b output before BN
+int run_saved_activation(bfcnn_handle* h, int which, int index, float* out, cudaStream_t st) {
+  const int N = h->lay.N;
+  BF_REQUIRE(h->tr_n > 0 && h->ws_train.p != nullptr, "no training step has run on this handle");
+  BF_REQUIRE(which >= 0 && which <= 2, "which must be 0 (X), 1 (T) or 2 (U)");
+  BF_REQUIRE(index >= 0 && index < (which == 0 ? N + 1 : N), "activation index out of range");
+  const size_t map_floats = (size_t)h->tr_n * h->tr_h * h->tr_w * C;
+  const size_t slot = which == 0 ? (size_t)index : (which == 1 ? (size_t)(N + 1 + index) : (size_t)(2 * N + 1 + index));
+  BF_CUDA(cudaMemcpyAsync(out, h->ws_train.as<float>() + slot * map_floats, map_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return BFCNN_OK;
 }
 

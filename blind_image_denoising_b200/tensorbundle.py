@@ -25,6 +25,8 @@ import numpy as np
 
 TABLE_MAGIC = 0xDB4775248B80FB57
 DT_FLOAT = 1
+DT_INT64 = 9   # tensorflow/core/framework/types.proto (the step / epoch counters of tf.train.Checkpoint)
+_NP_OF_DT = {DT_FLOAT: "<f4", DT_INT64: "<i8"}
 _KEY_RE = re.compile(r"variables/(\d+)/\.ATTRIBUTES/VARIABLE_VALUE$")
 
 # ---------------------------------------------------------------------------- crc32c
@@ -170,7 +172,7 @@ def read_index(index_path: str, verify: bool = True) -> Dict[str, dict]:
 
 
 def read_bundle(prefix: str, verify_crc: bool = True) -> Dict[str, np.ndarray]:
-    """Read every float32 tensor of the bundle `<prefix>.index` / `<prefix>.data-*`."""
+    """Read every float32 / int64 tensor of the bundle `<prefix>.index` / `<prefix>.data-*`."""
     entries = read_index(prefix + ".index")
     hdr = entries.pop("", {"num_shards": 1, "endianness": 0})
     if hdr.get("endianness", 0) != 0:
@@ -179,18 +181,19 @@ def read_bundle(prefix: str, verify_crc: bool = True) -> Dict[str, np.ndarray]:
     shards = {}
     out: Dict[str, np.ndarray] = {}
     for key, e in entries.items():
-        if e["dtype"] != DT_FLOAT:
+        if e["dtype"] not in _NP_OF_DT:
             continue
+        npdt = np.dtype(_NP_OF_DT[e["dtype"]])
         sid = e["shard_id"]
         if sid not in shards:
             shards[sid] = Path(f"{prefix}.data-{sid:05d}-of-{nsh:05d}").read_bytes()
         raw = shards[sid][e["offset"]:e["offset"] + e["size"]]
         n = int(np.prod(e["shape"])) if e["shape"] else 1
-        if len(raw) != 4 * n:
+        if len(raw) != npdt.itemsize * n:
             raise ValueError(f"tensor {key}: {len(raw)} bytes for shape {e['shape']}")
         if verify_crc and e["crc32c"] is not None and masked_crc32c(raw) != e["crc32c"]:
             raise ValueError(f"tensor {key}: crc32c mismatch")
-        out[key] = np.frombuffer(raw, dtype="<f4").reshape(e["shape"]).copy()
+        out[key] = np.frombuffer(raw, dtype=npdt).reshape(e["shape"]).copy()
     return out
 
 
@@ -246,7 +249,7 @@ def _field_bytes(field: int, b: bytes) -> bytes:
 
 
 def write_bundle(prefix: str, tensors: Dict[str, np.ndarray]) -> None:
-    """Write float32 tensors as a one-shard TensorBundle readable by
+    """Write float32 (and int64: step / epoch counters) tensors as a one-shard TensorBundle readable by
     `tf.train.load_checkpoint(prefix)` and by `read_bundle`."""
     keys = sorted(tensors.keys(), key=lambda s: s.encode("utf-8"))
     data = bytearray()
@@ -254,10 +257,12 @@ def write_bundle(prefix: str, tensors: Dict[str, np.ndarray]) -> None:
     header = _field_varint(1, 1) + _field_varint(2, 0) + _field_bytes(3, _field_varint(1, 1))
     entries.append((b"", header))
     for k in keys:
-        a = np.ascontiguousarray(tensors[k], dtype="<f4")
+        src = np.asarray(tensors[k])
+        dt = DT_INT64 if src.dtype.kind in "iu" else DT_FLOAT
+        a = np.ascontiguousarray(src, dtype=_NP_OF_DT[dt])
         raw = a.tobytes()
         shape = b"".join(_field_bytes(2, _field_varint(1, int(d))) for d in a.shape)
-        e = _field_varint(1, DT_FLOAT) + _field_bytes(2, shape)
+        e = _field_varint(1, dt) + _field_bytes(2, shape)
         if len(data):
             e += _field_varint(4, len(data))
         e += _field_varint(5, len(raw))

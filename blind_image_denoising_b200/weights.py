@@ -64,6 +64,23 @@ def synthetic_variables(arch: Arch, seed: int = 0,
     return out
 
 
+def initial_variables(arch: Arch, seed: int = 0) -> List[np.ndarray]:
+    """``hydra.variables`` as Keras initialises them (what `model_builder` yields before any training):
+    glorot_normal kernels (backbone_resnet.py:36, model.py:276), BN gamma = 1, moving_mean = 0, moving_var = 1."""
+    rng = np.random.default_rng(seed)
+    shapes = arch.variable_shapes()
+    out: List[np.ndarray] = [_glorot_truncated_normal(rng, shapes[0])]
+    for _ in range(arch.no_layers):
+        out.append(_glorot_truncated_normal(rng, (3, 3, arch.filters, arch.filters)))
+        out.append(_glorot_truncated_normal(rng, (3, 3, arch.filters, arch.filters)))
+        out.append(np.ones(arch.filters, np.float32))
+        out.append(np.zeros(arch.filters, np.float32))
+        out.append(np.ones(arch.filters, np.float32))
+    out.append(_glorot_truncated_normal(rng, shapes[-2]))
+    out.append(_glorot_truncated_normal(rng, shapes[-1]))
+    return out
+
+
 def flatten_variables(arch: Arch, variables: Sequence[np.ndarray]) -> np.ndarray:
     shapes = arch.variable_shapes()
     if len(variables) != len(shapes):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BFCNN_ABI_VERSION 2
+#define BFCNN_ABI_VERSION 3
 
 typedef enum bfcnn_status {
   BFCNN_OK = 0,
@@ -55,6 +55,8 @@ typedef enum bfcnn_precision {
 #define BFCNN_FLAG_IN_DEVICE   1u  /* `in` is a device pointer (else host)                        */
 #define BFCNN_FLAG_OUT_DEVICE  2u  /* `out` is a device pointer (else host)                       */
 #define BFCNN_FLAG_NO_PAD_POW2 4u  /* do NOT emulate pad_to_power_of_2 (utilities.py:736-751)     */
+#define BFCNN_FLAG_IN_F32      8u  /* `in` holds float32 pixels (0..255 scale; the hydra model's own input,
+                                      model.py:100-102) instead of uint8; BFCNN_PREC_FP32 only   */
 
 /* Hyper-parameters of bfcnn/backbone_resnet.py:19-49 + bfcnn/model.py:267-275 for the
  * 16-channel, two-3x3-convs-per-block family. */
@@ -76,7 +78,12 @@ typedef struct bfcnn_noise_cfg {
   int32_t random_left_right;                    /* dataset.py:141-148                       */
   int32_t random_up_down;                       /* dataset.py:150-158                       */
   int32_t subsample;                            /* 1: w.p. 1/2 decimate x2 + nearest up x2  */
-  int32_t round_values;                         /* dataset.py:228                           */
+  int32_t round_values;                         /* dataset.py:228 (the reference always rounds; 0 is for tests) */
+  int32_t draw_group;                           /* who shares the call-level draws of dataset.py:141-187 (flips, on/off
+                                                   switches, sigmas): 0/1 = every sample its own (no_crops_per_image = 1,
+                                                   the reference default); k > 1 = runs of k consecutive global sample
+                                                   indices, i.e. the k crops of one image (dataset.py:276-297); < 0 = the
+                                                   whole call.  Per-pixel noise values are always per sample.       */
 } bfcnn_noise_cfg;
 
 /* loss.py:152-187 configuration. */
@@ -141,6 +148,12 @@ int bfcnn_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, fl
                   int n, int height, int width, uint64_t seed, uint64_t sample_offset,
                   const bfcnn_noise_cfg* cfg, void* stream);
 
+/* replaces: one level of multiscales_generator_fn (bfcnn/utilities.py:625-685, called at bfcnn/train_loop.py:239-247,274):
+ * tf.nn.avg_pool2d(2x2, strides 2, VALID) -> clip [0,255] (clip_values) -> tf.round (round_values).  in: device float32
+ * [n,h,w,3]; out: device float32 [n,h/2,w/2,3]. */
+int bfcnn_downscale2x(bfcnn_handle* h, const float* in, float* out, int n, int height, int width, int clip_values,
+                      int round_values, void* stream);
+
 /* replaces: loss_function_builder(...)["denoiser"] (bfcnn/loss.py:190-247).
  * gt, pred: device float32 [n,h,w,3]; out5 (host): total, mae, rmse, hinged-mae, ssim loss (1 - mean SSIM; 0 when
  * ssim_multiplier == 0).  SSIM needs height, width >= 7. */
@@ -151,11 +164,24 @@ int bfcnn_loss(bfcnn_handle* h, const float* gt, const float* pred, int n, int h
  * statistics, hinged-MAE (+RMSE) loss, L1/L2 weight regularisation, backward.
  * clean, noisy: device float32 [n,h,w,3] (0..255).  flat_grads: device float32
  * [bfcnn_num_trainable] in Keras trainable_variables order (the buffer a data-parallel
- * caller all-reduces).  losses5 (host): total, denoiser total, mae, regularisation, ssim loss.
+ * caller all-reduces).  losses5 (host, or NULL = asynchronous, see bfcnn_train_losses): total, denoiser total, mae,
+ * regularisation, ssim loss.
  * update_moving != 0 applies the BN moving-statistics update (momentum 0.995). */
 int bfcnn_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int n, int height,
                      int width, const bfcnn_loss_cfg* cfg, float* flat_grads, float* losses5,
                      int update_moving, void* stream);
+
+/* bfcnn_train_step with losses5 == NULL is ASYNCHRONOUS: nothing is copied back and the host does not wait, so that
+ * corrupt -> step -> all-reduce -> Adam chain on the stream without a host round trip (the reference reads its loss
+ * tensors only when it logs them, train_loop.py:439-559).  bfcnn_train_losses fetches the five scalars of the LAST step
+ * (same order as losses5) and synchronises the stream. */
+int bfcnn_train_losses(bfcnn_handle* h, float* losses5, void* stream);
+
+/* Test hook: copy one activation map saved by the LAST bfcnn_train_step to `out` (device float32 [n,h,w,16]).
+ * which: 0 = X_i, the input of block i (index N = output of the stack; backbone_blocks.py:240-242), 1 = T_i =
+ * ReLU(conv_a(X_i)) (:174-178), 2 = U_i = conv_b(T_i) before BatchNormalization (:191-196).  The gradient-parity tests
+ * read the ReLU masks the kernels actually used from T_i. */
+int bfcnn_saved_activation(bfcnn_handle* h, int which, int index, float* out, void* stream);
 
 /* Engine of the 3x3 convs inside bfcnn_train_step: 2 (default) = tcgen05 with the fp16 hi/lo split (3 MMAs per product,
  * conv error ~4e-6 on O(1) data, i.e. FP32-grade; row-streaming kernel, conv_t5.cu), 1 = the same arithmetic on

@@ -228,19 +228,48 @@ def denoiser_loss(gt: torch.Tensor, pred: torch.Tensor, *, hinge=0.0, cutoff=255
 
 
 # ----------------------------------------------------------------------------
+# multi-scale ground truth: utilities.py:625-685 (multiscales_generator_fn), used at train_loop.py:239-247,274
+# ----------------------------------------------------------------------------
+def multiscales(x_nhwc: np.ndarray, no_scales: int, clip_values: bool = True, round_values: bool = True,
+                dtype=np.float32) -> List[np.ndarray]:
+    """[n, pool(n), pool(pool(n)), ...]: tf.nn.avg_pool2d(ksize 2x2, strides 2, VALID), then clip [0,255], then tf.round
+    (half to even) per level (utilities.py:655-668)."""
+    n = np.asarray(x_nhwc, dtype)
+    scales = [n]
+    for _ in range(no_scales):
+        b, h, w, c = n.shape
+        ho, wo = h // 2, w // 2
+        v = n[:, :2 * ho, :2 * wo, :].reshape(b, ho, 2, wo, 2, c)
+        n = ((v[:, :, 0, :, 0] + v[:, :, 0, :, 1]) + (v[:, :, 1, :, 0] + v[:, :, 1, :, 1])) * dtype(0.25)
+        if clip_values:
+            n = np.clip(n, 0.0, 255.0)
+        if round_values:
+            n = np.rint(n)
+        n = n.astype(dtype)
+        scales.append(n)
+    return scales
+
+
+# ----------------------------------------------------------------------------
 # training step: train_loop.py:263-312
 # ----------------------------------------------------------------------------
 def train_step(variables: Sequence[np.ndarray], clean_nhwc: np.ndarray, noisy_nhwc: np.ndarray, *,
                hinge: float = 0.5, cutoff: float = 255.0, mae_multiplier: float = 1.0,
                mse_multiplier: float = 0.0, regularization: float = 0.01, ssim_multiplier: float = 0.0,
-               dtype=torch.float64, head_literal: bool = False):
+               dtype=torch.float64, head_literal: bool = False, relu_flips: Optional[Dict[int, np.ndarray]] = None,
+               return_preact: bool = False):
     """One tape step: hydra(noisy, training=True) -> denoiser loss (+ L1/L2 weight
     regularisation * lambda) -> gradients w.r.t. trainable variables.
 
     BN in training mode: normalise with the biased batch variance; moving stats
     <- m*old + (1-m)*batch (moving_var uses the unbiased variance).
     Returns dict(total, denoiser_total, mae, mse, reg, grads[list in trainable order],
-    prediction, new_moving[list of (mean,var)])."""
+    prediction, new_moving[list of (mean,var)]).
+
+    relu_flips / return_preact serve the gradient-parity tests only: `preact[i]` is block i's conv_a output before
+    the ReLU (NCHW); `relu_flips[i]` (bool, NCHW) inverts the ReLU's 0/1 derivative mask of those units -- two
+    FP32-grade implementations may disagree on the sign of a pre-activation that is below their rounding error, which
+    moves that unit's whole share of the gradient while leaving the forward values unchanged to ~1e-6."""
     base, blocks, h0, h1 = split_variables(variables)
     params = {}
 
@@ -254,13 +283,20 @@ def train_step(variables: Sequence[np.ndarray], clean_nhwc: np.ndarray, noisy_nh
     x = torch.clamp(x, 0.0, 255.0) / 255.0 - 0.5
     x = _conv_same(x, wbase)
     new_moving = []
+    preacts = []
     reg = torch.abs(wbase).sum() * L1_COEFF
     order = ["base"]
     for i, (wa, wb, gamma, mean, var) in enumerate(blocks):
         pa, pb, pg = P(f"a{i}", wa), P(f"b{i}", wb), P(f"g{i}", gamma)
         order += [f"a{i}", f"b{i}", f"g{i}"]
         prev = x
-        t = torch.relu(_conv_same(x, pa))
+        pre = _conv_same(x, pa)
+        preacts.append(pre.detach().numpy())
+        if relu_flips is not None and i in relu_flips:
+            mask = (pre.detach() > 0) ^ torch.as_tensor(np.asarray(relu_flips[i], bool))
+            t = pre * mask.to(dtype)
+        else:
+            t = torch.relu(pre)
         u = _conv_same(t, pb)
         bm = u.mean(dim=(0, 2, 3))
         bv = ((u - bm.view(1, -1, 1, 1)) ** 2).mean(dim=(0, 2, 3))       # biased
@@ -285,7 +321,9 @@ def train_step(variables: Sequence[np.ndarray], clean_nhwc: np.ndarray, noisy_nh
                        mse_multiplier=mse_multiplier, ssim_multiplier=ssim_multiplier)
     total = dl["total_loss"] + reg * regularization            # train_loop.py:297-301
     grads = torch.autograd.grad(total, [params[k] for k in order])
+    extra = {"preact": preacts} if return_preact else {}
     return {
+        **extra,
         "total": float(total.detach()), "denoiser_total": float(dl["total_loss"].detach()),
         "mae": float(dl["mae_loss"].detach()), "mse": float(dl["mse_loss"].detach()), "reg": float(reg.detach()),
         "ssim": float(dl["ssim_loss"].detach()),

@@ -41,7 +41,10 @@ class NoiseConfig:
     random_left_right: bool = True
     random_up_down: bool = True
     subsample: bool = False
-    round_values: bool = True
+    round_values: bool = True          # dataset.py:228 always rounds; False exists for tests of the un-rounded values
+    draw_group: int = 0                # who shares the call-level draws of dataset.py:141-187: 0/1 every sample its own,
+                                       # k > 1 runs of k consecutive global sample indices (the crops of one image,
+                                       # dataset.py:276-297), < 0 the whole call
 
 
 # ----------------------------------------------------------------------------------
@@ -178,7 +181,12 @@ def corrupt(clean_u8: np.ndarray, seed: int, sample_offset: int, cfg: NoiseConfi
     pix = np.arange(h * w, dtype=np.uint32).reshape(h, w)
     for s in range(n):
         g = sample_offset + s
-        p = sample_parameters(g, seed, cfg)
+        gd = g
+        if cfg.draw_group > 1:
+            gd = g - g % cfg.draw_group
+        elif cfg.draw_group < 0:
+            gd = sample_offset
+        p = sample_parameters(gd, seed, cfg)
         img = clean_u8[s]
         if p["flip_lr"]:
             img = img[:, ::-1]

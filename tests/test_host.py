@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
     for s in declared:
         assert hasattr(native_lib, s), s
-    assert native_lib.bfcnn_abi_version() == 2
+    assert native_lib.bfcnn_abi_version() == 3
 
 
 def test_native_param_counts(native_lib):
