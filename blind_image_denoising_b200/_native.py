@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "bfcnn_abi_version", "bfcnn_last_error", "bfcnn_device_count", "bfcnn_num_weights",
     "bfcnn_num_trainable", "bfcnn_create", "bfcnn_destroy", "bfcnn_set_weights",
     "bfcnn_get_weights", "bfcnn_denoise_u8", "bfcnn_denoise_f32", "bfcnn_launch_count",
-    "bfcnn_last_stack_ms", "bfcnn_corrupt", "bfcnn_loss", "bfcnn_train_step", "bfcnn_train_losses", "bfcnn_saved_activation", "bfcnn_downscale2x",
+    "bfcnn_last_stack_ms", "bfcnn_set_kernel_timing", "bfcnn_kernel_times", "bfcnn_corrupt", "bfcnn_loss", "bfcnn_train_step", "bfcnn_train_losses", "bfcnn_saved_activation", "bfcnn_downscale2x",
     "bfcnn_adam_step", "bfcnn_conv3x3", "bfcnn_set_train_engine",
 ]
 
@@ -94,6 +94,10 @@ def load_library() -> ctypes.CDLL:
     lib.bfcnn_launch_count.restype = c_int64
     lib.bfcnn_last_stack_ms.argtypes = [H, POINTER(c_float)]
     lib.bfcnn_last_stack_ms.restype = c_int
+    lib.bfcnn_set_kernel_timing.argtypes = [H, c_int]
+    lib.bfcnn_set_kernel_timing.restype = c_int
+    lib.bfcnn_kernel_times.argtypes = [H, POINTER(c_float), POINTER(c_int), c_int, POINTER(c_int)]
+    lib.bfcnn_kernel_times.restype = c_int
     lib.bfcnn_corrupt.argtypes = [H, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_uint64,
                                   c_uint64, POINTER(NoiseCfg), c_void_p]
     lib.bfcnn_corrupt.restype = c_int

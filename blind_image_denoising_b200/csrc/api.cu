@@ -248,6 +248,7 @@ void bfcnn_destroy(bfcnn_handle* h) {
   h->ws_train.release(); h->ws_stats.release(); h->ws_grads.release();
   h->adam_m.release(); h->adam_v.release();
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ktime_ev) cudaEventDestroy(e);
   if (h->s_compute) cudaStreamDestroy(h->s_compute);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -302,6 +303,26 @@ int bfcnn_last_stack_ms(bfcnn_handle* h, float* ms) {
   BF_CUDA(cudaSetDevice(h->device));
   BF_CUDA(cudaEventSynchronize(h->ev1));
   BF_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return BFCNN_OK;
+}
+
+int bfcnn_set_kernel_timing(bfcnn_handle* h, int on) {
+  BF_REQUIRE(h != nullptr, "handle is NULL");
+  h->ktime_on = on != 0;
+  h->ktime_n = 0;
+  return BFCNN_OK;
+}
+
+int bfcnn_kernel_times(bfcnn_handle* h, float* ms, int* kinds, int capacity, int* count) {
+  BF_REQUIRE(h != nullptr && ms != nullptr && kinds != nullptr && count != nullptr, "NULL argument");
+  BF_CUDA(cudaSetDevice(h->device));
+  const int n = std::min(h->ktime_n, capacity);
+  for (int i = 0; i < n; ++i) {
+    BF_CUDA(cudaEventSynchronize(h->ktime_ev[2 * i + 1]));
+    BF_CUDA(cudaEventElapsedTime(&ms[i], h->ktime_ev[2 * i], h->ktime_ev[2 * i + 1]));
+    kinds[i] = h->ktime_kind[i];
+  }
+  *count = n;
   return BFCNN_OK;
 }
 

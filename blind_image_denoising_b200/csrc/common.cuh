@@ -111,8 +111,30 @@ struct bfcnn_handle {
   std::vector<cudaEvent_t> ev_pool;
   bool ev_valid = false;
   int sm_count = 148;
+  // optional per-launch timing of the conv-stack kernels (bfcnn_set_kernel_timing): event pairs of the last call
+  bool ktime_on = false;
+  std::vector<cudaEvent_t> ktime_ev;
+  std::vector<int> ktime_kind;      // 0 = base conv, 1 = pass, 2 = last pass (head fused in)
+  int ktime_n = 0;
 };
 
 namespace bfcnn {
 int pack_weights(bfcnn_handle* h);  // host fold + upload (host_pack.cu)
+// per-launch timing hooks (no-ops unless bfcnn_set_kernel_timing switched them on)
+inline void ktime_begin(bfcnn_handle* h, cudaStream_t st, int kind) {
+  if (!h->ktime_on) return;
+  while ((int)h->ktime_ev.size() < 2 * (h->ktime_n + 1)) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    h->ktime_ev.push_back(e);
+  }
+  if ((int)h->ktime_kind.size() <= h->ktime_n) h->ktime_kind.resize(h->ktime_n + 1);
+  h->ktime_kind[h->ktime_n] = kind;
+  cudaEventRecord(h->ktime_ev[2 * h->ktime_n], st);
+}
+inline void ktime_end(bfcnn_handle* h, cudaStream_t st) {
+  if (!h->ktime_on || (int)h->ktime_ev.size() < 2 * (h->ktime_n + 1)) return;
+  cudaEventRecord(h->ktime_ev[2 * h->ktime_n + 1], st);
+  h->ktime_n++;
+}
 }

@@ -597,7 +597,10 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
     BF_CUDA(cudaMemset2DAsync(h->ws_feat[k].as<__half>() + (size_t)e.we * C, (size_t)(e.we + 1) * C * sizeof(__half), 0, C * sizeof(__half),
                               (size_t)e.he * e.n, st));
   // pass "-1": base conv into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
+  h->ktime_n = 0;
+  ktime_begin(h, st, 0);
   BF_CHECK(launch_base_conv_f16(h, d_in, h->ws_feat[1].as<__half>(), e, st, nullptr, e.we + 1, vw));
+  ktime_end(h, st);
   Extent ev = e;   // what the TMA sees: one "image" of he rows and vw columns
   ev.n = 1; ev.we = (int)vw - 1;
   for (int ps = 0; ps < passes; ++ps) {
@@ -641,8 +644,10 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
     }
     CUtensorMap tmap;
     BF_CHECK(make_feature_tmap(&tmap, p.fin, ev, RW, 2, vw));
+    ktime_begin(h, st, last ? 2 : 1);
     if (last) stream_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     else stream_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
+    ktime_end(h, st);
     h->launches++;
     BF_CUDA(cudaGetLastError());
     if (p.trace) {

@@ -549,10 +549,13 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
       BF_CUDA(cudaMemset2DAsync(h->ws_feat[k].as<__half>() + part * feat_halves + (size_t)e.we * C, (size_t)(e.we + 1) * C * sizeof(__half), 0,
                                 C * sizeof(__half), (size_t)e.he * e.n, st));
   // pass "-1": base conv (hi + lo) into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
+  h->ktime_n = 0;
+  ktime_begin(h, st, 0);
   if (h->arch.base_kernel == 3 && !getenv("BFCNN_BASE_FFMA"))   // tensor-core base conv (fused_umma.cu), hi + lo outputs
     BF_CHECK(launch_base_conv_f16(h, d_in, h->ws_feat[1].as<__half>(), e, st, h->ws_feat[1].as<__half>() + feat_halves, e.we + 1, vw));
   else
     BF_CHECK(launch_base_conv_f16_x3(h, d_in, h->ws_feat[1].as<__half>(), h->ws_feat[1].as<__half>() + feat_halves, e, st, e.we + 1, vw));
+  ktime_end(h, st);
   Extent e2 = e;   // what the TMA sees: two "images" (hi part, lo part) of he rows and vw columns
   e2.n = 2; e2.we = (int)vw - 1;
   for (int ps = 0; ps < passes; ++ps) {
@@ -590,8 +593,10 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
     BF_REQUIRE(smem <= (size_t)MAX_SMEM, "internal: streaming pass does not fit in shared memory");
     CUtensorMap tmap;
     BF_CHECK(make_feature_tmap(&tmap, p.fin, e2, RW, 2, vw));
+    ktime_begin(h, st, last ? 2 : 1);
     if (last) stream_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
     else stream_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
+    ktime_end(h, st);
     h->launches++;
     BF_CUDA(cudaGetLastError());
   }

@@ -74,6 +74,18 @@ class Denoiser:
         _native.check(self._lib.bfcnn_last_stack_ms(self._h, ctypes.byref(ms)))
         return float(ms.value)
 
+    def set_kernel_timing(self, on: bool):
+        """Record CUDA events around every conv-stack launch of the following calls (bench.py's per-kernel roofline)."""
+        _native.check(self._lib.bfcnn_set_kernel_timing(self._h, int(bool(on))))
+
+    def kernel_times(self):
+        """[(kind, ms)] of the last timed call; kind 0 = base conv, 1 = pass, 2 = last pass."""
+        ms = (ctypes.c_float * 128)()
+        kinds = (ctypes.c_int * 128)()
+        cnt = ctypes.c_int()
+        _native.check(self._lib.bfcnn_kernel_times(self._h, ms, kinds, 128, ctypes.byref(cnt)))
+        return [(int(kinds[i]), float(ms[i])) for i in range(cnt.value)]
+
     # ------------------------------------------------------------------
     def __call__(self, image, *, precision: Optional[str] = None, pad_pow2: Optional[bool] = None,
                  return_float: bool = False, out=None):

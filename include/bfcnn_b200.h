@@ -140,6 +140,12 @@ int64_t bfcnn_launch_count(const bfcnn_handle* h);
  * (events on the caller's stream; ms).  Used for the roofline of the dominant kernel. */
 int bfcnn_last_stack_ms(bfcnn_handle* h, float* ms);
 
+/* Per-launch device times of the conv-stack kernels of the LAST denoise call made with timing switched on (CUDA events
+ * around every launch on the caller's stream; bench.py's roofline of the dominant kernel is measured with these inside
+ * its own run).  kinds[i]: 0 = base conv, 1 = pass of the fused stack, 2 = last pass (head + encode fused in). */
+int bfcnn_set_kernel_timing(bfcnn_handle* h, int on);
+int bfcnn_kernel_times(bfcnn_handle* h, float* ms, int* kinds, int capacity, int* count);
+
 /* ---- training step -------------------------------------------------------------
  * replaces: dataset_builder.prepare_data_fn (bfcnn/dataset.py:120-238).
  * clean_u8 [n,h,w,3] -> clean_f32, noisy_f32 [n,h,w,3] (device pointers).  Sample s

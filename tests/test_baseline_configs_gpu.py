@@ -1,0 +1,148 @@
+"""The five BASELINE.json configs at their own shapes, each against the CPU oracle (fp64), plus the natural-image input
+set of SURVEY 8d.  Gates: fp32-grade paths max-abs <= 0.5 / mean-abs <= 0.05 on the 0..255 scale (north_star), the
+fp16-operand tensor-core arm the stated looser bound 2.0 / 0.25; regression guards (TIGHT) at ~2x what the kernels measure.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GATES = {"fp32": (0.5, 0.05), "f16x3": (0.5, 0.05), "f16": (2.0, 0.25)}
+# ~2x the errors measured on B200 for the DEEPEST model (N = 18, GPUTEST of round 2; shallower models sit below)
+TIGHT = {"fp32": (0.02, 0.002), "f16x3": (0.02, 0.002), "f16": (1.0, 0.12)}
+
+
+def _vars(n_layers):
+    from blind_image_denoising_b200 import Arch, synthetic_variables
+    return synthetic_variables(Arch(no_layers=n_layers), 0)
+
+
+def _check(y, yref, prec, what):
+    d = np.abs(np.asarray(y, np.float64) - yref)
+    mx, mean = float(d.max()), float(d.mean())
+    print(f"[{what}] {prec}: max-abs {mx:.5f} mean-abs {mean:.6f}")
+    assert mx <= GATES[prec][0] and mean <= GATES[prec][1], (what, prec, mx, mean)
+    assert mx <= TIGHT[prec][0] and mean <= TIGHT[prec][1], ("regression", what, prec, mx, mean)
+    return mx, mean
+
+
+def _check_u8(u8, u8ref, prec):
+    du = np.abs(u8.astype(np.int32) - u8ref.astype(np.int32))
+    assert du.max() <= (2 if prec == "f16" else 1)
+    assert (du > 0).mean() < (0.25 if prec == "f16" else 0.01)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16"])
+def test_config0_1x6_single_256(native_lib, prec):
+    """configs[0]: pretrained resnet_color_1x6 on 1x256x256x3 through bfcnn.load_model(name), the drop-in call."""
+    import warnings
+    import bfcnn
+    from oracle import bfcnn_oracle as O
+    x = np.random.default_rng(0).integers(0, 256, size=(1, 256, 256, 3), dtype=np.uint8)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = bfcnn.load_model("resnet_color_1x6_bn_16x3x3_256x256_l1_relu", precision=prec)
+    assert any("SYNTHETIC" in str(i.message) for i in w)          # the shipped directories hold random weights: say so
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        bfcnn.load_model("resnet_color_1x6_bn_16x3x3_256x256_l1_relu", allow_synthetic=True).close()
+    yref, u8ref = O.denoise(_vars(6), x, pad_pow2=True)
+    _check(m(x, return_float=True), yref, prec, "configs[0]")
+    _check_u8(m(x), u8ref, prec)
+    m.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16"])
+def test_config1_1x12_batch64_256(native_lib, prec):
+    """configs[1]: 1x12, batch 64 of 256x256x3 in ONE call; the oracle checks images 0, 21, 42, 63 of the batch, and the
+    images of the batch come out as if denoised alone."""
+    import blind_image_denoising_b200 as bf
+    from oracle import bfcnn_oracle as O
+    x = np.random.default_rng(1).integers(0, 256, size=(64, 256, 256, 3), dtype=np.uint8)
+    m = bf.synthetic_model(12, precision=prec)
+    y, u8 = m(x, return_float=True), m(x)
+    pick = [0, 21, 42, 63]
+    yref, u8ref = O.denoise(_vars(12), x[pick], pad_pow2=True)
+    _check(y[pick], yref, prec, "configs[1]")
+    _check_u8(u8[pick], u8ref, prec)
+    assert np.array_equal(m(x[21:22]), u8[21:22])
+    m.close()
+
+
+@pytest.mark.parametrize("prec", ["f16x3", "f16"])
+def test_config2_1x18_4k_frame(native_lib, prec):
+    """configs[2]: 1x18 on a 3840x2160 frame, drop-in semantics (pow2 canvas).  The oracle cannot run a 4K frame in
+    seconds, so: (a) interior -- a 274x374 window cut with a margin of R = 37 reproduces the frame's values there (locality
+    of the receptive field), and the oracle runs that window; (b) canvas band -- the bottom-right 160x160 corner of the
+    frame sees the raw zeros of the 4096x4096 canvas; the oracle runs the corner embedded in a zero canvas of
+    its own with the same geometry relative to the corner; (c) determinism."""
+    import blind_image_denoising_b200 as bf
+    from oracle import bfcnn_oracle as O
+    v = _vars(18)
+    R = 37
+    x = np.random.default_rng(0).integers(0, 256, size=(1, 2160, 3840, 3), dtype=np.uint8)
+    m = bf.synthetic_model(18, precision=prec)          # pad_pow2=True: what load_model returns
+    y = m(x, return_float=True)
+    u8 = m(x)
+    assert np.array_equal(u8, m(x))
+    # (a) interior window
+    y0, x0, hh, ww = 700, 1900, 200, 300
+    win = np.ascontiguousarray(x[:, y0 - R:y0 + hh + R, x0 - R:x0 + ww + R])
+    yref, u8ref = O.denoise(v, win, pad_pow2=False)
+    _check(y[:, y0:y0 + hh, x0:x0 + ww], yref[:, R:R + hh, R:R + ww], prec, "configs[2] interior")
+    _check_u8(u8[:, y0:y0 + hh, x0:x0 + ww], u8ref[:, R:R + hh, R:R + ww], prec)
+    # (b) bottom-right corner: rows/cols beyond the frame are raw zeros out to the canvas edge, which is further than R away
+    c = 160
+    corner = np.zeros((1, c + R + 1, c + R + 1, 3), np.uint8)
+    corner[:, :c, :c] = x[:, 2160 - c:, 3840 - c:]
+    yref, u8ref = O.denoise(v, corner, pad_pow2=False)
+    _check(y[:, 2160 - c + R:, 3840 - c + R:], yref[:, R:c, R:c], prec, "configs[2] canvas corner")
+    _check_u8(u8[:, 2160 - c + R:, 3840 - c + R:], u8ref[:, R:c, R:c], prec)
+    m.close()
+
+
+@pytest.mark.parametrize("n_layers", [6, 18])
+@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16"])
+def test_natural_images(native_lib, prec, n_layers):
+    """The natural input set: windows of the reference's four 512x512 stock images with the sigma = 20 recipe
+    of tests/bfcnn/test_pretrained.py:41-56 (tests/golden/make_natural.py).  Smooth image content exercises other
+    activation statistics than uniform noise (long runs of equal pixels, saturated regions)."""
+    import blind_image_denoising_b200 as bf
+    from oracle import bfcnn_oracle as O
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "natural_inputs.npz"))
+    x = z["noisy"]
+    assert x.shape == (4, 160, 160, 3) and x.dtype == np.uint8
+    m = bf.synthetic_model(n_layers, precision=prec)
+    yref, u8ref = O.denoise(_vars(n_layers), x, pad_pow2=True)
+    _check(m(x, return_float=True), yref, prec, f"natural 1x{n_layers}")
+    _check_u8(m(x), u8ref, prec)
+    m.close()
+
+
+@pytest.mark.parametrize("engine", ["t5", "x3", "fp32"])
+def test_config3_train_step_256(native_lib, engine):
+    """configs[3]: 1x6 training step (corruption -> forward with batch statistics -> hinged MAE + L1/L2 -> backward) on
+    256x256x3 samples against the fp64 oracle: 4 samples here (the oracle needs ~20 s per step on the host), and the
+    full batch of 32 for finiteness / repeatability in test_training_gpu.py::test_full_size_train_step_properties."""
+    import torch
+    from blind_image_denoising_b200 import Arch
+    from blind_image_denoising_b200.training import Trainer
+    from oracle import corrupt_oracle as C
+    from test_training_gpu import _grad_check, _noise_cfg, _oracle_with_kernel_relu_masks
+    arch = Arch(no_layers=6)
+    v = _vars(6)
+    loss = dict(hinge=0.5, cutoff=255.0, mae_multiplier=1.0, mse_multiplier=0.0, regularization=0.01)
+    t = Trainer(arch, v, device=0, loss_config=dict(loss, ssim_multiplier=0.0), conv_engine=engine)
+    x = np.random.default_rng(3).integers(0, 256, size=(4, 256, 256, 3), dtype=np.uint8)
+    oc, nc = _noise_cfg()
+    clean_ref, noisy_ref = C.corrupt(x, 0, 0, oc)
+    clean, noisy = t.prepare_data(torch.from_numpy(x).cuda(), nc, 0, 0)
+    assert np.array_equal(noisy.cpu().numpy(), noisy_ref) and np.array_equal(clean.cpu().numpy(), clean_ref)
+    total, ml, dl, g = t.train_step_single_gpu(clean, noisy)
+    ref, n_flips = _oracle_with_kernel_relu_masks(t, v, clean_ref, noisy_ref, loss, 6)
+    assert total == pytest.approx(ref["total"], rel=1e-5) and dl["mae_loss"] == pytest.approx(ref["mae"], rel=1e-5)
+    cos, worst = _grad_check(g.cpu().numpy(), ref["grads"], arch)
+    print(f"[configs[3] {engine}] cosine {cos:.8f} worst per-variable error {worst:.2e}, {n_flips} ambiguous ReLU units of {6 * 4 * 65536 * 16}")
+    t.close()

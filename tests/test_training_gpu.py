@@ -107,32 +107,55 @@ def test_loss_matches_oracle(native_lib, cfg):
     t.close()
 
 
-# Gates on the flat gradient vs the fp64 oracle.  The convs are FP32-grade in both engines (error ~1e-6 FFMA, ~4e-6
-# tensor cores with the fp16 hi/lo split; test_conv_layer_engines_match_fp64), but on these tiny batches one pixel
-# carries ~1/3000 of the gradient and ONE ReLU whose pre-activation is below the rounding error (the oracle finds 0-2
-# of them per layer within 1e-6 of zero) switches and moves a whole pixel's contribution: ~1e-2 of a variable's
-# gradient scale, in either engine and from run to run (the BN statistics are reduced with atomics).  Hence: cosine
-# >= 0.9999 over the whole vector, max error <= 2e-2 of each variable's scale, and the strict 1e-4 gate only on the
-# head variables, which no ReLU mask separates from the loss.
-MAX_ERR = {"fp32": 2e-2, "x3": 2e-2, "t5": 2e-2}
+# Gates on the flat gradient vs the fp64 oracle: cosine >= 0.9999 and max error <= 1e-3 of each variable's
+# gradient scale, 1e-4 on the head variables.  A ReLU whose pre-activation is below the rounding error of an FP32-grade
+# conv (~1e-5 after a few layers) may come out on the other side of zero than in the fp64 oracle; that moves the unit's
+# whole share of the gradient (~1e-2 of a variable's scale on tiny batches) while the forward values stay equal to ~1e-6.
+# The test therefore reads the ReLU masks the kernels actually used (bfcnn_saved_activation: T_i > 0), REQUIRES every
+# disagreement with the oracle to sit on a pre-activation smaller than AMBIG_TOL, and re-runs the oracle with exactly
+# those units' 0/1 derivative inverted (oracle.train_step(relu_flips=...)): against that reference the 1e-3 gate holds.
+MAX_ERR = 1e-3
 HEAD_ERR = 1e-4
+AMBIG_TOL = 1e-4
 
 
-def _grad_check(got, ref_list, arch, engine="fp32"):
+def _grad_check(got, ref_list, arch, max_err=MAX_ERR):
     ref = np.concatenate([g.reshape(-1) for g in ref_list]).astype(np.float64)
     got = got.astype(np.float64)
     cos = float(got @ ref / (np.linalg.norm(got) * np.linalg.norm(ref)))
     assert cos >= 0.9999, cos
     # per variable: max error relative to that variable's gradient scale
     from blind_image_denoising_b200.weights import trainable_offsets
+    worst = 0.0
     for (_, n, t_off), g in zip(trainable_offsets(arch), ref_list):
         r = ref[t_off:t_off + n]
-        e = np.abs(got[t_off:t_off + n] - r).max()
-        assert e <= MAX_ERR[engine] * max(np.abs(r).max(), 1e-6), (engine, t_off, n, e, np.abs(r).max())
+        e = np.abs(got[t_off:t_off + n] - r).max() / max(np.abs(r).max(), 1e-6)
+        worst = max(worst, e)
+        assert e <= max_err, (t_off, n, e, np.abs(r).max())
     for (_, n, t_off) in trainable_offsets(arch)[-2:]:
         r = ref[t_off:t_off + n]
-        assert np.abs(got[t_off:t_off + n] - r).max() <= HEAD_ERR * np.abs(r).max(), (engine, "head", t_off)
-    return cos
+        assert np.abs(got[t_off:t_off + n] - r).max() <= HEAD_ERR * np.abs(r).max(), ("head", t_off)
+    return cos, worst
+
+
+def _oracle_with_kernel_relu_masks(t, v, clean, noisy, loss, n_layers):
+    """fp64 oracle step whose ReLU derivative masks are those the kernels used; asserts that every unit where they
+    differ from the oracle's own is numerically ambiguous.  Returns (oracle result, number of inverted units)."""
+    from oracle import bfcnn_oracle as O
+    ref = O.train_step(v, clean, noisy, return_preact=True, **loss)
+    flips, n_flips, worst_pre = {}, 0, 0.0
+    for i in range(n_layers):
+        mask_k = (t.saved_activation("t", i).cpu().numpy() > 0).transpose(0, 3, 1, 2)
+        pre = ref["preact"][i]
+        diff = mask_k != (pre > 0)
+        if diff.any():
+            worst_pre = max(worst_pre, float(np.abs(pre[diff]).max()))
+            flips[i] = diff
+            n_flips += int(diff.sum())
+    assert worst_pre <= AMBIG_TOL, f"a ReLU flipped at |pre-activation| = {worst_pre:.3e}: not a rounding ambiguity"
+    if flips:
+        ref = O.train_step(v, clean, noisy, relu_flips=flips, **loss)
+    return ref, n_flips
 
 
 @pytest.mark.parametrize("engine", ["fp32", "x3", "t5"])
@@ -152,14 +175,15 @@ def test_train_step_matches_oracle(native_lib, n_layers, shape, loss, engine):
     arch, v, t = _trainer(n_layers, loss=dict({"ssim_multiplier": 0.0}, **loss), engine=engine)
     x = np.random.default_rng(n_layers).integers(0, 256, size=shape, dtype=np.uint8)
     clean, noisy = C.corrupt(x, 11, 0, C.NoiseConfig())
-    ref = O.train_step(v, clean, noisy, **loss)
     total, model_loss, dl, grads = t.train_step_single_gpu(torch.from_numpy(clean).cuda(), torch.from_numpy(noisy).cuda())
+    ref, n_flips = _oracle_with_kernel_relu_masks(t, v, clean, noisy, loss, n_layers)
     assert total == pytest.approx(ref["total"], rel=1e-5)
     assert dl["total_loss"] == pytest.approx(ref["denoiser_total"], rel=1e-5)
     assert dl["mae_loss"] == pytest.approx(ref["mae"], rel=1e-5)
     assert model_loss["regularization_loss"] == pytest.approx(ref["reg"], rel=1e-5)
     assert dl["ssim_loss"] == pytest.approx(ref["ssim"], rel=1e-5, abs=1e-7)
-    _grad_check(grads.cpu().numpy(), ref["grads"], arch, engine)
+    cos, worst = _grad_check(grads.cpu().numpy(), ref["grads"], arch)
+    print(f"[{engine}] N={n_layers} {shape}: cosine {cos:.8f}, worst per-variable error {worst:.2e}, {n_flips} ambiguous ReLU units")
     # BN moving statistics (momentum 0.995, unbiased variance)
     new = t.get_weights()
     for i, (m, var) in enumerate(ref["new_moving"]):
@@ -179,7 +203,10 @@ def test_train_step_golden_and_base_kernel_7(native_lib):
     assert total == pytest.approx(float(z["train_total"]), rel=1e-5)
     g, r = grads.cpu().numpy().astype(np.float64), z["train_grads"].astype(np.float64)
     assert float(g @ r / np.linalg.norm(g) / np.linalg.norm(r)) >= 0.9999
-    assert np.abs(g - r).max() <= 2e-2 * np.abs(r).max()
+    assert np.abs(g - r).max() <= 2e-2 * np.abs(r).max()     # the committed vector knows nothing about ambiguous ReLUs ...
+    lk0 = {k: loss[k] for k in ("hinge", "cutoff", "mae_multiplier", "mse_multiplier", "regularization")}
+    ref0, _ = _oracle_with_kernel_relu_masks(t, v, z["train_clean"], z["train_noisy"], lk0, 3)
+    _grad_check(g, ref0["grads"], arch)                      # ... with the kernels' masks the 1e-3 gate holds
     assert all(np.array_equal(a, b) for a, b in zip(t.get_weights(), v))     # update_moving=False leaves variables alone
     t.close()
     # k0 = 7 (every in-tree resnet config uses 7, SURVEY 8 notation)
@@ -190,6 +217,7 @@ def test_train_step_golden_and_base_kernel_7(native_lib):
     ref = O.train_step(v, clean, noisy, **lk)
     total, _, _, grads = t.train_step_single_gpu(torch.from_numpy(clean).cuda(), torch.from_numpy(noisy).cuda())
     assert total == pytest.approx(ref["total"], rel=1e-5)
+    ref, _ = _oracle_with_kernel_relu_masks(t, v, clean, noisy, lk, 1)
     _grad_check(grads.cpu().numpy(), ref["grads"], arch)
     t.close()
 
