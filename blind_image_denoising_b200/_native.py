@@ -14,11 +14,9 @@ from .arch import CArch
 
 _LIB_PATH = Path(__file__).resolve().parent / "libbfcnn_b200.so"
 
-PREC_FP32, PREC_F16, PREC_F16X3, PREC_F16_MMA_SYNC, PREC_F16X3_MMA_SYNC = 0, 1, 2, 3, 4
+PREC_FP32, PREC_F16, PREC_F16X3 = 0, 1, 2
 # no "bf16" alias: the tensor-core arm computes with fp16 operands (10 mantissa bits, not bf16's 7)
-PRECISIONS = {"fp32": PREC_FP32, "f16": PREC_F16, "fp16": PREC_F16,
-              "f16x3": PREC_F16X3, "fp16x3": PREC_F16X3, "f16_mma_sync": PREC_F16_MMA_SYNC,
-              "f16x3_mma_sync": PREC_F16X3_MMA_SYNC}
+PRECISIONS = {"fp32": PREC_FP32, "f16": PREC_F16, "fp16": PREC_F16, "f16x3": PREC_F16X3, "fp16x3": PREC_F16X3}
 FLAG_IN_DEVICE, FLAG_OUT_DEVICE, FLAG_NO_PAD_POW2, FLAG_IN_F32 = 1, 2, 4, 8
 
 # every symbol include/bfcnn_b200.h declares (tests check the library exports all of them)

@@ -54,6 +54,7 @@ int run_stack(bfcnn_handle* h, const uint8_t* d_in, bool in_u8, void* d_out, boo
     BF_CHECK(h->ws_feat[1].reserve(feat));
     float* X = h->ws_feat[0].as<float>();
     float* T = h->ws_feat[1].as<float>();
+    h->feat_tag[0] = h->feat_tag[1] = 0ull;   // the buffers no longer hold a streaming stack's layout
     BF_CHECK(launch_base_conv(h, d_in, in_u8, X, h->d_base_f32.as<float>(), e, st));
     for (int i = 0; i < h->arch.no_layers; ++i) {
       const float* wa = h->d_conv_f32.as<float>() + (size_t)(2 * i) * 9 * C * C;
@@ -64,18 +65,15 @@ int run_stack(bfcnn_handle* h, const uint8_t* d_in, bool in_u8, void* d_out, boo
     }
     return launch_head(h, X, d_out, out_u8, h->d_head_f32.as<float>(), e, st);
   }
-  if (precision == BFCNN_PREC_F16) return run_fused_stack_umma(h, d_in, d_out, out_u8, e, st);
-  if (precision == BFCNN_PREC_F16X3) return run_fused_stack_umma_x3(h, d_in, d_out, out_u8, e, st);
-  return run_fused_stack(h, d_in, d_out, out_u8, e, precision == BFCNN_PREC_F16_MMA_SYNC ? BFCNN_PREC_F16 : BFCNN_PREC_F16X3, st);
+  if (precision == BFCNN_PREC_F16) return run_fused_stack_stream(h, d_in, d_out, out_u8, e, st);
+  return run_fused_stack_stream_x3(h, d_in, d_out, out_u8, e, st);
 }
 
 int denoise_impl(bfcnn_handle* h, const uint8_t* in, void* out, bool out_u8, int n, int height, int width,
                  int precision, uint32_t flags, void* stream) {
   BF_REQUIRE(h != nullptr, "handle is NULL");
   BF_CHECK(check_images(n, height, width));
-  BF_REQUIRE(precision == BFCNN_PREC_FP32 || precision == BFCNN_PREC_F16 || precision == BFCNN_PREC_F16X3 ||
-                 precision == BFCNN_PREC_F16_MMA_SYNC || precision == BFCNN_PREC_F16X3_MMA_SYNC,
-             "unknown precision");
+  BF_REQUIRE(precision == BFCNN_PREC_FP32 || precision == BFCNN_PREC_F16 || precision == BFCNN_PREC_F16X3, "unknown precision");
   const size_t npx = (size_t)n * height * width;
   if (npx == 0) return BFCNN_OK;  // empty batch / empty image: nothing to do
   // float32 input (the hydra model's own signature, model.py:100-102: the normaliser clips to [0,255]) runs on the
@@ -242,7 +240,7 @@ void bfcnn_destroy(bfcnn_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   h->d_vars.release(); h->d_base_f32.release(); h->d_conv_f32.release(); h->d_bias_f32.release();
-  h->d_head_f32.release(); h->d_conv_frag.release(); h->d_base_frag.release(); h->d_conv_umma.release(); h->d_conv_umma_x3.release();
+  h->d_head_f32.release(); h->d_conv_umma.release(); h->d_conv_umma_x3.release();
   h->ws_in.release(); h->ws_out.release();
   for (auto& b : h->ws_feat) b.release();
   h->ws_train.release(); h->ws_stats.release(); h->ws_grads.release();

@@ -85,8 +85,6 @@ struct bfcnn_handle {
   bfcnn::DevBuf d_conv_f32;   // [2N][9][16 cin][16 cout], conv_b folded with BN scale
   bfcnn::DevBuf d_bias_f32;   // [2N][16], zero for conv_a, BN constant for conv_b
   bfcnn::DevBuf d_head_f32;   // [16][4] collapsed head (4th column zero)
-  bfcnn::DevBuf d_conv_frag;  // HMMA B fragments: [2N][hi/lo][9][2][32] uint2
-  bfcnn::DevBuf d_base_frag;  // HMMA B fragments of the base conv (K padded to 32)
   bfcnn::DevBuf d_conv_umma_x3; // the same with a lo part: [2N][hi/lo][dx 3][N 48][K 16] fp16
   bfcnn::DevBuf d_conv_umma;  // tcgen05 B operands: [2N][dx 3][N 48 = (dy, cout)][K 16] fp16, K-major core matrices
   bool packed_valid = false;
@@ -94,6 +92,10 @@ struct bfcnn_handle {
   // workspaces
   bfcnn::DevBuf ws_in, ws_out;          // staging for host<->device images
   bfcnn::DevBuf ws_feat[3];             // feature maps
+  // what ws_feat[0 / 1] currently hold: the streaming stacks zero the separator columns of their virtual-row layout once
+  // per (buffer, geometry) and skip it while the tag still matches (a 2-D memset of ~9000 32-byte rows cost ~0.35 ms per
+  // buffer and call on 4K frames); every other user of the buffers resets the tag to 0
+  unsigned long long feat_tag[2] = {0ull, 0ull};
   bfcnn::DevBuf ws_train;               // saved activations for backward
   bfcnn::DevBuf ws_stats;               // BN batch statistics, reductions
   bfcnn::DevBuf ws_grads;               // scratch gradients
@@ -120,6 +122,14 @@ struct bfcnn_handle {
 
 namespace bfcnn {
 int pack_weights(bfcnn_handle* h);  // host fold + upload (host_pack.cu)
+// identity of a streaming stack's feature-map layout in a workspace buffer (engine, allocation, geometry); never 0
+inline unsigned long long feat_layout_tag(int engine, const void* ptr, const Extent& e) {
+  unsigned long long t = 1469598103934665603ull;
+  const unsigned long long parts[5] = {(unsigned long long)engine, (unsigned long long)(uintptr_t)ptr, (unsigned long long)e.n,
+                                       (unsigned long long)e.he, (unsigned long long)e.we};
+  for (unsigned long long v : parts) { t ^= v; t *= 1099511628211ull; }
+  return t | 1ull;
+}
 // per-launch timing hooks (no-ops unless bfcnn_set_kernel_timing switched them on)
 inline void ktime_begin(bfcnn_handle* h, cudaStream_t st, int kind) {
   if (!h->ktime_on) return;

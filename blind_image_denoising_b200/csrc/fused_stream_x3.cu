@@ -542,19 +542,20 @@ int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out,
   BF_CHECK(h->ws_feat[1].reserve(feat_halves * 2 * sizeof(__half)));   // hi part, then lo part
   if (passes > 1) BF_CHECK(h->ws_feat[0].reserve(feat_halves * 2 * sizeof(__half)));
   // the separator columns sit at a regular stride of (we + 1) pixels, in the hi and in the lo part: zero them in both maps
-  // (nothing else writes
-  // them); the last one lies outside the tensor map, where the TMA fills in zeros, so one image needs no memset
-  for (int k = (passes > 1 ? 0 : 1); k < 2 && e.n > 1; ++k)
+  // (nothing else writes them); the last one lies outside the tensor map, where the TMA fills in zeros, so one image needs
+  // no memset.  Once per buffer and geometry (feat_tag), see fused_stream.cu.
+  for (int k = (passes > 1 ? 0 : 1); k < 2 && e.n > 1; ++k) {
+    const unsigned long long tag = feat_layout_tag(2, h->ws_feat[k].p, e);
+    if (h->feat_tag[k] == tag) continue;
     for (int part = 0; part < 2; ++part)
       BF_CUDA(cudaMemset2DAsync(h->ws_feat[k].as<__half>() + part * feat_halves + (size_t)e.we * C, (size_t)(e.we + 1) * C * sizeof(__half), 0,
                                 C * sizeof(__half), (size_t)e.he * e.n, st));
+    h->feat_tag[k] = tag;
+  }
   // pass "-1": base conv (hi + lo) into ws_feat[1] (pass ps reads ws_feat[(ps-1)&1], writes ws_feat[ps&1])
   h->ktime_n = 0;
   ktime_begin(h, st, 0);
-  if (h->arch.base_kernel == 3 && !getenv("BFCNN_BASE_FFMA"))   // tensor-core base conv (fused_umma.cu), hi + lo outputs
-    BF_CHECK(launch_base_conv_f16(h, d_in, h->ws_feat[1].as<__half>(), e, st, h->ws_feat[1].as<__half>() + feat_halves, e.we + 1, vw));
-  else
-    BF_CHECK(launch_base_conv_f16_x3(h, d_in, h->ws_feat[1].as<__half>(), h->ws_feat[1].as<__half>() + feat_halves, e, st, e.we + 1, vw));
+  BF_CHECK(launch_base_conv_f16(h, d_in, h->ws_feat[1].as<__half>(), e, st, h->ws_feat[1].as<__half>() + feat_halves, e.we + 1, vw));
   ktime_end(h, st);
   Extent e2 = e;   // what the TMA sees: two "images" (hi part, lo part) of he rows and vw columns
   e2.n = 2; e2.we = (int)vw - 1;

@@ -61,27 +61,6 @@ void VarLayout::build(const bfcnn_arch& a) {
   total = o; t_total = t;
 }
 
-// B fragment of mma.m16n8k16 (B is K x N "col"): lane holds
-//   reg0 = {B[2q][g], B[2q+1][g]}, reg1 = {B[2q+8][g], B[2q+9][g]},  g = lane>>2, q = lane&3
-// with K = cin, N = cout - 8*ntile.
-static void pack_frag(const float* w /*[16 cin][16 cout]*/, int ntile, uint32_t* dst /*[32][2]*/, bool lo) {
-  for (int lane = 0; lane < 32; ++lane) {
-    const int g = lane >> 2, q = lane & 3;
-    const int co = ntile * 8 + g;
-    __half hv[4];
-    const int ks[4] = {2 * q, 2 * q + 1, 2 * q + 8, 2 * q + 9};
-    for (int i = 0; i < 4; ++i) {
-      const float v = w[ks[i] * C + co];
-      const __half hi = __float2half_rn(v);
-      hv[i] = lo ? __float2half_rn(v - __half2float(hi)) : hi;
-    }
-    uint16_t b[4];
-    memcpy(b, hv, sizeof(b));
-    dst[lane * 2 + 0] = (uint32_t)b[0] | ((uint32_t)b[1] << 16);
-    dst[lane * 2 + 1] = (uint32_t)b[2] | ((uint32_t)b[3] << 16);
-  }
-}
-
 int pack_weights(bfcnn_handle* h) {
   const VarLayout& L = h->lay;
   const float* v = h->h_vars.data();
@@ -107,16 +86,7 @@ int pack_weights(bfcnn_handle* h) {
       head[ci * 4 + o] = (float)a;
     }
 
-  // HMMA fragments: [conv 2N][plane hi/lo][tap 9][ntile 2][lane 32][2] uint32
-  std::vector<uint32_t> frag((size_t)2 * N * 2 * 9 * 2 * 64);
-  for (int l = 0; l < 2 * N; ++l)
-    for (int pl = 0; pl < 2; ++pl)
-      for (int tap = 0; tap < 9; ++tap)
-        for (int nt = 0; nt < 2; ++nt)
-          pack_frag(&conv[((size_t)l * 9 + tap) * C * C], nt,
-                    &frag[((((size_t)l * 2 + pl) * 9 + tap) * 2 + nt) * 64], pl == 1);
-
-  // tcgen05 B operands (fused_umma.cu): per conv, per dx, N = 48 rows n = j*16 + cout with j <-> dy = 1 - j
+  // tcgen05 B operands (fused_stream.cu): per conv, per dx, N = 48 rows n = j*16 + cout with j <-> dy = 1 - j
   // (input row q feeds output rows q-1, q, q+1), K = 16 cin, SWIZZLE_NONE K-major core matrices:
   // byte offset(n, k) = (k/8)*768 + (n/8)*128 + (n%8)*16 + (k%8)*2
   std::vector<__half> umma((size_t)2 * N * 3 * 48 * 16);
@@ -152,7 +122,6 @@ int pack_weights(bfcnn_handle* h) {
   BF_CHECK(h->d_conv_f32.reserve(std::max<size_t>(conv.size(), 1) * sizeof(float)));
   BF_CHECK(h->d_bias_f32.reserve(std::max<size_t>(bias.size(), 1) * sizeof(float)));
   BF_CHECK(h->d_head_f32.reserve(head.size() * sizeof(float)));
-  BF_CHECK(h->d_conv_frag.reserve(std::max<size_t>(frag.size(), 1) * sizeof(uint32_t)));
   BF_CHECK(h->d_conv_umma.reserve(std::max<size_t>(umma.size(), 1) * sizeof(__half)));
   BF_CHECK(h->d_conv_umma_x3.reserve(std::max<size_t>(umma3.size(), 1) * sizeof(__half)));
   BF_CUDA(cudaMemcpy(h->d_vars.p, v, L.total * sizeof(float), cudaMemcpyHostToDevice));
@@ -160,7 +129,6 @@ int pack_weights(bfcnn_handle* h) {
   if (N > 0) {
     BF_CUDA(cudaMemcpy(h->d_conv_f32.p, conv.data(), conv.size() * sizeof(float), cudaMemcpyHostToDevice));
     BF_CUDA(cudaMemcpy(h->d_bias_f32.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
-    BF_CUDA(cudaMemcpy(h->d_conv_frag.p, frag.data(), frag.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     BF_CUDA(cudaMemcpy(h->d_conv_umma.p, umma.data(), umma.size() * sizeof(__half), cudaMemcpyHostToDevice));
     BF_CUDA(cudaMemcpy(h->d_conv_umma_x3.p, umma3.data(), umma3.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }

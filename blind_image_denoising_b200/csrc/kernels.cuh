@@ -34,31 +34,19 @@ int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float*
 int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, float* partial, int max_parts, const Extent& e,
                        float g_scale, int* parts_out, cudaStream_t st);
 
-// ---- fused_f16.cu: the fused tensor-core stack (F16 / F16X3)
-int run_fused_stack(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
-                    int precision, cudaStream_t st);
-
-// ---- fused_umma.cu: the fused stack on tcgen05 (UMMA, accumulators in TMEM), F16
-int run_fused_stack_umma(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
-                         cudaStream_t st);
+// ---- base_conv.cu: normalise + base conv into the fp16 NHWC16 map of the streaming stacks, and its TMA descriptor
 // fp16 NHWC16 feature map as a 5-D TMA tensor {ch8, half, x, y, n}, box = box_x pixels x box_y rows of one channel half
 int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e, int box_x, int box_y, long long row_px = 0);
-// feat_lo != nullptr (F16X3 stacks, k0 = 3 only): also the lo part of the hi/lo split
+// feat_lo != nullptr (F16X3 stack): also the lo part of the fp16 hi/lo split
 // img_stride / row_stride (pixels; 0 = the plain [n][he][we] map): where pixel (b, y, x) goes, b * img_stride + y * row_stride + x
 int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, const Extent& e, cudaStream_t st,
                          __half* feat_lo = nullptr, long long img_stride = 0, long long row_stride = 0);
-// ---- fused_stream.cu: the same arithmetic as a row-streaming pipeline (no vertical halo recompute); default F16 engine
+// ---- fused_stream.cu: the fused conv-BN-ReLU stack on tcgen05 as a row-streaming pipeline, F16 arithmetic
 int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                            cudaStream_t st);
-// ---- fused_umma_x3.cu: the same stack in the F16X3 arithmetic (fp16 hi/lo operand parts, FP32-grade)
-int run_fused_stack_umma_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
-                            cudaStream_t st);
-
-// ---- fused_stream_x3.cu: the row-streaming pipeline in the F16X3 arithmetic (default engine of precision f16x3)
+// ---- fused_stream_x3.cu: the same pipeline in the F16X3 arithmetic (fp16 hi/lo operand parts, FP32-grade)
 int run_fused_stack_stream_x3(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                               cudaStream_t st);
-int launch_base_conv_f16_x3(bfcnn_handle* h, const uint8_t* d_in, __half* hi, __half* lo, const Extent& e, cudaStream_t st,
-                            long long img_stride = 0, long long row_stride = 0);
 
 // ---- train.cu
 int run_corrupt(bfcnn_handle* h, const uint8_t* clean_u8, float* clean_f32, float* noisy_f32, int n,

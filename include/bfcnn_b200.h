@@ -46,9 +46,7 @@ typedef enum bfcnn_status {
 typedef enum bfcnn_precision {
   BFCNN_PREC_FP32 = 0,   /* FP32 FFMA, layer by layer: the reference-grade path            */
   BFCNN_PREC_F16 = 1,    /* fused stack on tcgen05 (UMMA, TMEM accumulators): fp16 operands, fp32 accumulate */
-  BFCNN_PREC_F16X3 = 2,  /* fused stack on tcgen05, fp16 hi/lo split of activations and weights (3 MMAs per product): fp32-grade */
-  BFCNN_PREC_F16_MMA_SYNC = 3,   /* the F16 arithmetic on the legacy mma.sync path (comparison baseline)   */
-  BFCNN_PREC_F16X3_MMA_SYNC = 4  /* the F16X3 arithmetic on the legacy mma.sync path (comparison baseline) */
+  BFCNN_PREC_F16X3 = 2   /* fused stack on tcgen05, fp16 hi/lo split of activations and weights (3 MMAs per product): fp32-grade */
 } bfcnn_precision;
 
 /* Flags of bfcnn_denoise_*. */

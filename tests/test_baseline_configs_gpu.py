@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 
 GATES = {"fp32": (0.5, 0.05), "f16x3": (0.5, 0.05), "f16": (2.0, 0.25)}
 # ~2x the errors measured on B200 for the DEEPEST model (N = 18, GPUTEST of round 2; shallower models sit below)
-TIGHT = {"fp32": (0.02, 0.002), "f16x3": (0.02, 0.002), "f16": (1.0, 0.12)}
+# measured (GPUTEST r02a): f16 at N = 18 max-abs 0.78-0.88 / mean-abs 0.070-0.072 (N = 6: 0.18 / 0.020; N = 12: 0.42 / 0.046);
+# f16x3 at N = 18 0.0011 / 0.00013; fp32 0.0003 / 0.00003
+TIGHT = {"fp32": (0.01, 0.001), "f16x3": (0.01, 0.001), "f16": (1.6, 0.14)}
 
 
 def _vars(n_layers):

@@ -123,9 +123,17 @@ def test_accumulate_equals_one_big_batch_up_to_bn_statistics(native_lib):
     assert torch.allclose(a._accum, gs[0] + gs[1] + gs[2])
     a.apply_grads(None)
     _, _, _, g = b.train_step_single_gpu(clean, noisy, update_moving=False)
+    assert float((a._accum / 3 - g).abs().max()) <= 1e-4 * float(g.abs().max())
     b.apply_grads(g)
-    for wa, wb in zip(a.get_weights(), b.get_weights()):
-        assert np.allclose(wa, wb, rtol=1e-5, atol=1e-7)
+    # Adam's first update is lr * g / (|g| + eps): where the gradient is (numerically) zero the sign of a 1e-6 run-to-run
+    # difference (the BN statistics are reduced with atomics) decides the step, so compare where the gradient is not tiny
+    from blind_image_denoising_b200.weights import flatten_variables, gather_trainables
+    wa = gather_trainables(arch, flatten_variables(arch, a.get_weights()))
+    wb = gather_trainables(arch, flatten_variables(arch, b.get_weights()))
+    w0 = gather_trainables(arch, flatten_variables(arch, v))
+    solid = (g.abs() > 1e-3 * g.abs().max()).cpu().numpy()
+    assert solid.mean() > 0.5 and np.allclose(wa[solid], wb[solid], rtol=1e-5, atol=1e-6)
+    assert np.allclose(np.abs(wa[solid] - w0[solid]), 1e-2, rtol=1e-2)      # the 1/k scale does not change a first Adam step
     assert not np.array_equal(a.get_weights()[1], v[1])
     # the accumulator restarts from zero for the next update
     _, _, _, g = a.train_step_single_gpu(clean, noisy, update_moving=False)

@@ -1,4 +1,4 @@
-"""Random-shape sweep of the streaming F16 / F16X3 stacks (against the mma.sync stacks, same arithmetic class) and of the tcgen05
+"""Random-shape sweep of the streaming F16 / F16X3 stacks (against the layer-by-layer FP32 path) and of the tcgen05
 training conv (against the FFMA conv): python tools/fuzz_shapes.py [cases] [seed]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,37 +10,22 @@ cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 lib = _native.load_library()
 models = {}
-worst = 0
+worst, worst3 = 0, 0
 for t in range(cases):
     nl = int(rng.choice([1, 2, 3, 6, 12]))
     n, h, w = int(rng.integers(1, 5)), int(rng.integers(1, 320)), int(rng.integers(1, 420))
     pad = bool(rng.integers(0, 2))
     if nl not in models:
-        models[nl] = (bf.synthetic_model(nl, precision="f16"), bf.synthetic_model(nl, precision="f16_mma_sync"))
-    a, b = models[nl]
+        models[nl] = bf.synthetic_model(nl, precision="f16")
+    a = models[nl]
     x = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
-    ya, yb = a(x, pad_pow2=pad), b(x, pad_pow2=pad)
-    d = np.abs(ya.astype(int) - yb.astype(int))
-    worst = max(worst, int(d.max()))
-    assert d.max() <= 2, (nl, n, h, w, pad, int(d.max()))
+    ya, yx, yf = a(x, pad_pow2=pad), a(x, pad_pow2=pad, precision="f16x3"), a(x, pad_pow2=pad, precision="fp32")
+    d, d3 = np.abs(ya.astype(int) - yf.astype(int)), np.abs(yx.astype(int) - yf.astype(int))
+    worst, worst3 = max(worst, int(d.max())), max(worst3, int(d3.max()))
+    assert d.max() <= 3 and d3.max() <= 1, (nl, n, h, w, pad, int(d.max()), int(d3.max()))
     assert np.array_equal(ya, a(x, pad_pow2=pad))
-print(f"inference: {cases} random shapes ok (max u8 difference to the mma.sync stack {worst})", flush=True)
-# the f16x3 streaming stack against the f16x3 mma.sync stack (both FP32-grade: pre-round outputs agree to ~1e-3)
-models3, worst3 = {}, 0.0
-for t in range(cases // 2):
-    nl = int(rng.choice([1, 2, 3, 6]))
-    n, h, w = int(rng.integers(1, 6)), int(rng.integers(1, 200)), int(rng.integers(1, 300))
-    pad = bool(rng.integers(0, 2))
-    if nl not in models3:
-        models3[nl] = (bf.synthetic_model(nl, precision="f16x3"), bf.synthetic_model(nl, precision="f16x3_mma_sync"))
-    a, b = models3[nl]
-    x = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
-    ya, yb = a(x, pad_pow2=pad, return_float=True), b(x, pad_pow2=pad, return_float=True)
-    d = float(np.abs(ya - yb).max())
-    worst3 = max(worst3, d)
-    assert d <= 0.02 and not np.isnan(ya).any(), (nl, n, h, w, pad, d)
-print(f"inference f16x3: {cases // 2} random shapes ok (max pre-round difference to the mma.sync stack {worst3:.5f})", flush=True)
-m = models[next(iter(models))][0]
+print(f"inference: {cases} random shapes ok (max u8 difference to the FP32 path: f16 {worst}, f16x3 {worst3})", flush=True)
+m = models[next(iter(models))]
 for t in range(cases):
     n, h, w = int(rng.integers(1, 4)), int(rng.integers(1, 200)), int(rng.integers(1, 300))
     x = torch.tensor(rng.standard_normal((n, h, w, 16)), dtype=torch.float32).cuda()

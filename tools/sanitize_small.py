@@ -6,7 +6,7 @@ import blind_image_denoising_b200 as bf
 from blind_image_denoising_b200 import _native
 from blind_image_denoising_b200.training import Trainer
 x = np.random.default_rng(0).integers(0, 256, size=(2, 70, 150, 3), dtype=np.uint8)
-for prec in ("f16", "f16_mma_sync", "f16x3", "fp32"):
+for prec in ("f16", "f16x3", "fp32"):
     m = bf.synthetic_model(4, precision=prec)
     y = m(x); yf = m(torch.from_numpy(x).cuda(), return_float=True)
     m.close()
