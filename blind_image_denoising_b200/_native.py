@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "bfcnn_num_trainable", "bfcnn_create", "bfcnn_destroy", "bfcnn_set_weights",
     "bfcnn_get_weights", "bfcnn_denoise_u8", "bfcnn_denoise_f32", "bfcnn_launch_count",
     "bfcnn_last_stack_ms", "bfcnn_set_kernel_timing", "bfcnn_kernel_times", "bfcnn_corrupt", "bfcnn_loss", "bfcnn_train_step", "bfcnn_train_losses", "bfcnn_saved_activation", "bfcnn_downscale2x",
-    "bfcnn_adam_step", "bfcnn_conv3x3", "bfcnn_set_train_engine",
+    "bfcnn_allreduce_grads", "bfcnn_adam_step", "bfcnn_conv3x3", "bfcnn_set_train_engine",
 ]
 
 
@@ -115,6 +115,8 @@ def load_library() -> ctypes.CDLL:
     lib.bfcnn_set_train_engine.restype = c_int
     lib.bfcnn_conv3x3.argtypes = [H, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.bfcnn_conv3x3.restype = c_int
+    lib.bfcnn_allreduce_grads.argtypes = [H, c_void_p, c_void_p, c_void_p]
+    lib.bfcnn_allreduce_grads.restype = c_int
     lib.bfcnn_adam_step.argtypes = [H, c_void_p, c_float, POINTER(AdamCfg), c_int64, c_void_p]
     lib.bfcnn_adam_step.restype = c_int
     if lib.bfcnn_abi_version() != 3:

@@ -1,4 +1,5 @@
 // api.cu -- the extern "C" surface of libbfcnn_b200.so (include/bfcnn_b200.h)
+#include <dlfcn.h>
 #include <math.h>
 #include <string.h>
 
@@ -314,11 +315,15 @@ int bfcnn_set_kernel_timing(bfcnn_handle* h, int on) {
 int bfcnn_kernel_times(bfcnn_handle* h, float* ms, int* kinds, int capacity, int* count) {
   BF_REQUIRE(h != nullptr && ms != nullptr && kinds != nullptr && count != nullptr, "NULL argument");
   BF_CUDA(cudaSetDevice(h->device));
-  const int n = std::min(h->ktime_n, capacity);
-  for (int i = 0; i < n; ++i) {
+  int n = 0;
+  for (int i = 0; i < h->ktime_n && n < capacity; ++i) {
     BF_CUDA(cudaEventSynchronize(h->ktime_ev[2 * i + 1]));
-    BF_CUDA(cudaEventElapsedTime(&ms[i], h->ktime_ev[2 * i], h->ktime_ev[2 * i + 1]));
-    kinds[i] = h->ktime_kind[i];
+    if (i > 0 && n + 1 < capacity) {   // idle time on the stream between the previous launch and this one
+      BF_CUDA(cudaEventElapsedTime(&ms[n], h->ktime_ev[2 * i - 1], h->ktime_ev[2 * i]));
+      kinds[n++] = -1;
+    }
+    BF_CUDA(cudaEventElapsedTime(&ms[n], h->ktime_ev[2 * i], h->ktime_ev[2 * i + 1]));
+    kinds[n++] = h->ktime_kind[i];
   }
   *count = n;
   return BFCNN_OK;
@@ -404,6 +409,39 @@ int bfcnn_conv3x3(bfcnn_handle* h, const float* in, const float* weights, float*
   if (engine == 2) return launch_conv3x3_t5(h, in, out, weights, nullptr, nullptr, epi, e, 64.0f, st);
   set_error("invalid argument: engine must be 0 (FP32 FFMA), 1 (mma.sync hi/lo split) or 2 (tcgen05 hi/lo split)");
   return BFCNN_ERR_INVALID_ARGUMENT;
+}
+
+// NCCL is bound at run time (dlopen): the library has no link-time dependency on it, inference-only users never load it,
+// and inside a PyTorch process the already loaded libnccl.so.2 (the one torch.distributed uses) is the one that is found.
+namespace {
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+nccl_allreduce_fn g_nccl_allreduce = nullptr;
+nccl_errstr_fn g_nccl_errstr = nullptr;
+int load_nccl() {
+  if (g_nccl_allreduce) return BFCNN_OK;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { set_error("libnccl.so.2 cannot be loaded: %s", dlerror()); return BFCNN_ERR_UNSUPPORTED; }
+  g_nccl_errstr = (nccl_errstr_fn)dlsym(lib, "ncclGetErrorString");
+  g_nccl_allreduce = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
+  if (!g_nccl_allreduce) { set_error("libnccl has no ncclAllReduce"); return BFCNN_ERR_UNSUPPORTED; }
+  return BFCNN_OK;
+}
+}  // namespace
+
+int bfcnn_allreduce_grads(bfcnn_handle* h, float* flat_grads, void* nccl_comm, void* stream) {
+  BF_REQUIRE(h != nullptr && flat_grads != nullptr && nccl_comm != nullptr, "NULL argument");
+  BF_CUDA(cudaSetDevice(h->device));
+  BF_CHECK(load_nccl());
+  // one in-place sum over the flat gradient (<= 84 272 floats, latency-bound: one buffer, one collective, the compute
+  // stream); the 1/world average is the grad_scale of bfcnn_adam_step
+  const int r = g_nccl_allreduce(flat_grads, flat_grads, h->lay.t_total, /*ncclFloat32*/ 7, /*ncclSum*/ 0, nccl_comm, (cudaStream_t)stream);
+  if (r != 0) {
+    set_error("ncclAllReduce failed: %s", g_nccl_errstr ? g_nccl_errstr(r) : "unknown NCCL error");
+    return BFCNN_ERR_CUDA;
+  }
+  return BFCNN_OK;
 }
 
 int bfcnn_adam_step(bfcnn_handle* h, const float* flat_grads, float grad_scale, const bfcnn_adam_cfg* cfg,

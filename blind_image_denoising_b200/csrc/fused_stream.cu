@@ -334,6 +334,12 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+  // Programmatic dependent launch (host side: cudaLaunchAttributeProgrammaticStreamSerialization).  Everything above read
+  // only constants of the model; from here on the feature maps of the previous kernel are read (TMA) and the buffer it read
+  // from is overwritten, so wait for it to complete -- after telling the scheduler that the NEXT kernel's CTAs may be
+  // placed as soon as ours exit (they will wait at this same point).
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
   if (tr && tid == 0) p.trace[257] = clock64();
 
   if (warp < EPI_WARPS) {
@@ -650,8 +656,19 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
     CUtensorMap tmap;
     BF_CHECK(make_feature_tmap(&tmap, p.fin, ev, RW, 2, vw));
     ktime_begin(h, st, last ? 2 : 1);
-    if (last) stream_pass_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
-    else stream_pass_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(p, tmap);
+    {
+      // programmatic dependent launch: the CTAs of this pass take their SMs as the previous kernel's CTAs exit and run
+      // their prologue (barriers, TMEM, weights, zeroed rings) while its tail is still working; griddepcontrol.wait in the
+      // kernel holds every access to the feature maps until the previous kernel has completed
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      if (last) BF_CUDA(cudaLaunchKernelEx(&cfg, stream_pass_kernel<true>, p, tmap));
+      else BF_CUDA(cudaLaunchKernelEx(&cfg, stream_pass_kernel<false>, p, tmap));
+    }
     ktime_end(h, st);
     h->launches++;
     BF_CUDA(cudaGetLastError());

@@ -79,7 +79,8 @@ class Denoiser:
         _native.check(self._lib.bfcnn_set_kernel_timing(self._h, int(bool(on))))
 
     def kernel_times(self):
-        """[(kind, ms)] of the last timed call; kind 0 = base conv, 1 = pass, 2 = last pass."""
+        """[(kind, ms)] of the last timed call; kind 0 = base conv, 1 = pass, 2 = last pass, -1 = idle gap between two
+        launches."""
         ms = (ctypes.c_float * 128)()
         kinds = (ctypes.c_int * 128)()
         cnt = ctypes.c_int()

@@ -77,3 +77,70 @@ def allreduce_mean_(tensor, group=None):
             dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
             tensor.div_(world)
     return tensor
+
+
+class NcclCommunicator:
+    """A raw `ncclComm_t` for the C-ABI gradient exchange (`bfcnn_allreduce_grads`), created with ctypes on the
+    libnccl.so.2 already loaded in the process (PyTorch's).  Non-PyTorch hosts pass their own ncclComm_t to the C ABI;
+    this class exists so that the Python `Trainer` can drive the same entry point instead of `torch.distributed`.
+
+    `NcclCommunicator.from_torch_group()` makes rank 0 draw the unique id and shares it through the (already
+    initialised) torch.distributed group; `NcclCommunicator(rank, world, unique_id)` takes the 128 id bytes directly."""
+
+    def __init__(self, rank: int, world: int, unique_id: bytes, device: int = 0):
+        import ctypes
+        import torch
+        self._lib = self._load()
+
+        class _Id(ctypes.Structure):
+            _fields_ = [("internal", ctypes.c_char * 128)]
+        if len(unique_id) != 128:
+            raise ValueError("an ncclUniqueId is 128 bytes")
+        uid = _Id()
+        ctypes.memmove(ctypes.byref(uid), unique_id, 128)
+        self._lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _Id, ctypes.c_int]
+        self._lib.ncclCommInitRank.restype = ctypes.c_int
+        self.comm = ctypes.c_void_p()
+        torch.cuda.set_device(device)
+        r = self._lib.ncclCommInitRank(ctypes.byref(self.comm), int(world), uid, int(rank))
+        if r != 0:
+            raise RuntimeError(f"ncclCommInitRank failed with ncclResult {r}")
+        self.rank, self.world = int(rank), int(world)
+
+    @staticmethod
+    def _load():
+        import ctypes
+        import torch  # noqa: F401  (loads the bundled libnccl.so.2 into the process)
+        for name in ("libnccl.so.2", "libnccl.so"):
+            try:
+                return ctypes.CDLL(name, mode=ctypes.RTLD_GLOBAL)
+            except OSError:
+                continue
+        raise ImportError("libnccl.so.2 not found")
+
+    @classmethod
+    def unique_id(cls) -> bytes:
+        import ctypes
+        lib = cls._load()
+        buf = ctypes.create_string_buffer(128)
+        lib.ncclGetUniqueId.argtypes = [ctypes.c_void_p]
+        lib.ncclGetUniqueId.restype = ctypes.c_int
+        r = lib.ncclGetUniqueId(buf)
+        if r != 0:
+            raise RuntimeError(f"ncclGetUniqueId failed with ncclResult {r}")
+        return buf.raw
+
+    @classmethod
+    def from_torch_group(cls, device: int, group=None) -> "NcclCommunicator":
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(rank, world, box[0], device=device)
+
+    def close(self):
+        import ctypes
+        if getattr(self, "comm", None):
+            self._lib.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+            self._lib.ncclCommDestroy(self.comm)
+            self.comm = None

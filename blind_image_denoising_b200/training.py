@@ -98,12 +98,15 @@ class Trainer:
 
     def __init__(self, arch: Arch, variables: Sequence[np.ndarray], *, device: int = 0,
                  loss_config: Optional[Dict] = None, optimizer_config: Optional[Dict] = None,
-                 process_group=None, conv_engine: str = "t5"):
+                 process_group=None, conv_engine: str = "t5", nccl_comm=None):
         torch = _torch()
         self._lib = _native.load_library()
         self.arch = arch
         self.device = int(device)
         self.process_group = process_group
+        # a distributed.NcclCommunicator: the gradient exchange then goes through the C ABI (bfcnn_allreduce_grads, a raw
+        # ncclAllReduce on the compute stream) instead of torch.distributed
+        self.nccl_comm = nccl_comm
         flat = np.ascontiguousarray(flatten_variables(arch, variables), dtype=np.float32)
         carch = arch.to_c()
         h = ctypes.c_void_p()
@@ -314,7 +317,10 @@ class Trainer:
         if divisor is not None:
             k = float(divisor)
         world = 1
-        if dist.is_available() and dist.is_initialized():
+        if self.nccl_comm is not None:
+            world = self.nccl_comm.world
+            _native.check(self._lib.bfcnn_allreduce_grads(self._h, grads.data_ptr(), self.nccl_comm.comm, _stream_ptr(self.device)))
+        elif dist.is_available() and dist.is_initialized():
             world = dist.get_world_size(self.process_group)
             if world > 1:
                 dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=self.process_group)

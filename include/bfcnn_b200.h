@@ -140,7 +140,8 @@ int bfcnn_last_stack_ms(bfcnn_handle* h, float* ms);
 
 /* Per-launch device times of the conv-stack kernels of the LAST denoise call made with timing switched on (CUDA events
  * around every launch on the caller's stream; bench.py's roofline of the dominant kernel is measured with these inside
- * its own run).  kinds[i]: 0 = base conv, 1 = pass of the fused stack, 2 = last pass (head + encode fused in). */
+ * its own run).  kinds[i]: 0 = base conv, 1 = pass of the fused stack, 2 = last pass (head + encode fused in), -1 = the
+ * idle time on the stream between the launch before and the launch after this entry. */
 int bfcnn_set_kernel_timing(bfcnn_handle* h, int on);
 int bfcnn_kernel_times(bfcnn_handle* h, float* ms, int* kinds, int capacity, int* count);
 
@@ -199,6 +200,12 @@ int bfcnn_set_train_engine(bfcnn_handle* h, int engine);
  * with the fp16 hi/lo split (the engines of the training step); exposed so that the layer kernels can be tested in isolation. */
 int bfcnn_conv3x3(bfcnn_handle* h, const float* in, const float* weights, float* out, int n, int height, int width,
                   int engine, int relu, void* stream);
+
+/* The one exchange step of data-parallel training (the reference is single-device and accumulates micro-batches
+ * instead, train_loop.py:404-437): in-place ncclAllReduce(sum, float32) of the flat gradient over `nccl_comm` (an
+ * ncclComm_t of the caller, passed as void*) on `stream`.  Averaging is left to bfcnn_adam_step's grad_scale = 1/world.
+ * NCCL is dlopen'ed (libnccl.so.2) on first use; BFCNN_ERR_UNSUPPORTED if it is not installed. */
+int bfcnn_allreduce_grads(bfcnn_handle* h, float* flat_grads, void* nccl_comm, void* stream);
 
 /* replaces: optimizer.apply_gradients with keras Adam + global_clipnorm
  * (bfcnn/optimizer.py:145-224, bfcnn/train_loop.py:314-321, 421-434).  flat_grads is

@@ -254,3 +254,28 @@ def test_image_pipeline_batches(native_lib):
     other = [int(c[0, 0, 0]) for clean, _ in ds.training.epoch(1) for c in clean]
     assert again == seen and other != seen
     t.close()
+
+
+def test_c_abi_allreduce_single_rank(native_lib):
+    """bfcnn_allreduce_grads on a real ncclComm_t (one rank: the sum over ranks is the identity); bench.py's dp_check
+    exercises it over N ranks.  Also: a NULL communicator is an argument error, not a crash."""
+    import ctypes
+    import torch
+    import blind_image_denoising_b200 as bf
+    from blind_image_denoising_b200 import _native
+    from blind_image_denoising_b200.distributed import NcclCommunicator
+    from blind_image_denoising_b200.training import Trainer
+    arch = bf.Arch(no_layers=2)
+    comm = NcclCommunicator(0, 1, NcclCommunicator.unique_id(), device=0)
+    t = Trainer(arch, bf.synthetic_variables(arch, 0), nccl_comm=comm)
+    g = torch.randn(arch.num_trainable(), device="cuda")
+    g0 = g.clone()
+    _native.check(t._lib.bfcnn_allreduce_grads(t.handle, g.data_ptr(), comm.comm, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert torch.equal(g, g0)
+    w0 = t.get_weights()
+    t.apply_grads(g)                      # all-reduce through the C ABI, then Adam
+    assert not np.array_equal(t.get_weights()[1], w0[1])
+    assert t._lib.bfcnn_allreduce_grads(t.handle, g.data_ptr(), None, None) == -1      # BFCNN_ERR_INVALID_ARGUMENT
+    t.close()
+    comm.close()
