@@ -241,7 +241,7 @@ void bfcnn_destroy(bfcnn_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   h->d_vars.release(); h->d_base_f32.release(); h->d_conv_f32.release(); h->d_bias_f32.release();
-  h->d_head_f32.release(); h->d_conv_umma.release(); h->d_conv_umma_x3.release();
+  h->d_head_f32.release(); h->d_last_umma.release(); h->d_conv_umma.release(); h->d_conv_umma_x3.release();
   h->ws_in.release(); h->ws_out.release();
   for (auto& b : h->ws_feat) b.release();
   h->ws_train.release(); h->ws_stats.release(); h->ws_grads.release();

@@ -285,6 +285,11 @@ int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, con
   using namespace bconv;
   if (img_stride == 0) { img_stride = (long long)e.he * e.we; row_stride = e.we; }   // [n][he][we][16]
   const int k0 = h->arch.base_kernel, r0 = (k0 - 1) / 2;
+  // k0 = 3 into the virtual-row map of the streaming stacks: the tcgen05 kernel (base_conv_t5.cu); BFCNN_BASE_MMA_SYNC=1
+  // keeps the mma.sync kernel below for A/B runs
+  static const bool mma_sync = getenv("BFCNN_BASE_MMA_SYNC") != nullptr && atoi(getenv("BFCNN_BASE_MMA_SYNC")) != 0;
+  if (k0 == 3 && !mma_sync && img_stride == e.we + 1 && row_stride == (long long)e.n * (e.we + 1))
+    return launch_base_conv3_t5(h, d_in, feat, feat_lo, e, st);
   if (k0 == 3) {
     const int tx = (e.we + BM_W - 1) / BM_W, ty = (e.he + BM_H - 1) / BM_H;
     const long long tiles = (long long)tx * ty * e.n;

@@ -86,6 +86,7 @@ struct bfcnn_handle {
   bfcnn::DevBuf d_bias_f32;   // [2N][16], zero for conv_a, BN constant for conv_b
   bfcnn::DevBuf d_head_f32;   // [16][4] collapsed head (4th column zero)
   bfcnn::DevBuf d_conv_umma_x3; // the same with a lo part: [2N][hi/lo][dx 3][N 48][K 16] fp16
+  bfcnn::DevBuf d_last_umma;  // last conv_b with the collapsed head folded in [dx 3][N 48][K 16] + the head matrix [N 16][K 16] (fp16)
   bfcnn::DevBuf d_conv_umma;  // tcgen05 B operands: [2N][dx 3][N 48 = (dy, cout)][K 16] fp16, K-major core matrices
   bool packed_valid = false;
 

@@ -66,7 +66,9 @@ constexpr uint32_t BAR_MMA = 0, BAR_EPI = 2 * 4, BAR_XFULL = BAR_EPI + 2, BAR_XF
 constexpr uint32_t SM_BARS = 0, SM_TMEM = 512, SM_HEAD = 528, SM_BIAS = 784, SM_WTS = 1152;
 
 __host__ __device__ inline uint32_t plane_bytes_of(int rows) { return (uint32_t)(rows * RW + 2 * SLACK_PX) * 16u; }
-__host__ __device__ inline uint32_t rings_offset(int nl) { return (SM_WTS + (uint32_t)nl * W_LAYER_BYTES + 127u) & ~127u; }
+constexpr uint32_t HEAD_B_BYTES = 16 * 16 * 2;   // B operand of the head matrix [N 16][K 16] fp16 (last pass)
+__host__ __device__ inline uint32_t head_b_offset(int nl) { return SM_WTS + (uint32_t)nl * W_LAYER_BYTES; }
+__host__ __device__ inline uint32_t rings_offset(int nl) { return (head_b_offset(nl) + HEAD_B_BYTES + 127u) & ~127u; }
 __host__ __device__ inline uint32_t smem_bytes(int nl) {
   uint32_t b = rings_offset(nl) + 2 * plane_bytes_of(2 * K0) + 2 * plane_bytes_of(2 * KT);
   if (nl > 2) b += 2 * plane_bytes_of(2 * KX) + 2 * plane_bytes_of(2 * KT);
@@ -82,6 +84,7 @@ struct Params {
   int vw;                  // n * (we + 1)
   void* out;               // [n][h][w][3] uint8 or float
   const uint8_t* wumma;    // [2N][W_LAYER_BYTES]
+  const uint8_t* wlast;    // last pass: the final conv_b with the collapsed head folded in [W_LAYER_BYTES] + the head matrix [HEAD_B_BYTES]
   const float* bias;       // [2N][16]
   const float* whead;      // [16][4]
   int n, h, w, he, we;
@@ -170,6 +173,33 @@ template <int KIND, bool LAST_PASS>
 __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const EpiCtx& E, uint32_t bars, const float (&bias)[16],
                                          const float* s_head, const float* s_bias_l, int l, int rho, long long* tp = nullptr) {
   const uint32_t taddr = E.tq + (uint32_t)((rho + 14 * l) & 31) * 16u;
+  if (KIND == KIND_B_OUT && LAST_PASS) {
+    // Last layer of the model: the collapsed head is folded into this conv's weights and the residual came in through an
+    // MMA of its own (issuer), so accumulator columns 0..2 hold the pre-tanh head output of the pixel; add the head's
+    // share of the BN constant (bias[0..2]), tanh(2y)*0.51 + denormalise (model.py:342, utilities.py:435-443), store.
+    uint32_t y[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]) :: "memory");
+    tmem_zero16(taddr);
+    const bool inside_l = E.col_ok && ((unsigned)(E.y00 + rho) < (unsigned)E.he);
+    if (E.col_out && inside_l && rho >= E.nl && rho < E.P - E.nl && (E.y00 + rho) < E.h_img) {
+      const float r0o = head_activation_fast(__uint_as_float(y[0]) + bias[0]);
+      const float r1o = head_activation_fast(__uint_as_float(y[1]) + bias[1]);
+      const float r2o = head_activation_fast(__uint_as_float(y[2]) + bias[2]);
+      if (p.out_u8) {
+        uint8_t* d = E.out_col + (long long)rho * E.row_out;
+        d[0] = (uint8_t)__float2int_rn(r0o); d[1] = (uint8_t)__float2int_rn(r1o); d[2] = (uint8_t)__float2int_rn(r2o);
+      } else {
+        float* d = reinterpret_cast<float*>(E.out_col) + (long long)rho * E.row_out;
+        d[0] = r0o; d[1] = r1o; d[2] = r2o;
+      }
+    }
+    if (l == 1) {   // one block in this pass: the X0 row was the residual operand of the issuer's extra MMA, now complete
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(bars + (BAR_XFREE + (uint32_t)((E.gb0 + (rho >> 1)) % K0)) * 8);
+    }
+    return;
+  }
   uint32_t v[16];
   if (tp) tp[0] = clock64();
   tmem_ld16_issue(taddr, v);
@@ -203,42 +233,6 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
     const uint4 xa = lds128(xsrc), xb = lds128(xsrc + xplane);
     tmem_ld_wait(v);
     tmem_zero16(taddr);
-    if (KIND == KIND_B_OUT && LAST_PASS) {
-      // collapsed 1x1 head + tanh(2y)*0.51 + denormalise (+ round + uint8), accumulated channel pair by channel pair
-      // (the 19-warp CTA caps the kernel at 96 registers; bias and head weights stay in shared memory)
-      if (E.col_out && inside && rho >= E.nl && rho < E.P - E.nl && (E.y00 + rho) < E.h_img) {
-        // s_head is packed [16 ch][3] here (12 broadcast LDS.128 per thread) and the BN constant b' of the last conv_b
-        // enters as bias[0..2] = sum_ch b'[ch] w[ch][j], folded once per thread
-        const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-        float s0 = bias[0], s1 = bias[1], s2 = bias[2];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {   // 4 channels = 12 weights = 3 float4 per iteration
-          const float4 wa = *reinterpret_cast<const float4*>(s_head + 12 * q), wb = *reinterpret_cast<const float4*>(s_head + 12 * q + 4);
-          const float4 wc = *reinterpret_cast<const float4*>(s_head + 12 * q + 8);
-          const float2 x01 = unpack_h2(xs[2 * q]), x23 = unpack_h2(xs[2 * q + 1]);
-          const float f0 = __uint_as_float(v[4 * q]) + x01.x, f1 = __uint_as_float(v[4 * q + 1]) + x01.y;
-          const float f2 = __uint_as_float(v[4 * q + 2]) + x23.x, f3 = __uint_as_float(v[4 * q + 3]) + x23.y;
-          s0 = fmaf(f0, wa.x, s0); s1 = fmaf(f0, wa.y, s1); s2 = fmaf(f0, wa.z, s2);
-          s0 = fmaf(f1, wa.w, s0); s1 = fmaf(f1, wb.x, s1); s2 = fmaf(f1, wb.y, s2);
-          s0 = fmaf(f2, wb.z, s0); s1 = fmaf(f2, wb.w, s1); s2 = fmaf(f2, wc.x, s2);
-          s0 = fmaf(f3, wc.y, s0); s1 = fmaf(f3, wc.z, s1); s2 = fmaf(f3, wc.w, s2);
-        }
-        const float r0o = head_activation_fast(s0), r1o = head_activation_fast(s1), r2o = head_activation_fast(s2);
-        if (p.out_u8) {
-          uint8_t* d = E.out_col + (long long)rho * E.row_out;
-          d[0] = (uint8_t)__float2int_rn(r0o); d[1] = (uint8_t)__float2int_rn(r1o); d[2] = (uint8_t)__float2int_rn(r2o);
-        } else {
-          float* d = reinterpret_cast<float*>(E.out_col) + (long long)rho * E.row_out;
-          d[0] = r0o; d[1] = r1o; d[2] = r2o;
-        }
-      }
-      if (l == 1) {
-        fence_async_smem();
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + (BAR_XFREE + (uint32_t)((E.gb0 + (rho >> 1)) % K0)) * 8);
-      }
-      return;
-    }
     float f[16];
     {
       const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
@@ -316,8 +310,12 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(s0 + SM_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
-  for (int i = tid; i < nl * (W_LAYER_BYTES / 16); i += NTHREADS)
+  // last pass: layer nl - 1 takes the head-folded weights, and the head matrix follows the conv weights
+  for (int i = tid; i < (nl - (LAST_PASS ? 1 : 0)) * (W_LAYER_BYTES / 16); i += NTHREADS)
     reinterpret_cast<uint4*>(smem + SM_WTS)[i] = reinterpret_cast<const uint4*>(p.wumma + (size_t)(2 * p.blk0) * W_LAYER_BYTES)[i];
+  if (LAST_PASS)
+    for (int i = tid; i < (int)((W_LAYER_BYTES + HEAD_B_BYTES) / 16); i += NTHREADS)
+      reinterpret_cast<uint4*>(smem + SM_WTS + (nl - 1) * W_LAYER_BYTES)[i] = reinterpret_cast<const uint4*>(p.wlast)[i];
   for (int i = tid; i < nl * C; i += NTHREADS) s_bias[i] = p.bias[(size_t)(2 * p.blk0) * C + i];
   if (LAST_PASS) {
     if (tid < C * 3) s_head[tid] = p.whead[(tid / 3) * 4 + (tid % 3)];   // packed [16][3]
@@ -427,6 +425,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t adesc_x0 = desc_lo(R.x0, R.x0_plane), adesc_t0 = desc_lo(R.t0, R.t_plane);
     const uint32_t adesc_x1 = desc_lo(R.x1, R.x1_plane), adesc_t1 = desc_lo(R.t1, R.t_plane);
     const uint32_t bdesc0 = desc_lo(s0 + SM_WTS, 48 * 16);
+    const uint32_t bdesc_head = desc_lo(s0 + head_b_offset(nl), 16 * 16);   // [N 16][K 16]: the K halves are 256 B apart
     uint32_t S = 0;
     long long gg = 0;
     for (long long a = r0; a < r1;) {
@@ -444,6 +443,12 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         st_ad[l] = adl + (uint32_t)(st_slot[l] * RW - 1);
         st_blk[l] = (14 * l - 1) & 31;
       }
+      // last pass: the residual of the last block reaches the (folded) head through one MMA per output row, A = row rho of
+      // the block's input ring at pixel 0 (X1 for two blocks in the pass, X0 for one), B = the head matrix, N = 16
+      auto head_x_desc = [&](int rho) -> uint32_t {
+        return nl == 4 ? adesc_x1 + (uint32_t)((rho & (2 * KX - 1)) * RW)
+                       : adesc_x0 + (uint32_t)((((gb0 + (rho >> 1)) % K0) * 2 + (rho & 1)) * RW);
+      };
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
         if (lane == 0) STREAM_TRACE(0);
         asm volatile("bar.sync %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");   // the helper has seen this step's barriers
@@ -481,9 +486,11 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
               mma_lo(d, ad, bd, id);
               mma_lo(d, ad + 1, bd + (48 * 16 * 2 / 16), id);
               mma_lo(d, ad + 2, bd + 2 * (48 * 16 * 2 / 16), id);
+              if (LAST_PASS && l == nl - 1) mma_lo(d + 16, head_x_desc(rho0), bdesc_head, idesc0 + (2u << 17));
               mma_lo(d + 16, ad + RW, bd, id);
               mma_lo(d + 16, ad + RW + 1, bd + (48 * 16 * 2 / 16), id);
               mma_lo(d + 16, ad + RW + 2, bd + 2 * (48 * 16 * 2 / 16), id);
+              if (LAST_PASS && l == nl - 1) mma_lo(d + 32, head_x_desc(rho0 + 1), bdesc_head, idesc0 + (2u << 17));
               umma_commit(mbar_l);
               advance();
               continue;
@@ -513,6 +520,9 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 mma_lo(tmem, adr + 1, b + (48 * 16 * 2 / 16), id);
                 mma_lo(tmem, adr + 2, b + 2 * (48 * 16 * 2 / 16), id);
               }
+              // residual -> head of output row rho (same place in the row's accumulation order as on the fast path)
+              if (LAST_PASS && l == nl - 1)
+                mma_lo(tmem + (uint32_t)((blk0 + par + 1) & 31) * 16u, head_x_desc(rho), bdesc_head, idesc0 + (2u << 17));
             }
             umma_commit(mbar_l);
             advance();
@@ -621,6 +631,7 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
     p.fin = h->ws_feat[(ps + 1) & 1].as<__half>();
     p.fout = last ? nullptr : h->ws_feat[ps & 1].as<__half>();
     p.wumma = h->d_conv_umma.as<uint8_t>();
+    p.wlast = h->d_last_umma.as<uint8_t>();
     p.bias = h->d_bias_f32.as<float>();
     p.whead = h->d_head_f32.as<float>();
     p.n = e.n; p.h = e.h; p.w = e.w; p.he = e.he; p.we = e.we; p.vw = (int)vw;

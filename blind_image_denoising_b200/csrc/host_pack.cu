@@ -115,6 +115,27 @@ int pack_weights(bfcnn_handle* h) {
           umma3[(size_t)(l * 2 + 1) * 2304 + off] = __float2half_rn(v0 - __half2float(hi));
         }
 
+  // Last pass of the F16 stack: the collapsed 1x1 head [16][3] is folded INTO the last conv_b (its 16 output channels
+  // become the 3 head outputs, columns 3..15 zero) and the residual reaches the head through one extra MMA per row
+  // (A = the block's input row, B = the head matrix), so the accumulator of the last layer holds the pre-tanh head value
+  // and the epilogue neither loads the residual nor multiplies 16 x 3 per pixel.  [dx 3][N 48][K 16] + [N 16][K 16].
+  std::vector<__half> last((size_t)3 * 48 * 16 + 16 * 16, __float2half_rn(0.f));
+  if (N > 0) {
+    const int l = 2 * N - 1;
+    for (int dxi = 0; dxi < 3; ++dxi)
+      for (int n = 0; n < 48; ++n)
+        for (int k = 0; k < 16; ++k) {
+          const int j = n / 16, o = n % 16, dy = 1 - j;
+          const int tap = (dy + 1) * 3 + dxi;
+          double a = 0.0;
+          if (o < 3)
+            for (int co = 0; co < C; ++co) a += (double)conv[((size_t)l * 9 + tap) * C * C + k * C + co] * (double)head[co * 4 + o];
+          last[(size_t)dxi * 768 + (k / 8) * 384 + (n / 8) * 64 + (n % 8) * 8 + (k % 8)] = __float2half_rn((float)a);
+        }
+    for (int n = 0; n < 3; ++n)
+      for (int k = 0; k < 16; ++k) last[(size_t)2304 + (k / 8) * 128 + (n / 8) * 64 + (n % 8) * 8 + (k % 8)] = __float2half_rn(head[k * 4 + n]);
+  }
+
   BF_CUDA(cudaSetDevice(h->device));
   const size_t nbase = (size_t)k0 * k0 * 3 * C;
   BF_CHECK(h->d_vars.reserve(L.total * sizeof(float)));
@@ -124,6 +145,7 @@ int pack_weights(bfcnn_handle* h) {
   BF_CHECK(h->d_head_f32.reserve(head.size() * sizeof(float)));
   BF_CHECK(h->d_conv_umma.reserve(std::max<size_t>(umma.size(), 1) * sizeof(__half)));
   BF_CHECK(h->d_conv_umma_x3.reserve(std::max<size_t>(umma3.size(), 1) * sizeof(__half)));
+  BF_CHECK(h->d_last_umma.reserve(last.size() * sizeof(__half)));
   BF_CUDA(cudaMemcpy(h->d_vars.p, v, L.total * sizeof(float), cudaMemcpyHostToDevice));
   BF_CUDA(cudaMemcpy(h->d_base_f32.p, v + L.base, nbase * sizeof(float), cudaMemcpyHostToDevice));
   if (N > 0) {
@@ -131,6 +153,7 @@ int pack_weights(bfcnn_handle* h) {
     BF_CUDA(cudaMemcpy(h->d_bias_f32.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
     BF_CUDA(cudaMemcpy(h->d_conv_umma.p, umma.data(), umma.size() * sizeof(__half), cudaMemcpyHostToDevice));
     BF_CUDA(cudaMemcpy(h->d_conv_umma_x3.p, umma3.data(), umma3.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    BF_CUDA(cudaMemcpy(h->d_last_umma.p, last.data(), last.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
   BF_CUDA(cudaMemcpy(h->d_head_f32.p, head.data(), head.size() * sizeof(float), cudaMemcpyHostToDevice));
   h->packed_valid = true;

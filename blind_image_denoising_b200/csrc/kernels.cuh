@@ -41,6 +41,8 @@ int make_feature_tmap(CUtensorMap* out, const __half* base, const Extent& e, int
 // img_stride / row_stride (pixels; 0 = the plain [n][he][we] map): where pixel (b, y, x) goes, b * img_stride + y * row_stride + x
 int launch_base_conv_f16(bfcnn_handle* h, const uint8_t* d_in, __half* feat, const Extent& e, cudaStream_t st,
                          __half* feat_lo = nullptr, long long img_stride = 0, long long row_stride = 0);
+// ---- base_conv_t5.cu: the k0 = 3 base conv on tcgen05 into the virtual-row map [he][n (we + 1)][16] (feat_lo: F16X3)
+int launch_base_conv3_t5(bfcnn_handle* h, const uint8_t* d_in, __half* feat, __half* feat_lo, const Extent& e, cudaStream_t st);
 // ---- fused_stream.cu: the fused conv-BN-ReLU stack on tcgen05 as a row-streaming pipeline, F16 arithmetic
 int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bool out_u8, const Extent& e,
                            cudaStream_t st);
