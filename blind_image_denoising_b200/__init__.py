@@ -18,6 +18,7 @@ from . import _native
 from .arch import (Arch, arch_from_config, arch_from_name, arch_from_variable_shapes,
                    default_pipeline_config)
 from .denoiser import Denoiser, PipelinedDenoiser
+from .generic import GenericDenoiser, ResnetSpec, spec_from_config
 from .model import BuilderResults, model_builder
 from .optimizer import deep_supervision_schedule_builder, optimizer_builder, schedule_builder
 from .tensorbundle import read_model_variables, write_model_variables
@@ -78,10 +79,21 @@ def load_variables(path) -> List[np.ndarray]:
     return read_model_variables(str(vdir))
 
 
-def _build_denoiser(path, name: str = "", **kwargs) -> Denoiser:
+def _build_denoiser(path, name: str = "", **kwargs):
     path = pathlib.Path(path)
     variables = load_variables(path)
-    arch = arch_from_variable_shapes([v.shape for v in variables])
+    try:
+        arch = arch_from_variable_shapes([v.shape for v in variables])
+    except ValueError:
+        # not the 16-channel two-conv family of the tcgen05 stacks: any other resnet configuration (1-3 convs per block,
+        # depthwise / grouped convs, extra normalisations and multipliers) runs on the FP32 layer kernels, and needs its
+        # pipeline.json to say what the variables are
+        cfg_path = _find_config(path if path.is_dir() else path.parent)
+        if cfg_path is None:
+            raise
+        spec = spec_from_config(load_config(cfg_path))
+        kwargs.pop("allow_synthetic", None)
+        return GenericDenoiser(spec, variables, name=name, **kwargs)
     cfg_path = _find_config(path if path.is_dir() else path.parent)
     allow_synthetic = bool(kwargs.pop("allow_synthetic", False))
     if cfg_path is not None:
@@ -146,6 +158,15 @@ def load_denoiser_model(model_path: str, **kwargs) -> Denoiser:
 load_default_denoiser = list(models.values())[0][DENOISER_STR] if len(models) > 0 else None
 
 
+def generic_model(config, seed: int = 0, **kwargs) -> GenericDenoiser:
+    """A generic-path denoiser for a resnet pipeline config (or its name in CONFIGS_DICT) with deterministic synthetic
+    weights (parity tests)."""
+    from .generic import initial_variables as generic_variables
+    cfg = CONFIGS_DICT[config] if isinstance(config, str) else config
+    spec = spec_from_config(cfg)
+    return GenericDenoiser(spec, generic_variables(spec, seed), **kwargs)
+
+
 def synthetic_model(no_layers: int, seed: int = 0, **kwargs) -> Denoiser:
     """A denoiser with deterministic synthetic weights (benchmarks, parity tests)."""
     arch = Arch(no_layers=no_layers)
@@ -158,7 +179,8 @@ __all__ = [
     "optimizer_builder", "load_denoiser_model", "load_default_denoiser", "load_config",
     "dataset_builder", "loss_function_builder", "deep_supervision_schedule_builder", "create_checkpoint",
     "BuilderResults", "DatasetResults", "Trainer", "trainer_from_config",
-    "load_variables", "synthetic_model", "Denoiser", "PipelinedDenoiser", "Arch",
+    "load_variables", "synthetic_model", "generic_model", "Denoiser", "PipelinedDenoiser", "GenericDenoiser", "ResnetSpec",
+    "spec_from_config", "Arch",
     "arch_from_config", "arch_from_name", "default_pipeline_config", "synthetic_variables", "initial_variables",
     "read_model_variables", "write_model_variables",
 ]

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "bfcnn_get_weights", "bfcnn_denoise_u8", "bfcnn_denoise_f32", "bfcnn_launch_count",
     "bfcnn_last_stack_ms", "bfcnn_set_kernel_timing", "bfcnn_kernel_times", "bfcnn_corrupt", "bfcnn_loss", "bfcnn_train_step", "bfcnn_train_losses", "bfcnn_saved_activation", "bfcnn_downscale2x",
     "bfcnn_allreduce_grads", "bfcnn_adam_step", "bfcnn_conv3x3", "bfcnn_set_train_engine",
+    "bfcnn_generic_prepare", "bfcnn_generic_conv2d", "bfcnn_generic_finish",
 ]
 
 
@@ -117,6 +118,13 @@ def load_library() -> ctypes.CDLL:
     lib.bfcnn_conv3x3.restype = c_int
     lib.bfcnn_allreduce_grads.argtypes = [H, c_void_p, c_void_p, c_void_p]
     lib.bfcnn_allreduce_grads.restype = c_int
+    lib.bfcnn_generic_prepare.argtypes = [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.bfcnn_generic_prepare.restype = c_int
+    lib.bfcnn_generic_conv2d.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.bfcnn_generic_conv2d.restype = c_int
+    lib.bfcnn_generic_finish.argtypes = [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.bfcnn_generic_finish.restype = c_int
     lib.bfcnn_adam_step.argtypes = [H, c_void_p, c_float, POINTER(AdamCfg), c_int64, c_void_p]
     lib.bfcnn_adam_step.restype = c_int
     if lib.bfcnn_abi_version() != 3:

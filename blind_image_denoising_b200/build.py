@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libbfcnn_b200.so"
-SOURCES = ["host_pack.cu", "api.cu", "conv_f32.cu", "conv_x3.cu", "conv_t5.cu", "base_conv.cu", "base_conv_t5.cu", "fused_stream.cu", "fused_stream_x3.cu", "train.cu"]
+SOURCES = ["host_pack.cu", "api.cu", "conv_f32.cu", "conv_x3.cu", "conv_t5.cu", "base_conv.cu", "base_conv_t5.cu", "fused_stream.cu", "fused_stream_x3.cu", "train.cu", "generic.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",

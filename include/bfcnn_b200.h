@@ -213,6 +213,28 @@ int bfcnn_allreduce_grads(bfcnn_handle* h, float* flat_grads, void* nccl_comm, v
 int bfcnn_adam_step(bfcnn_handle* h, const float* flat_grads, float grad_scale,
                     const bfcnn_adam_cfg* cfg, int64_t step, void* stream);
 
+/* ---- every other `type: "resnet"` configuration -------------------------------------------------
+ * Reference-grade FP32 layer kernels for the block layouts the tcgen05 stacks do not cover: 1-3 convs per block, any
+ * odd kernel size / filter counts, grouped and depthwise convs (bfcnn/backbone_resnet.py:149-178; the in-tree config
+ * bfcnn/configs/resnet_color_1x6_bn_32x128x32_1x3x1_128x128_depthwise_l1_relu.json), initial / final BatchNormalization
+ * (:266-276) and the ChannelwiseMultiplier / Multiplier scalings (bfcnn/custom_layers.py:1028-1162), which the host folds
+ * into a per-channel (scale, bias) of the preceding conv.  All pointers are device pointers, float32 NHWC; no handle.
+ *
+ * prepare : uint8 [n,h,w,3] -> clip/255-0.5 on the zero-padded pow2 canvas [n,hc,wc,3] (module_denoiser.py:53-56,
+ *           utilities.py:449-461,736-751)
+ * conv2d  : Conv2D(groups) with kernel [k,k,cin/groups,cout] (depth_multiplier = 0) or DepthwiseConv2D with kernel
+ *           [k,k,cin,depth_multiplier]; "same" zero padding, stride 1, no bias; y = acc*scale + bias (either may be NULL),
+ *           optional ReLU, optional residual add (utilities.py:195-215, backbone_blocks.py:240-242)
+ * finish  : head output [n,hc,wc,3] -> tanh(2y)*0.51 -> denormalise -> crop -> float32 or round-half-even uint8
+ *           (model.py:342, utilities.py:435-443, module_denoiser.py:68-73) */
+int bfcnn_generic_prepare(int device, const uint8_t* img, float* canvas, int n, int height, int width, int canvas_h,
+                          int canvas_w, void* stream);
+int bfcnn_generic_conv2d(int device, const float* in, float* out, const float* weights, const float* scale, const float* bias,
+                         const float* residual, int n, int height, int width, int cin, int cout, int kernel, int groups,
+                         int depth_multiplier, int relu, void* stream);
+int bfcnn_generic_finish(int device, const float* y, void* out, int n, int height, int width, int canvas_h, int canvas_w,
+                         int out_u8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
