@@ -22,7 +22,7 @@ FLAG_IN_DEVICE, FLAG_OUT_DEVICE, FLAG_NO_PAD_POW2, FLAG_IN_F32 = 1, 2, 4, 8
 # every symbol include/bfcnn_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "bfcnn_abi_version", "bfcnn_last_error", "bfcnn_device_count", "bfcnn_num_weights",
-    "bfcnn_num_trainable", "bfcnn_create", "bfcnn_destroy", "bfcnn_set_weights",
+    "bfcnn_num_trainable", "bfcnn_create", "bfcnn_destroy", "bfcnn_release_workspaces", "bfcnn_set_weights",
     "bfcnn_get_weights", "bfcnn_denoise_u8", "bfcnn_denoise_f32", "bfcnn_launch_count",
     "bfcnn_last_stack_ms", "bfcnn_set_kernel_timing", "bfcnn_kernel_times", "bfcnn_corrupt", "bfcnn_loss", "bfcnn_train_step", "bfcnn_train_losses", "bfcnn_saved_activation", "bfcnn_downscale2x",
     "bfcnn_allreduce_grads", "bfcnn_adam_step", "bfcnn_conv3x3", "bfcnn_set_train_engine",
@@ -82,6 +82,8 @@ def load_library() -> ctypes.CDLL:
     lib.bfcnn_create.restype = c_int
     lib.bfcnn_destroy.argtypes = [H]
     lib.bfcnn_destroy.restype = None
+    lib.bfcnn_release_workspaces.argtypes = [H]
+    lib.bfcnn_release_workspaces.restype = c_int
     lib.bfcnn_set_weights.argtypes = [H, c_void_p, c_size_t]
     lib.bfcnn_set_weights.restype = c_int
     lib.bfcnn_get_weights.argtypes = [H, c_void_p, c_size_t]

@@ -258,6 +258,18 @@ void bfcnn_destroy(bfcnn_handle* h) {
   delete h;
 }
 
+int bfcnn_release_workspaces(bfcnn_handle* h) {
+  BF_REQUIRE(h != nullptr, "handle is NULL");
+  BF_CUDA(cudaSetDevice(h->device));
+  BF_CUDA(cudaDeviceSynchronize());
+  h->ws_in.release(); h->ws_out.release();
+  for (auto& b : h->ws_feat) b.release();
+  h->feat_tag[0] = h->feat_tag[1] = 0ull;
+  h->ws_train.release(); h->ws_stats.release(); h->ws_grads.release();
+  h->tr_n = h->tr_h = h->tr_w = 0;
+  return BFCNN_OK;
+}
+
 int bfcnn_set_weights(bfcnn_handle* h, const float* weights, size_t n_floats) {
   BF_REQUIRE(h != nullptr && weights != nullptr, "NULL argument");
   if (n_floats != h->lay.total) {

@@ -69,6 +69,10 @@ class Denoiser:
     def launch_count(self) -> int:
         return int(self._lib.bfcnn_launch_count(self._h))
 
+    def release_workspaces(self):
+        """Give the feature-map / staging workspaces back to the driver (they grow to the largest call seen)."""
+        _native.check(self._lib.bfcnn_release_workspaces(self._h))
+
     def last_stack_ms(self) -> float:
         ms = ctypes.c_float()
         _native.check(self._lib.bfcnn_last_stack_ms(self._h, ctypes.byref(ms)))

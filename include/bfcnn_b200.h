@@ -120,6 +120,9 @@ int64_t bfcnn_num_trainable(const bfcnn_arch* arch);
 int bfcnn_create(const bfcnn_arch* arch, const float* weights, size_t n_floats, int device,
                  bfcnn_handle** out);
 void bfcnn_destroy(bfcnn_handle* h);
+/* Workspaces (feature maps, staging buffers, saved activations) grow to the largest call seen and are kept for reuse; this
+ * returns them to the driver (weights, packed operands and optimizer state stay).  The next call allocates again. */
+int bfcnn_release_workspaces(bfcnn_handle* h);
 int bfcnn_set_weights(bfcnn_handle* h, const float* weights, size_t n_floats);
 int bfcnn_get_weights(bfcnn_handle* h, float* weights, size_t n_floats);
 

@@ -262,3 +262,17 @@ def test_f16x3_streaming_matches_fp32(native_lib):
         assert d.max() <= 1 and (d > 0).mean() < 0.01, (n_layers, shape, int(d.max()), float((d > 0).mean()))
         assert np.array_equal(a, m(x)) and np.array_equal(h16, m(x, precision="f16"))
         m.close()
+
+
+def test_release_workspaces(native_lib):
+    """Workspaces grow to the largest call and can be handed back; the next call allocates again and computes the same."""
+    import torch
+    m = _model(6, precision="f16")
+    x = np.random.default_rng(3).integers(0, 256, size=(2, 700, 900, 3), dtype=np.uint8)
+    ref = m(x)
+    torch.cuda.synchronize()
+    used = torch.cuda.mem_get_info()[0]
+    m.release_workspaces()
+    assert torch.cuda.mem_get_info()[0] > used + 2 * 700 * 900 * 32          # at least the two fp16 feature maps came back
+    assert np.array_equal(m(x), ref)
+    m.close()
