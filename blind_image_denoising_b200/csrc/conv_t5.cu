@@ -20,6 +20,15 @@
 // Per 128-pixel row the shared-memory data pipe moves 9 x 5.5 KB of operands + 8 KB of plane stores (~450 cycles), HBM
 // moves 128 x (64 + 64 [+ 64]) bytes (HBM floor 41-62 us at 2.1 MP); measured 72 us (conv_x3.cu: 117-181 us).
 //
+// Fused prologue (PRO = 1): the converters build the conv input from TWO maps, x = ca[ch] * in + cb[ch] * in2 + cc[ch], write
+// it to out2 (the map the rest of the step needs: X_{i+1} in the forward pass, dU in the backward pass) and feed the MMAs
+// from registers.  With the per-channel coefficients of train.cu::bn_coef_kernel this is
+//   forward   X_{i+1} = X_i + (U_i - mean) * gamma / sigma                   (BN(center=False) + Add, backbone_blocks.py:191-242)
+//   backward  dU_i = gamma / sigma * (dY - mean(dY) - xhat * mean(dY * xhat))  (BN batch-statistics backward)
+// so bn_residual_kernel / bn_bwd_apply_kernel (a 192 B/pixel HBM round trip each) disappear from the step: the fused conv
+// moves 64 B/pixel more than the plain one.  A fused step converts its 4 rows in two batches of 2 (both operands of 4 rows
+// would not fit the 78-register budget of the 26-warp CTA).
+//
 // Reference: the forward convs of backbone_blocks.py:167-246 in training mode and the dgrad convs of
 // train_loop.py:302-304 (a correlation of dOut with the flipped, transposed kernel, prepared by the caller).
 #include "kernels.cuh"
@@ -54,6 +63,9 @@ struct Params {
   float* out;
   const float* w;       // [9][16 cin][16 cout] fp32
   const float* res;     // residual / mask source (fp32 NHWC16) or nullptr
+  const float* in2;     // PRO = 1: second input map
+  float* out2;          // PRO = 1: the combined input is written here
+  const float* coef;    // PRO = 1: [3][16] per-channel ca, cb, cc
   double* stats;        // [32]: per-channel sum, sum of squares (CONV_STATS)
   int n, h, wd;
   int tiles_x;
@@ -103,7 +115,7 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
   f = unpack_h2(hi.w); lo.w = pack_h2(b.z - f.x, b.w - f.y);
 }
 
-template <int EPI>
+template <int EPI, int PRO>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3x3_t5_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -324,9 +336,59 @@ conv3x3_t5_kernel(const Params p) {
       const int vb = vx >= 0 ? vx / (p.wd + 1) : -1, gx = vx - vb * (p.wd + 1);
       const bool col_in = (vb >= 0) && (vb < p.n) && (gx < p.wd);   // separator columns and the outside are zero ("same" padding)
       const float* in_b = p.in + (long long)vb * p.h * p.wd * C + 8 * hf;
+      float ca[8], cb[8], cc[8];   // PRO = 1: this thread's channel half of the per-channel coefficients
+      if (PRO == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ca[k] = p.coef[8 * hf + k]; cb[k] = p.coef[C + 8 * hf + k]; cc[k] = p.coef[2 * C + 8 * hf + k]; }
+      }
+      const bool col_side = col_in && (c >= 1) && (c < RW - 1);   // columns this strip owns (the halo columns belong to its neighbours)
       for (int sr = 0; sr < nsteps; ++sr, ++S) {
         if ((int)(S % CVT_GROUPS) != cgrp) continue;   // the other converter group's step
         const uint32_t slot = S % KIN;
+        if (PRO == 1) {
+          // two batches of G / 2 rows, both operands of a batch in flight together; the first batch's loads are issued
+          // before the wait for the ring slot
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            float4 f[G / 2][2], g2[G / 2][2];
+            bool ok[G / 2];
+#pragma unroll
+            for (int i = 0; i < G / 2; ++i) {
+              const int rho = G * sr + (G / 2) * hb + i, gy = y00 + rho;
+              ok[i] = sr < Gm && col_in && rho < P && gy >= 0 && gy < p.h;
+              if (ok[i]) {
+                const long long o = ((long long)gy * p.wd + gx) * C;
+                ldg256(in_b + o, f[i][0], f[i][1]);
+                ldg256(p.in2 + (in_b - p.in) + o, g2[i][0], g2[i][1]);
+              }
+            }
+            if (hb == 0 && S >= (uint32_t)KIN) mbar_wait_sleep(bars + (BAR_FREE + slot) * 8, ((S / KIN) - 1u) & 1u);
+#pragma unroll
+            for (int i = 0; i < G / 2 && sr < Gm; ++i) {
+              const int rho = G * sr + (G / 2) * hb + i;
+              float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;   // outside the image: the zero padding, whatever the coefficients
+              if (ok[i]) {
+                u.x = fmaf(ca[0], f[i][0].x, fmaf(cb[0], g2[i][0].x, cc[0])); u.y = fmaf(ca[1], f[i][0].y, fmaf(cb[1], g2[i][0].y, cc[1]));
+                u.z = fmaf(ca[2], f[i][0].z, fmaf(cb[2], g2[i][0].z, cc[2])); u.w = fmaf(ca[3], f[i][0].w, fmaf(cb[3], g2[i][0].w, cc[3]));
+                v.x = fmaf(ca[4], f[i][1].x, fmaf(cb[4], g2[i][1].x, cc[4])); v.y = fmaf(ca[5], f[i][1].y, fmaf(cb[5], g2[i][1].y, cc[5]));
+                v.z = fmaf(ca[6], f[i][1].z, fmaf(cb[6], g2[i][1].z, cc[6])); v.w = fmaf(ca[7], f[i][1].w, fmaf(cb[7], g2[i][1].w, cc[7]));
+                // rows 0 and P - 1 of a segment are halo rows: another segment (or nobody, outside the image) owns them
+                if (col_side && rho >= 1 && rho < P - 1) stg256(p.out2 + (in_b - p.in) + ((long long)(y00 + rho) * p.wd + gx) * C, u, v);
+              }
+              u.x *= p.in_scale; u.y *= p.in_scale; u.z *= p.in_scale; u.w *= p.in_scale;
+              v.x *= p.in_scale; v.y *= p.in_scale; v.z *= p.in_scale; v.w *= p.in_scale;
+              uint4 hi, lo;
+              split8(u, v, hi, lo);
+              const uint32_t dst = pl0 + (uint32_t)hf * PLANE_BYTES + ((slot * G + (uint32_t)((G / 2) * hb + i)) * RW + (uint32_t)c) * 16u;
+              sts128(dst, hi);
+              sts128(dst + 2 * PLANE_BYTES, lo);
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars + (BAR_FULL + slot) * 8);
+          continue;
+        }
         // all loads of the step first (no shared-memory store in between: they stay in flight together, and while this
         // group waits for its ring slot)
         float4 f[G][2];
@@ -366,21 +428,27 @@ conv3x3_t5_kernel(const Params p) {
 }  // namespace t5
 
 int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
-                      ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st) {
+                      ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st, const float* in2, float* out2,
+                      const float* coef) {
   using namespace t5;
   BF_REQUIRE(in_scale > 0.f, "in_scale must be a positive power of two");
   static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
   bool& attr_set = attr_set_dev[h->device & 63];
   if (!attr_set) {
-    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_PLAIN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_RELU, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_RESIDUAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_STATS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_MASK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_RELU, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BF_CUDA(cudaFuncSetAttribute((const void*)conv3x3_t5_kernel<CONV_MASK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   Params p;
   p.in = in; p.out = out; p.w = w; p.res = res; p.stats = stats;
+  p.in2 = in2; p.out2 = out2; p.coef = coef;
+  const bool fused = in2 != nullptr;
+  BF_REQUIRE(!fused || ((epi == CONV_RELU || epi == CONV_MASK) && out2 && coef), "fused conv prologue: ReLU / mask epilogues only");
   p.n = e.n; p.h = e.he; p.wd = e.we;
   // The images of the batch are laid side by side in one VIRTUAL row with a zero column between neighbours (which is the
   // zero padding of both): strips of 126 output columns run across image boundaries, so a 256-pixel-wide crop does not
@@ -396,11 +464,17 @@ int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float*
   p.in_scale = in_scale;
   p.out_scale = 1.0f / (in_scale * W_SCALE);
   switch (epi) {
-    case CONV_PLAIN: conv3x3_t5_kernel<CONV_PLAIN><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
-    case CONV_RELU: conv3x3_t5_kernel<CONV_RELU><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
-    case CONV_RESIDUAL: conv3x3_t5_kernel<CONV_RESIDUAL><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
-    case CONV_STATS: conv3x3_t5_kernel<CONV_STATS><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
-    case CONV_MASK: conv3x3_t5_kernel<CONV_MASK><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
+    case CONV_PLAIN: conv3x3_t5_kernel<CONV_PLAIN, 0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
+    case CONV_RELU:
+      if (fused) conv3x3_t5_kernel<CONV_RELU, 1><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p);
+      else conv3x3_t5_kernel<CONV_RELU, 0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p);
+      break;
+    case CONV_RESIDUAL: conv3x3_t5_kernel<CONV_RESIDUAL, 0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
+    case CONV_STATS: conv3x3_t5_kernel<CONV_STATS, 0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
+    case CONV_MASK:
+      if (fused) conv3x3_t5_kernel<CONV_MASK, 1><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p);
+      else conv3x3_t5_kernel<CONV_MASK, 0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p);
+      break;
     default: set_error("unsupported conv epilogue"); return BFCNN_ERR_INTERNAL;
   }
   h->launches++;

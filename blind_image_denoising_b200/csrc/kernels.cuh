@@ -28,8 +28,10 @@ int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float*
                       ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st);
 
 // ---- conv_t5.cu: the same layer contract on tcgen05 (row-streaming, F16X3 arithmetic); default training conv engine
+// in2 / out2 / coef: fused prologue (the conv input is ca*in + cb*in2 + cc per channel, written to out2), ReLU / mask epilogues
 int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
-                      ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st);
+                      ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st, const float* in2 = nullptr,
+                      float* out2 = nullptr, const float* coef = nullptr);
 
 int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, float* partial, int max_parts, const Extent& e,
                        float g_scale, int* parts_out, cudaStream_t st);

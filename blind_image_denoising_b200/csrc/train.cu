@@ -507,7 +507,7 @@ train_prep_kernel(const float* __restrict__ vars, const long long* __restrict__ 
 // (Keras fused BN: moving <- moving*m + batch*(1-m), moving_var takes the unbiased variance)
 __global__ void bn_finalize_kernel(const double* __restrict__ stats /*[2][16]*/, double cnt, float eps, float momentum,
                                    float* __restrict__ vars, long long gamma_off, long long mean_off, long long var_off,
-                                   float* __restrict__ bn /*[4][16]*/, int update_moving) {
+                                   float* __restrict__ bn /*[4][16]*/, float* __restrict__ coef /*[3][16]*/, int update_moving) {
   const int c = threadIdx.x;
   if (c >= C) return;
   const double m = stats[c] / cnt;
@@ -516,6 +516,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats /*[2][16]*/,
   const double inv = 1.0 / sqrt(v + (double)eps);
   bn[c] = (float)m; bn[C + c] = (float)v; bn[2 * C + c] = (float)inv;
   bn[3 * C + c] = (float)((double)vars[gamma_off + c] * inv);
+  // x_next = x + (u - mean) * scale as ca * x + cb * u + cc: the fused prologue of the next conv_a (conv_t5.cu)
+  coef[c] = 1.0f; coef[C + c] = bn[3 * C + c]; coef[2 * C + c] = (float)(-m * (double)bn[3 * C + c]);
   if (update_moving) {
     const double ub = v * (cnt / fmax(cnt - 1.0, 1.0));
     vars[mean_off + c] = (float)((double)vars[mean_off + c] * (double)momentum + m * (1.0 - (double)momentum));
@@ -713,6 +715,19 @@ bn_bwd_apply_kernel(const float4* __restrict__ dy, const float4* __restrict__ u,
     r.w = s_bn[3 * C + c + 3] * (d.w - s_m[c + 3] - (uv.w - s_bn[c + 3]) * s_bn[2 * C + c + 3] * s_m[C + c + 3]);
     du[i] = r;
   }
+}
+
+// The same as per-channel coefficients of the fused conv prologue (conv_t5.cu): du = ca * dy + cb * u + cc, and dgamma
+__global__ void bn_bwd_coef_kernel(const float* __restrict__ bn, const double* __restrict__ sums, double cnt,
+                                   float* __restrict__ coef /*[3][16]*/, float* __restrict__ g_gamma) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const double m1 = sums[c] / cnt, m2 = sums[C + c] / cnt;
+  const double mean = bn[c], inv = bn[2 * C + c], scale = bn[3 * C + c];
+  coef[c] = (float)scale;
+  coef[C + c] = (float)(-scale * inv * m2);
+  coef[2 * C + c] = (float)(scale * (mean * inv * m2 - m1));
+  g_gamma[c] = (float)sums[C + c];
 }
 
 // -------------------------------------------------------------------------------------
@@ -943,7 +958,7 @@ __global__ void step_scalars_kernel(const float* __restrict__ loss_scal, const d
 // =====================================================================================
 struct TrainWs {
   // offsets into ws_stats (bytes)
-  size_t bn_stats, bn_params, bwd_sums, loss_sums, ssim_sums, loss_scal, loss_coef, G, reg, out4, end;
+  size_t bn_stats, bn_params, bn_coef, bwd_sums, loss_sums, ssim_sums, loss_scal, loss_coef, G, reg, out4, end;
 };
 
 static TrainWs plan_stats(int N, int n) {
@@ -957,6 +972,7 @@ static TrainWs plan_stats(int N, int n) {
   w.G = take((size_t)C * 3 * sizeof(double));
   w.reg = take(sizeof(double));
   w.bn_params = take((size_t)std::max(N, 1) * 4 * C * sizeof(float));
+  w.bn_coef = take((size_t)std::max(N, 1) * 6 * C * sizeof(float));   // per block: forward [3][16], backward [3][16]
   w.loss_scal = take(8 * sizeof(float));
   w.loss_coef = take((size_t)(1 + n) * sizeof(float));
   w.out4 = take(8 * sizeof(float));
@@ -1004,6 +1020,7 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   double* Gd = reinterpret_cast<double*>(sb + W.G);
   double* regd = reinterpret_cast<double*>(sb + W.reg);
   float* bn_params = reinterpret_cast<float*>(sb + W.bn_params);
+  float* bn_coef = reinterpret_cast<float*>(sb + W.bn_coef);
   float* loss_scal = reinterpret_cast<float*>(sb + W.loss_scal);
   float* loss_coef = reinterpret_cast<float*>(sb + W.loss_coef);
   float* out4_d = reinterpret_cast<float*>(sb + W.out4);
@@ -1064,16 +1081,27 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
                   : launch_conv3x3_f32(h, in, out, wts, nullptr, res, stats, epi, e, st);
   };
   // ---- forward (training mode)
+  // tcgen05 engine: BN + Add of block i-1 is the prologue of block i's conv_a, and the BN backward of block i the prologue of
+  // its conv_b dgrad (conv_t5.cu, PRO = 1); the element-wise kernels remain for the last block and for the other engines
+  static const bool fuse_env = !(getenv("BFCNN_TRAIN_FUSE") && atoi(getenv("BFCNN_TRAIN_FUSE")) == 0);
+  const bool fuse = t5 && h->train_fuse && fuse_env;
   BF_CHECK(launch_base_conv(h, noisy, false, Xm(0), vars + L.base, e, st));
   for (int i = 0; i < N; ++i) {
-    BF_CHECK(conv(Xm(i), Tm(i), vars + L.wa[i], nullptr, nullptr, CONV_RELU));
+    if (fuse && i > 0)
+      BF_CHECK(launch_conv3x3_t5(h, Xm(i - 1), Tm(i), vars + L.wa[i], nullptr, nullptr, CONV_RELU, e, 64.0f, st, Um(i - 1), Xm(i),
+                                 bn_coef + (size_t)(i - 1) * 6 * C));
+    else
+      BF_CHECK(conv(Xm(i), Tm(i), vars + L.wa[i], nullptr, nullptr, CONV_RELU));
     BF_CHECK(conv(Tm(i), Um(i), vars + L.wb[i], nullptr, bn_stats + (size_t)i * 2 * C, CONV_STATS));
     bn_finalize_kernel<<<1, 32, 0, st>>>(bn_stats + (size_t)i * 2 * C, cnt, h->arch.bn_epsilon, h->arch.bn_momentum, vars,
                                          (long long)L.gamma[i], (long long)L.mean[i], (long long)L.var[i],
-                                         bn_params + (size_t)i * 4 * C, update_moving);
-    bn_residual_kernel<<<ew_blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(Xm(i)), reinterpret_cast<const float4*>(Um(i)),
-                                                  reinterpret_cast<float4*>(Xm(i + 1)), bn_params + (size_t)i * 4 * C, n4);
-    h->launches += 2;
+                                         bn_params + (size_t)i * 4 * C, bn_coef + (size_t)i * 6 * C, update_moving);
+    h->launches++;
+    if (!fuse || i == N - 1) {
+      bn_residual_kernel<<<ew_blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(Xm(i)), reinterpret_cast<const float4*>(Um(i)),
+                                                    reinterpret_cast<float4*>(Xm(i + 1)), bn_params + (size_t)i * 4 * C, n4);
+      h->launches++;
+    }
   }
   // ---- loss
   const int px_per_sample = height * width;
@@ -1123,10 +1151,17 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
     const float* bnp = bn_params + (size_t)i * 4 * C;
     double* bs = bwd_sums + (size_t)i * 2 * C;
     bn_bwd_reduce_kernel<<<ew_blocks4, 256, 0, st>>>(reinterpret_cast<const float4*>(dX), reinterpret_cast<const float4*>(Um(i)), bnp, bs, n4);
-    bn_bwd_apply_kernel<<<ew_blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dX), reinterpret_cast<const float4*>(Um(i)), bnp, bs, cnt,
-                                                   reinterpret_cast<float4*>(dU), flat_grads + L.t_gamma[i], n4);
-    // conv_b: dT = dgrad(dU) masked by ReLU ; dWb = T (x) dU
-    BF_CHECK(conv(dU, dT, dgrad_w + (size_t)(2 * i + 1) * 9 * C * C, Tm(i), nullptr, CONV_MASK));
+    // conv_b: dU = BN backward of dX ; dT = dgrad(dU) masked by ReLU ; dWb = T (x) dU
+    if (fuse) {
+      float* cf = bn_coef + (size_t)i * 6 * C + 3 * C;
+      bn_bwd_coef_kernel<<<1, 32, 0, st>>>(bnp, bs, cnt, cf, flat_grads + L.t_gamma[i]);
+      BF_CHECK(launch_conv3x3_t5(h, dX, dT, dgrad_w + (size_t)(2 * i + 1) * 9 * C * C, Tm(i), nullptr, CONV_MASK, e, gscale * 64.0f, st,
+                                 Um(i), dU, cf));
+    } else {
+      bn_bwd_apply_kernel<<<ew_blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dX), reinterpret_cast<const float4*>(Um(i)), bnp, bs, cnt,
+                                                     reinterpret_cast<float4*>(dU), flat_grads + L.t_gamma[i], n4);
+      BF_CHECK(conv(dU, dT, dgrad_w + (size_t)(2 * i + 1) * 9 * C * C, Tm(i), nullptr, CONV_MASK));
+    }
     BF_CHECK(wgrad(Tm(i), dU, vars + L.wb[i], flat_grads + L.t_wb[i]));
     // conv_a: dX_i = dgrad(dT) + dX_{i+1} ; dWa = X_i (x) dT
     BF_CHECK(conv(dT, dXn, dgrad_w + (size_t)(2 * i) * 9 * C * C, dX, nullptr, CONV_RESIDUAL));
