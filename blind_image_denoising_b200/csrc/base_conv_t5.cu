@@ -17,15 +17,14 @@
 //
 // Output layout: the virtual-row map of the streaming stacks, [he][vw = n (we + 1)][16] (fused_stream.cu): the images of
 // the batch side by side, a zero column after each; strips of 126 output columns run across the image boundaries.
-#include "kernels.cuh"
-#include "umma_ptx.cuh"
+#include "stream_common.cuh"
 
 namespace bfcnn {
 namespace bt5 {
 
 using namespace tc5;
+using stream::RW; using stream::SLACK_PX; using stream::Split; using stream::Seg; using stream::seg_at; using stream::cta_rows;
 
-constexpr int RW = 128, SLACK_PX = 8;
 constexpr int G = 4;                    // rows per step
 constexpr int EPI_WARPS = 8;            // G rows x 4 TMEM lane quarters = 16 tasks per step, two per warp
 constexpr int WARP_MMA = 8, WARP_HELP = 9, WARP_CVT = 10, CVT_WARPS = 4;   // converter warps per group: thread = pixel column
@@ -43,39 +42,14 @@ static_assert(SM_WTS + 2 * W_PART_BYTES <= SM_PLANES, "weights overlap the plane
 constexpr int SMEM_BYTES = SM_PLANES + PLANE_BYTES;
 constexpr int MIN_SHARE = 16;
 constexpr int SEG_OVERHEAD = 2 + 2 * G;   // halo rows + pipeline fill / drain of a segment, in rows (cost-space split)
-constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
 
-struct Params {
+struct Params : Split {   // rows_needed = he, seg_overhead = SEG_OVERHEAD
   const uint8_t* img;   // [n][h][w][3]
   __half* out;          // [he][vw][16] hi part
   __half* out_lo;       // lo part or nullptr
   const float* w;       // [9][3][16 cout] fp32 (d_base_f32)
   int n, h, wd, he, we, vw;
-  int tiles_x;
-  long long total_rows, share;
 };
-
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
-__device__ __forceinline__ void mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ long long cost_to_row(const Params& p, long long c) {
-  const long long per = (long long)p.he + SEG_OVERHEAD;
-  const long long s = c / per, off = c - s * per;
-  return s * p.he + max(0ll, min((long long)p.he, off - SEG_OVERHEAD));
-}
-struct Seg { int j, ya, yb; };
-__device__ __forceinline__ Seg seg_at(const Params& p, long long a, long long r1) {
-  Seg s;
-  const long long strip = a / p.he;
-  s.ya = (int)(a - strip * p.he);
-  s.yb = (int)min((long long)p.he, (long long)s.ya + (r1 - a));
-  s.j = (int)strip;
-  return s;
-}
 
 template <bool WITH_LO>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -86,8 +60,8 @@ base_conv3_t5_kernel(const Params p) {
   const uint32_t s0 = smem_u32(smem);
   const uint32_t bars = s0 + SM_BARS;
   const uint32_t pl0 = s0 + SM_PLANES + SLACK_PX * 16;   // pixel 0 of ring row 0
-  const long long r0 = min(p.total_rows, cost_to_row(p, (long long)blockIdx.x * p.share));
-  const long long r1 = min(p.total_rows, cost_to_row(p, ((long long)blockIdx.x + 1) * p.share));
+  long long r0, r1;
+  cta_rows(p, r0, r1);
 
   // ---------------- setup: barriers, TMEM, weights (normalisation folded in, scaled hi / lo, UMMA B layout), zeroed plane
   if (tid < (int)NBARS) {
@@ -342,11 +316,8 @@ int launch_base_conv3_t5(bfcnn_handle* h, const uint8_t* d_in, __half* feat, __h
   BF_REQUIRE(vw < (1ll << 30), "batch too wide for the virtual row");
   p.vw = (int)vw;
   p.tiles_x = (int)((vw - 1 + (RW - 2) - 1) / (RW - 2));
-  p.total_rows = (long long)p.tiles_x * e.he;
-  const long long total_cost = (long long)p.tiles_x * ((long long)e.he + SEG_OVERHEAD);
-  int grid = (int)std::min<long long>(h->sm_count, std::max<long long>(1, p.total_rows / MIN_SHARE));
-  p.share = (total_cost + grid - 1) / grid;
-  grid = (int)((total_cost + p.share - 1) / p.share);
+  p.rows_needed = e.he; p.seg_overhead = SEG_OVERHEAD;
+  const int grid = stream::plan_split(p, h->sm_count, MIN_SHARE);
   if (feat_lo) base_conv3_t5_kernel<true><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p);
   else base_conv3_t5_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p);
   h->launches++;

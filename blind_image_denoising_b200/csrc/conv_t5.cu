@@ -31,15 +31,14 @@
 //
 // Reference: the forward convs of backbone_blocks.py:167-246 in training mode and the dgrad convs of
 // train_loop.py:302-304 (a correlation of dOut with the flipped, transposed kernel, prepared by the caller).
-#include "kernels.cuh"
-#include "umma_ptx.cuh"
+#include "stream_common.cuh"
 
 namespace bfcnn {
 namespace t5 {
 
 using namespace tc5;
+using stream::RW; using stream::SLACK_PX; using stream::Split; using stream::Seg; using stream::seg_at; using stream::cta_rows;
 
-constexpr int RW = 128, SLACK_PX = 8;
 constexpr int G = 4;                    // rows per step
 constexpr int EPI_WARPS = 8;            // G rows x 4 TMEM lane quarters = 16 tasks per step, two per warp
 constexpr int WARP_MMA = 8, WARP_HELP = 9, WARP_CVT = 10, CVT_WARPS = 8;   // converter warps per group: thread = (pixel, half)
@@ -47,7 +46,6 @@ constexpr int CVT_GROUPS = 2;           // converter groups take alternate steps
                                         // the ring slot, so two steps of global loads are in flight
 constexpr int NTHREADS = 32 * (WARP_CVT + CVT_GROUPS * CVT_WARPS);
 constexpr int KIN = 4;                  // input ring: groups of G rows
-constexpr int ROW_BYTES = RW * 16;
 constexpr int PLANE_BYTES = (KIN * G * RW + 2 * SLACK_PX) * 16;   // one channel-half plane of the hi or lo part
 constexpr int W_PART_BYTES = 3 * 48 * 16 * 2;                     // B operand of one part: [dx 3][N 48][K 16] fp16
 constexpr float W_SCALE = 256.f;        // as conv_x3.cu: keeps the low part of the weights out of the fp16 subnormals
@@ -56,9 +54,8 @@ constexpr uint32_t SM_BARS = 0, SM_TMEM = 256, SM_STAT = 384, SM_WTS = 512, SM_P
 constexpr int SMEM_BYTES = SM_PLANES + 4 * PLANE_BYTES;
 constexpr int MIN_SHARE = 16;
 constexpr int SEG_OVERHEAD = 2 + 2 * G;   // halo rows + pipeline fill / drain of a segment, in rows (cost-space split)
-constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
 
-struct Params {
+struct Params : Split {   // rows_needed = h, seg_overhead = SEG_OVERHEAD
   const float* in;
   float* out;
   const float* w;       // [9][16 cin][16 cout] fp32
@@ -68,33 +65,9 @@ struct Params {
   const float* coef;    // PRO = 1: [3][16] per-channel ca, cb, cc
   double* stats;        // [32]: per-channel sum, sum of squares (CONV_STATS)
   int n, h, wd;
-  int tiles_x;
-  long long total_rows, share;
   float in_scale, out_scale;
 };
 
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
-__device__ __forceinline__ void mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ long long cost_to_row(const Params& p, long long c) {
-  const long long per = (long long)p.h + SEG_OVERHEAD;
-  const long long s = c / per, off = c - s * per;
-  return s * p.h + max(0ll, min((long long)p.h, off - SEG_OVERHEAD));
-}
-struct Seg { int b, j, ya, yb; };
-__device__ __forceinline__ Seg seg_at(const Params& p, long long a, long long r1) {
-  Seg s;
-  const long long strip = a / p.h;
-  s.ya = (int)(a - strip * p.h);
-  s.yb = (int)min((long long)p.h, (long long)s.ya + (r1 - a));
-  s.b = (int)(strip / p.tiles_x);
-  s.j = (int)(strip - (long long)s.b * p.tiles_x);
-  return s;
-}
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread moves a whole 32-byte sector, so an fp32 NHWC16 pixel is
 // two full-sector stores instead of four half-sector ones (the 16-byte stores were the epilogue's critical path)
 __device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
@@ -126,8 +99,8 @@ conv3x3_t5_kernel(const Params p) {
   float* s_stat = reinterpret_cast<float*>(smem + SM_STAT);   // [32]
   // planes: hi half 0, hi half 1, lo half 0, lo half 1; pixel 0 of ring row 0 sits SLACK_PX pixels into each plane
   const uint32_t pl0 = s0 + SM_PLANES + SLACK_PX * 16;
-  const long long r0 = min(p.total_rows, cost_to_row(p, (long long)blockIdx.x * p.share));
-  const long long r1 = min(p.total_rows, cost_to_row(p, ((long long)blockIdx.x + 1) * p.share));
+  long long r0, r1;
+  cta_rows(p, r0, r1);
 
   // ---------------- setup: barriers, TMEM, weights (fp32 -> scaled hi / lo in the UMMA B layout), zeroed planes
   if (tid < (int)NBARS) {
@@ -456,11 +429,8 @@ int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float*
   const long long vwidth = (long long)e.n * (e.we + 1) - 1;
   BF_REQUIRE(vwidth < (1ll << 30), "batch too wide for the virtual row");
   p.tiles_x = (int)((vwidth + (RW - 2) - 1) / (RW - 2));
-  p.total_rows = (long long)p.tiles_x * e.he;
-  const long long total_cost = (long long)p.tiles_x * ((long long)e.he + SEG_OVERHEAD);
-  int grid = (int)std::min<long long>(h->sm_count, std::max<long long>(1, p.total_rows / MIN_SHARE));
-  p.share = (total_cost + grid - 1) / grid;
-  grid = (int)((total_cost + p.share - 1) / p.share);
+  p.rows_needed = e.he; p.seg_overhead = SEG_OVERHEAD;
+  const int grid = stream::plan_split(p, h->sm_count, MIN_SHARE);
   p.in_scale = in_scale;
   p.out_scale = 1.0f / (in_scale * W_SCALE);
   switch (epi) {

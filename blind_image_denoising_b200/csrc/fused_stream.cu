@@ -34,30 +34,15 @@
 //
 // Reference arithmetic: module_denoiser.py:53-73, backbone_blocks.py:167-246 (block), model.py:297-342 (head),
 // utilities.py:435-443 (denormalise).
-#include "kernels.cuh"
-#include "umma_ptx.cuh"
+#include "stream_common.cuh"
 
 namespace bfcnn {
 namespace ustream {
 
-using namespace tc5;
+using namespace stream;
 
-constexpr int RW = 128;                 // strip width == UMMA M
-constexpr int SLACK_PX = 8;             // pixels of slack before/after every plane (tap shift -1/+1)
-constexpr int EPI_WARPS = 16;           // 4 sets x 4 TMEM lane quarters
-constexpr int WARP_MMA = 16;            // warp 16 issues the MMAs, warp 17 waits on its barriers, warp 18 is the TMA producer
-constexpr int NTHREADS = 32 * 19;
-constexpr int LAG = 3;                  // steps between consecutive layers
 constexpr int K0 = 11;                  // X0 ring: groups of 2 rows (TMA prefetch depth)
 constexpr int KX = 8;                   // X1 ring groups: written at step w+4, last read (residual) at step w+10
-constexpr int KT = 3;                   // T rings: written by the epilogue of layer l at step w+1 (which has only seen layer l's
-                                        // MMAs of that step), read by the MMAs of layer l+1 at step w+3: three groups
-constexpr int ROW_BYTES = RW * 16;      // one row of one channel-half plane
-constexpr int GROUP_BYTES = 2 * ROW_BYTES;
-constexpr int W_LAYER_BYTES = 3 * 48 * 16 * 2;   // B operand of one conv: [dx 3][N 48][K 16] fp16
-constexpr int MAX_SMEM = 232448;
-constexpr int MAX_NL = 4;
-constexpr int MIN_SHARE = 8;            // rows per CTA below which fewer CTAs are launched
 
 // barriers (8 B each)
 // mma_done[l][s & 1] (per layer: the epilogue of layer l starts while the later layers of the step are still being
@@ -65,7 +50,6 @@ constexpr int MIN_SHARE = 8;            // rows per CTA below which fewer CTAs a
 constexpr uint32_t BAR_MMA = 0, BAR_EPI = 2 * 4, BAR_XFULL = BAR_EPI + 2, BAR_XFREE = BAR_XFULL + K0, NBARS = BAR_XFREE + K0;
 constexpr uint32_t SM_BARS = 0, SM_TMEM = 512, SM_HEAD = 528, SM_BIAS = 784, SM_WTS = 1152;
 
-__host__ __device__ inline uint32_t plane_bytes_of(int rows) { return (uint32_t)(rows * RW + 2 * SLACK_PX) * 16u; }
 constexpr uint32_t HEAD_B_BYTES = 16 * 16 * 2;   // B operand of the head matrix [N 16][K 16] fp16 (last pass)
 __host__ __device__ inline uint32_t head_b_offset(int nl) { return SM_WTS + (uint32_t)nl * W_LAYER_BYTES; }
 __host__ __device__ inline uint32_t rings_offset(int nl) { return (head_b_offset(nl) + HEAD_B_BYTES + 127u) & ~127u; }
@@ -75,7 +59,7 @@ __host__ __device__ inline uint32_t smem_bytes(int nl) {
   return b;
 }
 
-struct Params {
+struct Params : Split {
   // Feature maps between passes are laid out as ONE virtual row per image row: the n images side by side, each followed by
   // a zero column (the "same" padding of both neighbours): [he][vw = n (we + 1)][16].  Strips of tw columns run across the
   // image boundaries, so narrow images (64 x 256 x 256: three 128-lane strips per image otherwise) waste no lanes.
@@ -90,10 +74,8 @@ struct Params {
   int n, h, w, he, we;
   int blk0, nblk;
   int out_u8;
-  int tw, tiles_x, rows_needed;   // output columns per strip, strips per virtual row, output rows per strip
-  long long total_rows, share;    // linearised (strip, row) space; COST units each CTA owns (see cost_to_row)
-  int seg_overhead;               // cost of starting a segment at a strip start, in rows (halo rows + pipeline fill / drain)
-  long long* trace;               // debug timeline (BFCNN_STREAM_TRACE=1) of CTA trace_block, steps [TRACE_S0, TRACE_S0 + 32)
+  int tw;                  // output columns per strip
+  long long* trace;        // debug timeline (BFCNN_STREAM_TRACE=1) of CTA trace_block, steps [TRACE_S0, TRACE_S0 + 32)
   int trace_block;
 };
 constexpr uint32_t TRACE_S0 = 100;
@@ -105,67 +87,10 @@ constexpr uint32_t TRACE_S0 = 100;
 #define STREAM_TRACE_PTR(cond) nullptr
 #endif
 
-// Work is split in COST space: every strip costs rows_needed + seg_overhead units, the first seg_overhead of which stand
-// for the halo rows and the pipeline fill / drain a CTA pays when it starts a new segment at a strip boundary.  Equal
-// cost ranges instead of equal row ranges keep CTAs whose range spans two strips from running ~28 rows longer than the
-// others (6 % at one 4K frame per pass).
-__device__ __forceinline__ long long cost_to_row(const Params& p, long long c) {
-  const long long per = (long long)p.rows_needed + p.seg_overhead;
-  const long long s = c / per, off = c - s * per;
-  return s * p.rows_needed + max(0ll, min((long long)p.rows_needed, off - p.seg_overhead));
-}
-struct Seg { int b, j, ya, yb; };
-// the next segment of the linear row range [a, r1): rows [ya, yb) of strip j of image b
-__device__ __forceinline__ Seg seg_at(const Params& p, long long a, long long r1) {
-  Seg s;
-  const long long strip = a / p.rows_needed;
-  s.ya = (int)(a - strip * p.rows_needed);
-  s.yb = (int)min((long long)p.rows_needed, (long long)s.ya + (r1 - a));
-  s.b = (int)(strip / p.tiles_x);
-  s.j = (int)(strip - (long long)s.b * p.tiles_x);
-  return s;
-}
-
 // rings: byte address of pixel 0, row slot 0, channel half 0; the other half is +plane
 struct Rings {
   uint32_t x0, t0, x1, t1;
   uint32_t x0_plane, t_plane, x1_plane;
-};
-
-enum Kind { KIND_A = 0, KIND_B_TO_X = 1, KIND_B_OUT = 2 };
-
-// Every shared-memory descriptor of this kernel has SBO = 128 B, version 1, SWIZZLE_NONE: the high word is one constant
-// and the issuer's arithmetic (tap shifts, ring rows, weight blocks) touches the 14-bit start-address field of the low
-// word only -- 32-bit adds instead of 64-bit ones on the issuing thread.
-constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
-__device__ __forceinline__ void mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc)
-      : "memory");
-}
-
-// model.py:342 tanh(2y)*0.51, then utilities.py:435-443 (clip(+-0.5)+0.5)*255, with tanh(z) = 1 - 2/(exp(2z)+1) on the
-// fast exp / divide units (absolute error ~1e-6 of the +-1 range, 1e-4 on the 0-255 scale): the head sits on the
-// epilogue's critical path in the last pass
-__device__ __forceinline__ float head_activation_fast(float y) {
-  const float e = __expf(4.0f * y);
-  float t = (1.0f - __fdividef(2.0f, e + 1.0f)) * 0.51f;
-  t = fminf(fmaxf(t, -0.5f), 0.5f);
-  return (t + 0.5f) * 255.0f;
-}
-
-struct EpiCtx {
-  uint32_t tq;             // TMEM address of this warp's lane quarter, column 0
-  uint32_t pix;            // byte offset of this thread's pixel inside a ring row
-  int y00, he, h_img;      // row rho of the segment is image row y00 + rho
-  int P, nl;
-  bool col_ok, col_out;
-  __half* fout_col;        // feature-map address of (b, y00, gx); row rho adds rho * row_halves
-  uint8_t* out_col;        // output address of (b, y00, gx)
-  long long row_halves, row_out;
-  int gb0;                 // X0 ring group slot of the segment's group 0
 };
 
 // one (layer, row) task of one warp: 32 pixels of output row rho of layer l
@@ -186,13 +111,7 @@ __device__ __forceinline__ void epi_task(const Params& p, const Rings& R, const 
       const float r0o = head_activation_fast(__uint_as_float(y[0]) + bias[0]);
       const float r1o = head_activation_fast(__uint_as_float(y[1]) + bias[1]);
       const float r2o = head_activation_fast(__uint_as_float(y[2]) + bias[2]);
-      if (p.out_u8) {
-        uint8_t* d = E.out_col + (long long)rho * E.row_out;
-        d[0] = (uint8_t)__float2int_rn(r0o); d[1] = (uint8_t)__float2int_rn(r1o); d[2] = (uint8_t)__float2int_rn(r2o);
-      } else {
-        float* d = reinterpret_cast<float*>(E.out_col) + (long long)rho * E.row_out;
-        d[0] = r0o; d[1] = r1o; d[2] = r2o;
-      }
+      store_rgb(E.out_col + (long long)rho * E.row_out * (p.out_u8 ? 1 : 4), p.out_u8, r0o, r1o, r2o);
     }
     if (l == 1) {   // one block in this pass: the X0 row was the residual operand of the issuer's extra MMA, now complete
       __syncwarp();
@@ -293,23 +212,13 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     R.x1 = o + SLACK_PX * 16; o += 2 * R.x1_plane;
     R.t1 = o + SLACK_PX * 16;
   }
-  const long long r0 = min(p.total_rows, cost_to_row(p, (long long)blockIdx.x * p.share));
-  const long long r1 = min(p.total_rows, cost_to_row(p, ((long long)blockIdx.x + 1) * p.share));
+  long long r0, r1;
+  cta_rows(p, r0, r1);
   const bool tr = (p.trace != nullptr) && ((int)blockIdx.x == p.trace_block);
   if (tr && tid == 0) p.trace[256] = clock64();
 
   // ---------------- one-time setup: barriers, TMEM, weights, zeroed rings
-  if (tid < (int)NBARS) {
-    // epi_done: one arrival per epilogue warp; x_free: one per warp of the 2 rows x 4 quarters that read the group
-    // (32 same-address arrivals per warp showed up as ~200 extra shared-memory wavefronts per step)
-    const uint32_t cnt = tid < (int)BAR_EPI ? 1u : (tid < (int)BAR_XFULL ? (uint32_t)EPI_WARPS : (tid < (int)BAR_XFREE ? 1u : 8u));
-    mbar_init(bars + tid * 8, cnt);
-  }
-  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(s0 + SM_TMEM) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
+  init_barriers_and_tmem<BAR_EPI, BAR_XFULL, BAR_XFREE, NBARS>(bars, s0 + SM_TMEM, tid, warp);
   // last pass: layer nl - 1 takes the head-folded weights, and the head matrix follows the conv weights
   for (int i = tid; i < (nl - (LAST_PASS ? 1 : 0)) * (W_LAYER_BYTES / 16); i += NTHREADS)
     reinterpret_cast<uint4*>(smem + SM_WTS)[i] = reinterpret_cast<const uint4*>(p.wumma + (size_t)(2 * p.blk0) * W_LAYER_BYTES)[i];
@@ -332,12 +241,7 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
-  // Programmatic dependent launch (host side: cudaLaunchAttributeProgrammaticStreamSerialization).  Everything above read
-  // only constants of the model; from here on the feature maps of the previous kernel are read (TMA) and the buffer it read
-  // from is overwritten, so wait for it to complete -- after telling the scheduler that the NEXT kernel's CTAs may be
-  // placed as soon as ours exit (they will wait at this same point).
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  pdl_wait_for_previous();   // programmatic dependent launch: everything above read only constants of the model
   if (tr && tid == 0) p.trace[257] = clock64();
 
   if (warp < EPI_WARPS) {
@@ -383,7 +287,8 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     for (long long a = r0; a < r1;) {
       const Seg sg = seg_at(p, a, r1);
       a += sg.yb - sg.ya;
-      const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
+      int P, Gm, nsteps;
+      seg_steps(sg.yb - sg.ya, nl, P, Gm, nsteps);
       {
         const int vx = sg.j * p.tw - halo + c;                     // column of the virtual row
         const int vb = vx >= 0 ? vx / (p.we + 1) : -1, gx = vx - vb * (p.we + 1);   // image, column inside the image
@@ -431,7 +336,8 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     for (long long a = r0; a < r1;) {
       const Seg sg = seg_at(p, a, r1);
       a += sg.yb - sg.ya;
-      const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
+      int P, Gm, nsteps;
+      seg_steps(sg.yb - sg.ya, nl, P, Gm, nsteps);
       const int gb0 = (int)(gg % K0);
       // per-layer issue state at the layer's group 0: A descriptor of input row 0 (pixel -1), its ring row, TMEM block of row -1
       uint32_t st_ad[MAX_NL];
@@ -536,49 +442,9 @@ stream_pass_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     }
     if (tr && lane == 0) { p.trace[258] = clock64(); p.trace[259] = S; }
   } else if (warp == WARP_MMA + 1) {
-    // ================= barrier helper of the MMA issuer =================
-    // step S needs: epi_done(S-2) (lane 0: input rows written, accumulator blocks drained), x_full of layer 0's group
-    // (lane 1), and at a segment start epi_done(S-1) too (lane 2: every accumulator block drained before the ring
-    // restarts at row 0).  One barrier per lane, in parallel.
-    uint32_t S = 0;
-    long long gg = 0;
-    for (long long a = r0; a < r1;) {
-      const Seg sg = seg_at(p, a, r1);
-      a += sg.yb - sg.ya;
-      const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1, nsteps = Gm + LAG * (nl - 1) + 1;
-      for (int sr = 0; sr < nsteps; ++sr, ++S) {
-        if (lane == 0 && S >= 2) mbar_wait_sleep(bars + (BAR_EPI + (S & 1u)) * 8, ((S - 2) >> 1) & 1u);
-        if (lane == 1 && sr < Gm) {
-          const long long k = gg + sr;
-          mbar_wait_sleep(bars + (BAR_XFULL + (uint32_t)(k % K0)) * 8, (uint32_t)(k / K0) & 1u);
-        }
-        if (lane == 2 && sr == 0 && S >= 1) mbar_wait_sleep(bars + (BAR_EPI + ((S - 1) & 1u)) * 8, ((S - 1) >> 1) & 1u);
-        __syncwarp();
-        tc_fence_before();
-        asm volatile("bar.arrive %0, 64;\n" ::"r"(2 + (S & 1u)) : "memory");
-      }
-      gg += Gm;
-    }
+    helper_warp_loop<K0, BAR_EPI, BAR_XFULL>(p, bars, r0, r1, nl, lane);
   } else {
-    // ================= TMA producer =================
-    if (elect_one_sync()) {
-      long long gg = 0;
-      for (long long a = r0; a < r1;) {
-        const Seg sg = seg_at(p, a, r1);
-        a += sg.yb - sg.ya;
-        const int P = (sg.yb - sg.ya) + 2 * nl, Gm = (P + 1) >> 1;
-        const int gx0 = sg.j * p.tw - halo, y00 = sg.ya - nl;
-        for (int g = 0; g < Gm; ++g, ++gg) {
-          const uint32_t k = (uint32_t)(gg % K0), n = (uint32_t)(gg / K0);
-          if (n >= 1) mbar_wait_sleep(bars + (BAR_XFREE + k) * 8, (n - 1) & 1u);
-          const uint32_t bar = bars + (BAR_XFULL + k) * 8;
-          mbar_arrive_expect_tx(bar, 2 * GROUP_BYTES);
-          const uint32_t dst = R.x0 + k * GROUP_BYTES;
-          tma_load_q(dst, &tmap, 0, gx0, y00 + 2 * g, 0, bar);   // gx0: column of the virtual row
-          tma_load_q(dst + R.x0_plane, &tmap, 1, gx0, y00 + 2 * g, 0, bar);
-        }
-      }
-    }
+    if (elect_one_sync()) tma_producer_loop<K0, 1, BAR_XFULL, BAR_XFREE>(p, &tmap, bars, R.x0, R.x0_plane, r0, r1, nl, p.tw);
     __syncwarp();
   }
   tc_fence_before();
@@ -639,22 +505,7 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
     p.nblk = std::min(kb, N - p.blk0);
     p.out_u8 = out_u8 ? 1 : 0;
     const int nl = 2 * p.nblk;
-    p.tw = RW - 2 * nl;
-    // Rows / columns this pass has to produce: the layers that are still to come (rem) shrink the cone of influence by one
-    // pixel each, so beyond h + rem (w + rem) nothing can reach the cropped output any more (the band of the
-    // pow2 canvas is only as wide as the receptive field that is LEFT).  What lies beyond keeps stale values: never read
-    // by a valid output.
-    const int rem = 2 * (N - p.blk0 - p.nblk);
-    p.rows_needed = std::min(e.he, e.h + rem);
-    // columns of the virtual row that need an output: up to the last needed column of the last image
-    const long long cols_needed = (long long)(e.n - 1) * (e.we + 1) + std::min(e.we, e.w + rem);
-    p.tiles_x = (int)((cols_needed + p.tw - 1) / p.tw);
-    p.total_rows = (long long)p.tiles_x * p.rows_needed;
-    p.seg_overhead = 2 * nl + 2 * (LAG * (nl - 1) + 1);
-    const long long total_cost = (long long)p.tiles_x * ((long long)p.rows_needed + p.seg_overhead);
-    int grid = (int)std::min<long long>(h->sm_count, std::max<long long>(1, p.total_rows / MIN_SHARE));
-    p.share = (total_cost + grid - 1) / grid;
-    grid = (int)((total_cost + p.share - 1) / p.share);
+    const int grid = plan_pass(p, p.tw, e, N, p.blk0, p.nblk, h->sm_count);
     const size_t smem = smem_bytes(nl);
     BF_REQUIRE(smem <= (size_t)MAX_SMEM, "internal: streaming pass does not fit in shared memory");
     static const int trace_on = getenv("BFCNN_STREAM_TRACE") ? atoi(getenv("BFCNN_STREAM_TRACE")) : 0;
@@ -667,19 +518,8 @@ int run_fused_stack_stream(bfcnn_handle* h, const uint8_t* d_in, void* d_out, bo
     CUtensorMap tmap;
     BF_CHECK(make_feature_tmap(&tmap, p.fin, ev, RW, 2, vw));
     ktime_begin(h, st, last ? 2 : 1);
-    {
-      // programmatic dependent launch: the CTAs of this pass take their SMs as the previous kernel's CTAs exit and run
-      // their prologue (barriers, TMEM, weights, zeroed rings) while its tail is still working; griddepcontrol.wait in the
-      // kernel holds every access to the feature maps until the previous kernel has completed
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
-      if (last) BF_CUDA(cudaLaunchKernelEx(&cfg, stream_pass_kernel<true>, p, tmap));
-      else BF_CUDA(cudaLaunchKernelEx(&cfg, stream_pass_kernel<false>, p, tmap));
-    }
+    if (last) BF_CUDA(launch_pdl(stream_pass_kernel<true>, grid, NTHREADS, smem, st, p, tmap));
+    else BF_CUDA(launch_pdl(stream_pass_kernel<false>, grid, NTHREADS, smem, st, p, tmap));
     ktime_end(h, st);
     h->launches++;
     BF_CUDA(cudaGetLastError());

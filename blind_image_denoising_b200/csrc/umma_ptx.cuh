@@ -33,6 +33,17 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// Every shared-memory descriptor of the streaming kernels has SBO = 128 B, version 1, SWIZZLE_NONE: the high word is one
+// constant and the issuer's arithmetic (tap shifts, ring rows, weight blocks) touches the 14-bit start-address field of the
+// low word only -- 32-bit adds instead of 64-bit ones on the issuing thread.
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ void mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc)
+      : "memory");
+}
 // one lane of a converged warp; the compiler keeps the tcgen05 operands in uniform registers only on this path
 // (a plain `lane == 0` branch wraps every UTCHMMA in an ELECT/BRA.U.ANY loop: 392 instead of 143 cycles per row)
 __device__ __forceinline__ uint32_t elect_one_sync() {
