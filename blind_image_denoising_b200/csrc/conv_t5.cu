@@ -132,6 +132,10 @@ conv3x3_t5_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+  // Programmatic dependent launch: the setup above (barriers, TMEM, weight split, zeroed planes: a few microseconds, 24
+  // convs per step) read only the weights, which were final before the PREVIOUS kernel started; it overlaps that kernel when
+  // it is one of the small ones that release their dependents at once (bn_finalize / bn_bwd_coef / wgrad_reduce).
+  pdl_wait_for_previous();
 
   if (warp < EPI_WARPS) {
     // ================= epilogue warps =================
@@ -433,18 +437,13 @@ int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float*
   const int grid = stream::plan_split(p, h->sm_count, MIN_SHARE);
   p.in_scale = in_scale;
   p.out_scale = 1.0f / (in_scale * W_SCALE);
+  auto go = [&](auto kernel) { return launch_pdl(kernel, grid, NTHREADS, (size_t)SMEM_BYTES, st, p); };
   switch (epi) {
-    case CONV_PLAIN: conv3x3_t5_kernel<CONV_PLAIN, 0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
-    case CONV_RELU:
-      if (fused) conv3x3_t5_kernel<CONV_RELU, 1><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p);
-      else conv3x3_t5_kernel<CONV_RELU, 0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p);
-      break;
-    case CONV_RESIDUAL: conv3x3_t5_kernel<CONV_RESIDUAL, 0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
-    case CONV_STATS: conv3x3_t5_kernel<CONV_STATS, 0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p); break;
-    case CONV_MASK:
-      if (fused) conv3x3_t5_kernel<CONV_MASK, 1><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p);
-      else conv3x3_t5_kernel<CONV_MASK, 0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, st>>>(p);
-      break;
+    case CONV_PLAIN: BF_CUDA(go(conv3x3_t5_kernel<CONV_PLAIN, 0>)); break;
+    case CONV_RELU: BF_CUDA(fused ? go(conv3x3_t5_kernel<CONV_RELU, 1>) : go(conv3x3_t5_kernel<CONV_RELU, 0>)); break;
+    case CONV_RESIDUAL: BF_CUDA(go(conv3x3_t5_kernel<CONV_RESIDUAL, 0>)); break;
+    case CONV_STATS: BF_CUDA(go(conv3x3_t5_kernel<CONV_STATS, 0>)); break;
+    case CONV_MASK: BF_CUDA(fused ? go(conv3x3_t5_kernel<CONV_MASK, 1>) : go(conv3x3_t5_kernel<CONV_MASK, 0>)); break;
     default: set_error("unsupported conv epilogue"); return BFCNN_ERR_INTERNAL;
   }
   h->launches++;

@@ -14,6 +14,27 @@ __device__ __forceinline__ float head_activation(float y) {
   return (t + 0.5f) * 255.0f;
 }
 
+// Programmatic dependent launch.  Host: the kernel's CTAs may take their SMs as the previous kernel's CTAs exit (or, when
+// that kernel released its dependents early, while it still runs) and execute whatever precedes pdl_wait_for_previous():
+// setup that reads nothing the previous kernels of the stream wrote.  A kernel launched the ordinary way in between is a
+// full fence (train_prep / adam, the writers of the weights the conv setups read, are launched that way).
+template <typename Kernel, typename... Args>
+inline cudaError_t launch_pdl(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+// Device: tell the scheduler that the NEXT kernel's CTAs may be placed (they wait at this same point), then wait until the
+// previous kernel has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait_for_previous() {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+
 // ---- conv_f32.cu
 int launch_base_conv(bfcnn_handle* h, const void* img, bool img_is_u8, float* out, const float* w,
                      const Extent& e, cudaStream_t st);

@@ -205,26 +205,5 @@ inline int plan_pass(Split& sp, int& tw, const Extent& e, int N, int blk0, int n
   return plan_split(sp, sm_count, MIN_SHARE);
 }
 
-// host: programmatic dependent launch.  The CTAs of this pass take their SMs as the previous kernel's CTAs exit and run
-// their prologue (barriers, TMEM, weights, zeroed rings) while its tail is still working; griddepcontrol.wait in the kernel
-// holds every access to the feature maps until the previous kernel has completed.
-template <typename Kernel, typename... Args>
-inline cudaError_t launch_pdl(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, args...);
-}
-// device: everything before this point read only constants of the model; from here on the feature maps of the previous
-// kernel are read (TMA) and the buffer it read from is overwritten, so wait for it to complete -- after telling the
-// scheduler that the NEXT kernel's CTAs may be placed as soon as ours exit (they will wait at this same point).
-__device__ __forceinline__ void pdl_wait_for_previous() {
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-  asm volatile("griddepcontrol.wait;\n" ::: "memory");
-}
-
 }  // namespace stream
 }  // namespace bfcnn

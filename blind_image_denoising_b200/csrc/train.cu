@@ -508,6 +508,7 @@ train_prep_kernel(const float* __restrict__ vars, const long long* __restrict__ 
 __global__ void bn_finalize_kernel(const double* __restrict__ stats /*[2][16]*/, double cnt, float eps, float momentum,
                                    float* __restrict__ vars, long long gamma_off, long long mean_off, long long var_off,
                                    float* __restrict__ bn /*[4][16]*/, float* __restrict__ coef /*[3][16]*/, int update_moving) {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // the next conv may run its setup now (conv_t5.cu, launch_pdl)
   const int c = threadIdx.x;
   if (c >= C) return;
   const double m = stats[c] / cnt;
@@ -720,6 +721,7 @@ bn_bwd_apply_kernel(const float4* __restrict__ dy, const float4* __restrict__ u,
 // The same as per-channel coefficients of the fused conv prologue (conv_t5.cu): du = ca * dy + cb * u + cc, and dgamma
 __global__ void bn_bwd_coef_kernel(const float* __restrict__ bn, const double* __restrict__ sums, double cnt,
                                    float* __restrict__ coef /*[3][16]*/, float* __restrict__ g_gamma) {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // the next conv may run its setup now (conv_t5.cu, launch_pdl)
   const int c = threadIdx.x;
   if (c >= C) return;
   const double m1 = sums[c] / cnt, m2 = sums[C + c] / cnt;
@@ -901,6 +903,7 @@ constexpr int WR_OUT = 32, WR_LANES = 8;
 __global__ void __launch_bounds__(WR_OUT * WR_LANES)
 wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int nout, const float* __restrict__ wts, float reg1,
                     float* __restrict__ out) {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // the next conv may run its setup now (conv_t5.cu, launch_pdl)
   __shared__ double s_sum[WR_LANES][WR_OUT];
   const int j = threadIdx.x >> 5, li = threadIdx.x & 31;
   const int i = blockIdx.x * WR_OUT + li;
