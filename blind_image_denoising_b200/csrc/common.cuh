@@ -105,7 +105,6 @@ struct bfcnn_handle {
   bfcnn::DevBuf d_train_tables;         // conv offsets / regulariser segments of the training step (uploaded once)
   int tr_n = 0, tr_h = 0, tr_w = 0;     // shape of the last training step (its saved activations sit in ws_train)
   size_t tr_out5_off = 0;               // byte offset of the last step's five loss scalars inside ws_stats
-  int train_fuse = 1;     // tcgen05 engine: BN + Add / BN backward as prologues of the neighbouring convs (BFCNN_TRAIN_FUSE=0: separate kernels)
   int train_engine = 2;   // convs of the training step: 2 = tcgen05, fp16 hi/lo split (conv_t5.cu), 1 = the same on mma.sync (conv_x3.cu), 0 = FP32 FFMA
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

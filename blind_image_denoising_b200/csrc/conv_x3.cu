@@ -339,44 +339,13 @@ __device__ __forceinline__ void wgrad_zero_slack(int t /* 0 .. 63 */, uint32_t b
 constexpr int WG_A_PLANE = ((WG_TH + 2) * RW + 2 * SLACK_PX) * PX_BYTES, WG_G_PLANE = (WG_TH * RW + 2 * SLACK_PX) * PX_BYTES;
 constexpr int WG_BUF = 2 * WG_A_PLANE + 2 * WG_G_PLANE;   // hi + lo planes of A and of G: 108.5 KB
 
-// Version 1 (BFCNN_WGRAD_V1=1, kept for A/B): two 8-warp CTAs per SM, each stage / barrier / MMA / barrier per tile.
-__global__ void __launch_bounds__(NT, 2)
-wgrad3x3_x3_kernel(const float* __restrict__ A, const float* __restrict__ G, float* __restrict__ partial, int n, int h, int wd,
-                   int tiles_x, int tiles_y, float g_scale, float out_scale) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
-  const uint32_t aH = s0 + SLACK_PX * PX_BYTES, aL = aH + WG_A_PLANE;
-  const uint32_t gH = s0 + 2 * WG_A_PLANE + SLACK_PX * PX_BYTES, gL = gH + WG_G_PLANE;
-  float acc[9][2][4];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[t][nt][k] = 0.f;
-  if (tid < 2 * 2 * SLACK_PX * 2) wgrad_zero_slack(tid, s0, WG_A_PLANE);
-  const int ntiles = tiles_x * tiles_y;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int tx = tile % tiles_x, ty = tile / tiles_x;
-    __syncthreads();
-    wgrad_stage_tile<NT, 4, 4>(tid, aH, aL, gH, gL, A, G, n, h, wd, ty * WG_TH - 1, tx * (RW - 2) - 1, g_scale);
-    __syncthreads();
-    wgrad_mma_tile(acc, warp, lane, aH, aL, gH, gL);
-  }
-  __syncthreads();
-  wgrad_store_acc(acc, warp, lane, smem);
-  __syncthreads();
-  wgrad_sum_cta<NT>(tid, smem, partial, out_scale);
-}
-
-// Version 2 (default): ONE 16-warp CTA per SM, warps 0-7 multiply, warps 8-15 stage the next tile into the other of two
-// shared-memory buffers, so global-load latency and the hi / lo split hide behind the MMAs of the previous tile instead of
-// alternating with them (ncu of version 1: tensor pipe 47 % active, half of the stall samples in the staging phase and at
-// its two barriers -- profiles/r01i_train_ncu.md).  Hand-over through named barriers: FULL[b] (256 loader arrivals +
+// ONE 16-warp CTA per SM, warps 0-7 multiply, warps 8-15 stage the next tile into the other of two shared-memory
+// buffers, so global-load latency and the hi / lo split hide behind the MMAs of the previous tile instead of alternating
+// with them (a first version, two 8-warp CTAs per SM that staged / multiplied in turn, left the tensor pipe 47 % active
+// with half of the stall samples in the staging phase and at its two barriers -- profiles/r01i_train_ncu.md; this one:
+// 56 %, profiles/r02_wgrad_ncu.md).  Hand-over through named barriers: FULL[b] (256 loader arrivals +
 // 256 consumer waits), FREE[b] (the other way round, only when the CTA has another tile for that buffer).
 constexpr int WS_NT = 512;
-constexpr bool WGRAD_V1_DEFAULT = false;  // BFCNN_WGRAD_V1=1 selects the two-CTA kernel (A/B: tools/check_wgrad.py)
 __device__ __forceinline__ void nbar_sync(int id, int cnt) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(cnt) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int cnt) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(cnt) : "memory"); }
 
@@ -469,13 +438,10 @@ int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float*
 int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, float* partial, int max_parts, const Extent& e,
                        float g_scale, int* parts_out, cudaStream_t st) {
   using namespace x3;
-  const char* v1s = getenv("BFCNN_WGRAD_V1");
-  const bool v1 = v1s ? atoi(v1s) != 0 : WGRAD_V1_DEFAULT;   // 1: the two-CTA kernel, 0: the loader-warp kernel
-  const size_t smem = (size_t)WG_BUF * (v1 ? 1 : 2);
+  const size_t smem = (size_t)WG_BUF * 2;
   static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
   bool& attr_set = attr_set_dev[h->device & 63];
   if (!attr_set) {
-    BF_CUDA(cudaFuncSetAttribute((const void*)wgrad3x3_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_BUF));
     BF_CUDA(cudaFuncSetAttribute((const void*)wgrad3x3_x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * WG_BUF));
     attr_set = true;
   }
@@ -486,11 +452,8 @@ int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, flo
   const int tiles_x = (int)((vcols + (RW - 2) - 1) / (RW - 2)), tiles_y = (e.he + WG_TH - 1) / WG_TH;
   const long long ntiles = (long long)tiles_x * tiles_y;
   BF_REQUIRE(ntiles < (1ll << 30), "too many tiles");
-  const int grid = (int)std::min<long long>(ntiles, std::min(max_parts, (v1 ? 2 : 1) * h->sm_count));
-  if (v1)
-    wgrad3x3_x3_kernel<<<grid, NT, smem, st>>>(act, grad, partial, e.n, e.he, e.we, tiles_x, tiles_y, g_scale, 1.0f / (64.f * g_scale));
-  else
-    wgrad3x3_x3_ws_kernel<<<grid, WS_NT, smem, st>>>(act, grad, partial, e.n, e.he, e.we, tiles_x, tiles_y, g_scale, 1.0f / (64.f * g_scale));
+  const int grid = (int)std::min<long long>(ntiles, std::min(max_parts, h->sm_count));
+  wgrad3x3_x3_ws_kernel<<<grid, WS_NT, smem, st>>>(act, grad, partial, e.n, e.he, e.we, tiles_x, tiles_y, g_scale, 1.0f / (64.f * g_scale));
   h->launches++;
   BF_CUDA(cudaGetLastError());
   *parts_out = grid;

@@ -1086,8 +1086,7 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   // ---- forward (training mode)
   // tcgen05 engine: BN + Add of block i-1 is the prologue of block i's conv_a, and the BN backward of block i the prologue of
   // its conv_b dgrad (conv_t5.cu, PRO = 1); the element-wise kernels remain for the last block and for the other engines
-  static const bool fuse_env = !(getenv("BFCNN_TRAIN_FUSE") && atoi(getenv("BFCNN_TRAIN_FUSE")) == 0);
-  const bool fuse = t5 && h->train_fuse && fuse_env;
+  const bool fuse = t5;
   BF_CHECK(launch_base_conv(h, noisy, false, Xm(0), vars + L.base, e, st));
   for (int i = 0; i < N; ++i) {
     if (fuse && i > 0)

@@ -324,22 +324,21 @@ def test_conv_layer_engines_match_fp64(native_lib, shape):
 
 
 @pytest.mark.parametrize("shape", [(3, 36, 28, 3), (2, 100, 130, 3)])
-def test_wgrad_kernels_agree(native_lib, monkeypatch, shape):
-    """The loader-warp wgrad kernel (default) and the two-CTA kernel (BFCNN_WGRAD_V1=1) compute the same partial sums in a
-    different tile order: the step gradients agree to rounding (gates as loose as the oracle ones: a ReLU mask may flip)."""
+def test_wgrad_repeatable(native_lib, shape):
+    """The wgrad partial sums are combined in a fixed order (warps through shared memory, CTAs by wgrad_reduce_kernel): two
+    trainers give the same step gradient up to the BN-statistic atomics upstream (~2e-6 of the gradient scale)."""
     import torch
     from oracle import corrupt_oracle as C
     x = np.random.default_rng(0).integers(0, 256, size=shape, dtype=np.uint8)
     clean, noisy = C.corrupt(x, 11, 0, C.NoiseConfig())
-    grads = {}
-    for v1 in ("1", "0"):
-        monkeypatch.setenv("BFCNN_WGRAD_V1", v1)
+    grads = []
+    for _ in range(2):
         arch, v, t = _trainer(6)
         _, _, _, g = t.train_step_single_gpu(torch.from_numpy(clean).cuda(), torch.from_numpy(noisy).cuda())
-        grads[v1] = g.cpu().numpy().astype(np.float64)
+        grads.append(g.cpu().numpy().astype(np.float64))
         t.close()
-    a, b = grads["0"], grads["1"]
+    a, b = grads
     assert np.isfinite(a).all()
     cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
-    assert cos >= 0.9999, cos
-    assert np.abs(a - b).max() <= 2e-2 * np.abs(b).max()
+    assert cos >= 0.999999, cos
+    assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max()

@@ -1,5 +1,4 @@
-"""Training step time (default engine) on batch 32 of 256x256: python tools/train_time.py [n_layers ...]
-A/B a library switch with the environment, one process per setting (e.g. BFCNN_TRAIN_FUSE=0)."""
+"""Training step time (default engine) on batch 32 of 256x256: python tools/train_time.py [n_layers ...]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -25,5 +24,5 @@ for nl in [int(a) for a in sys.argv[1:]] or [6, 18]:
     for s in range(10):
         losses.append(float(once(3 + s)))
     e1.record(); torch.cuda.synchronize()
-    print(f"1x{nl} fuse={os.environ.get('BFCNN_TRAIN_FUSE', '1')}: {e0.elapsed_time(e1) / 10:.3f} ms per step; losses {['%.6f' % l for l in losses[:3]]}", flush=True)
+    print(f"1x{nl}: {e0.elapsed_time(e1) / 10:.3f} ms per step; losses {['%.6f' % l for l in losses[:3]]}", flush=True)
     t.close()
