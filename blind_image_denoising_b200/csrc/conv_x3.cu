@@ -397,6 +397,126 @@ wgrad3x3_x3_ws_kernel(const float* __restrict__ A, const float* __restrict__ G, 
   wgrad_sum_cta<WS_NT>(tid, smem, partial, out_scale);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Base-conv wgrad (k0 = 3) on tensor cores: dWb[tap][c3][co] = sum_p xn[p + tap][c3] * G[p][co], xn = clip(x,0,255)/255 - 0.5
+// inside the image and 0 outside (zero padding of the NORMALISED tensor; utilities.py:449-461, backbone_resnet.py:258-262).
+// The same K-over-pixels scheme as the 3x3 wgrad above: the image tile sits in shared memory as one 16-byte chunk per
+// pixel (r, g, b, 0 x 5; fp16 hi plane + lo plane), so ldmatrix.trans delivers [8 "channels" x 8 pixels] blocks and an
+// m16 tile of the MMA is TWO taps (rows 0-7 / 8-15, three rows of each valid): 5 m-tiles x 2 n-tiles x 3 products = 30
+// HMMA per 16 pixels.  Tile 64 x 8 pixels, warp = one tile row; per-CTA partials in fixed order (deterministic).
+// (The FFMA kernel it replaces, train.cu::wgrad_base_kernel, took 199 us per step at 32 x 256 x 256: 8x its HBM floor.)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int WB3_W = 64, WB3_H = 8, WB3_AW = WB3_W + 2, WB3_AH = WB3_H + 2;
+constexpr int WB3_A_PLANE = WB3_AH * WB3_AW * 16, WB3_G_PLANE = WB3_H * WB3_W * PX_BYTES;
+constexpr int WB3_SMEM = 2 * WB3_A_PLANE + 2 * WB3_G_PLANE;   // 53.9 KB; the cross-warp sums (8 x 432 floats) reuse it
+__global__ void __launch_bounds__(NT, 4)
+wgrad_base3_x3_kernel(const float* __restrict__ img, const float* __restrict__ G, float* __restrict__ partial, int n, int h, int wd,
+                      int tiles_x, int tiles_y, float g_scale, float out_scale) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t aH = s0, aL = s0 + WB3_A_PLANE, gH = s0 + 2 * WB3_A_PLANE, gL = gH + WB3_G_PLANE;
+  float acc[5][2][4];
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[j][nt][k] = 0.f;
+  // ldmatrix.trans row addresses (see wgrad_mma_tile): lane -> matrix (lane >> 3), row (lane & 7)
+  const int mi = lane >> 3, ri = lane & 7;
+  const int gp = (lane & 7) + ((lane >> 3) & 1) * 8, gh = (lane >> 4) & 1;
+  const int ntiles = tiles_x * tiles_y * n;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const int x0 = tx * WB3_W, y0 = ty * WB3_H;
+    const float* i_b = img + (size_t)b * h * wd * 3;
+    const float* g_b = G + (size_t)b * h * wd * C;
+    __syncthreads();   // the previous tile's fragments are read
+    for (int i = tid; i < WB3_AH * WB3_AW; i += NT) {
+      const int ly = i / WB3_AW, lx = i - ly * WB3_AW;
+      const int gx = x0 + lx - 1, gy = y0 + ly - 1;
+      float v[3] = {0.f, 0.f, 0.f};
+      if (gx >= 0 && gx < wd && gy >= 0 && gy < h) {
+        const float* px = i_b + ((size_t)gy * wd + gx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = __fsub_rn(__fdiv_rn(fminf(fmaxf(px[c], 0.f), 255.f), 255.f), 0.5f) * 64.f;
+      }
+      uint4 hi, lo;
+      hi.x = pack_h2(v[0], v[1]); hi.y = pack_h2(v[2], 0.f); hi.z = 0u; hi.w = 0u;
+      float2 f = unpack_h2(hi.x);
+      lo.x = pack_h2(v[0] - f.x, v[1] - f.y);
+      f = unpack_h2(hi.y);
+      lo.y = pack_h2(v[2] - f.x, 0.f); lo.z = 0u; lo.w = 0u;
+      sts128(aH + i * 16, hi);
+      sts128(aL + i * 16, lo);
+    }
+    for (int i = tid; i < WB3_H * WB3_W * 2; i += NT) {
+      const int hf = i & 1, pix = i >> 1;
+      const int ly = pix / WB3_W, lx = pix - ly * WB3_W;
+      const int gx = x0 + lx, gy = y0 + ly;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a;
+      if (gx < wd && gy < h) {
+        const float4* sp = reinterpret_cast<const float4*>(g_b + ((size_t)gy * wd + gx) * C + 8 * hf);
+        a = sp[0]; bq = sp[1];
+        a.x *= g_scale; a.y *= g_scale; a.z *= g_scale; a.w *= g_scale; bq.x *= g_scale; bq.y *= g_scale; bq.z *= g_scale; bq.w *= g_scale;
+      }
+      split_store(gH + px_off(pix, hf), gL + px_off(pix, hf), a, bq);
+    }
+    __syncthreads();
+    const int r = warp;   // tile row of this warp
+#pragma unroll 1
+    for (int ks = 0; ks < WB3_W / 16; ++ks) {
+      uint32_t bh[4], bl[4];
+      const int gpix = r * WB3_W + ks * 16 + gp;
+      ldsm4t(bh, gH + px_off(gpix, gh));
+      ldsm4t(bl, gL + px_off(gpix, gh));
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        // matrices 0 / 2: tap 2j, pixels 0-7 / 8-15; matrices 1 / 3: tap 2j + 1 (j = 4: tap 8 again, its rows are dropped)
+        const int t = min(2 * j + (mi & 1), 8), dy = t / 3, dx = t - 3 * dy;
+        const uint32_t off = (uint32_t)(((r + dy) * WB3_AW + ks * 16 + ri + 8 * (mi >> 1) + dx) * 16);
+        uint32_t ah[4], al[4];
+        ldsm4t(ah, aH + off);
+        ldsm4t(al, aL + off);
+        mma16816(acc[j][0], al, make_uint2(bh[0], bh[1]));
+        mma16816(acc[j][1], al, make_uint2(bh[2], bh[3]));
+        mma16816(acc[j][0], ah, make_uint2(bl[0], bl[1]));
+        mma16816(acc[j][1], ah, make_uint2(bl[2], bl[3]));
+        mma16816(acc[j][0], ah, make_uint2(bh[0], bh[1]));
+        mma16816(acc[j][1], ah, make_uint2(bh[2], bh[3]));
+      }
+    }
+  }
+  // the 8 warps' accumulators in fixed order through shared memory: [warp][tap 9][c3 3][co 16]
+  __syncthreads();
+  float* s_red = reinterpret_cast<float*>(smem);
+  {
+    const int g = lane >> 2, q = lane & 3;
+    if (g < 3) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          float* d0 = s_red + warp * 432 + ((2 * j) * 3 + g) * C + nt * 8 + 2 * q;
+          d0[0] = acc[j][nt][0]; d0[1] = acc[j][nt][1];
+          if (j < 4) {
+            float* d1 = s_red + warp * 432 + ((2 * j + 1) * 3 + g) * C + nt * 8 + 2 * q;
+            d1[0] = acc[j][nt][2]; d1[1] = acc[j][nt][3];
+          }
+        }
+    }
+  }
+  __syncthreads();
+  float* dst = partial + (size_t)blockIdx.x * 432;
+  for (int i = tid; i < 432; i += NT) {
+    float a = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) a += s_red[w8 * 432 + i];
+    dst[i] = a * out_scale;
+  }
+}
+
 }  // namespace x3
 
 int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
@@ -454,6 +574,28 @@ int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, flo
   BF_REQUIRE(ntiles < (1ll << 30), "too many tiles");
   const int grid = (int)std::min<long long>(ntiles, std::min(max_parts, h->sm_count));
   wgrad3x3_x3_ws_kernel<<<grid, WS_NT, smem, st>>>(act, grad, partial, e.n, e.he, e.we, tiles_x, tiles_y, g_scale, 1.0f / (64.f * g_scale));
+  h->launches++;
+  BF_CUDA(cudaGetLastError());
+  *parts_out = grid;
+  return BFCNN_OK;
+}
+
+// dWb partials of the k0 = 3 base conv: `partial` receives [returned grid][432]
+int launch_wgrad_base3_x3(bfcnn_handle* h, const float* img, const float* grad, float* partial, int max_parts, const Extent& e,
+                          float g_scale, int* parts_out, cudaStream_t st) {
+  using namespace x3;
+  static bool attr_set_dev[64] = {};
+  bool& attr_set = attr_set_dev[h->device & 63];
+  if (!attr_set) {
+    BF_CUDA(cudaFuncSetAttribute((const void*)wgrad_base3_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WB3_SMEM));
+    attr_set = true;
+  }
+  static_assert(8 * 432 * 4 <= WB3_SMEM, "cross-warp reduction buffer does not fit");
+  const int tiles_x = (e.we + WB3_W - 1) / WB3_W, tiles_y = (e.he + WB3_H - 1) / WB3_H;
+  const long long ntiles = (long long)tiles_x * tiles_y * e.n;
+  BF_REQUIRE(ntiles < (1ll << 30), "too many tiles");
+  const int grid = (int)std::min<long long>(ntiles, std::min(max_parts, 4 * h->sm_count));
+  wgrad_base3_x3_kernel<<<grid, NT, WB3_SMEM, st>>>(img, grad, partial, e.n, e.he, e.we, tiles_x, tiles_y, g_scale, 1.0f / (64.f * g_scale));
   h->launches++;
   BF_CUDA(cudaGetLastError());
   *parts_out = grid;

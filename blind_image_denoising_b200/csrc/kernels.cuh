@@ -56,6 +56,9 @@ int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float*
 
 int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, float* partial, int max_parts, const Extent& e,
                        float g_scale, int* parts_out, cudaStream_t st);
+// base-conv wgrad (k0 = 3) on the same arithmetic: img = the fp32 image [n,h,w,3] (0..255), partial [grid][432]
+int launch_wgrad_base3_x3(bfcnn_handle* h, const float* img, const float* grad, float* partial, int max_parts, const Extent& e,
+                          float g_scale, int* parts_out, cudaStream_t st);
 
 // ---- base_conv.cu: normalise + base conv into the fp16 NHWC16 map of the streaming stacks, and its TMA descriptor
 // fp16 NHWC16 feature map as a 5-D TMA tensor {ch8, half, x, y, n}, box = box_x pixels x box_y rows of one channel half

@@ -1173,15 +1173,22 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   }
   // ---- backward: base conv (weights only; no gradient into the image)
   {
-    const int r0 = (k0 - 1) / 2;
-    const int btx = (width + WB_W - 1) / WB_W, bty = (height + WB_H - 1) / WB_H;
-    // latency-bound tile loads: up to 6 CTAs per SM, as many as the partial-sum buffer holds rows for
-    const int blocks = (int)std::min<size_t>(std::min<size_t>((size_t)btx * bty * n, (size_t)6 * h->sm_count), part_floats / nbase);
-    const size_t smem = (size_t)((((WB_H + 2 * r0) * (WB_W + 2 * r0) * 3 + 3) & ~3) + WB_H * WB_W * C) * sizeof(float);
-    wgrad_base_kernel<<<blocks, 256, smem, st>>>(noisy, dX, partial, n, height, width, k0, btx, bty);
+    int blocks = 0;
+    if (k0 == 3 && x3_mode) {
+      // tensor cores, the arithmetic of the 3x3 wgrads (conv_x3.cu)
+      BF_CHECK(launch_wgrad_base3_x3(h, noisy, dX, partial, (int)(part_floats / nbase), e, gscale * 64.0f, &blocks, st));
+    } else {
+      const int r0 = (k0 - 1) / 2;
+      const int btx = (width + WB_W - 1) / WB_W, bty = (height + WB_H - 1) / WB_H;
+      // latency-bound tile loads: up to 6 CTAs per SM, as many as the partial-sum buffer holds rows for
+      blocks = (int)std::min<size_t>(std::min<size_t>((size_t)btx * bty * n, (size_t)6 * h->sm_count), part_floats / nbase);
+      const size_t smem = (size_t)((((WB_H + 2 * r0) * (WB_W + 2 * r0) * 3 + 3) & ~3) + WB_H * WB_W * C) * sizeof(float);
+      wgrad_base_kernel<<<blocks, 256, smem, st>>>(noisy, dX, partial, n, height, width, k0, btx, bty);
+      h->launches++;
+    }
     wgrad_reduce_kernel<<<(unsigned)((nbase + WR_OUT - 1) / WR_OUT), WR_OUT * WR_LANES, 0, st>>>(partial, blocks, (int)nbase, vars + L.base, reg1,
                                                                          flat_grads + L.t_base);
-    h->launches += 2;
+    h->launches++;
   }
   BF_CUDA(cudaGetLastError());
   h->tr_n = n; h->tr_h = height; h->tr_w = width;
