@@ -409,6 +409,29 @@ wgrad3x3_x3_ws_kernel(const float* __restrict__ A, const float* __restrict__ G, 
 constexpr int WB3_W = 64, WB3_H = 8, WB3_AW = WB3_W + 2, WB3_AH = WB3_H + 2;
 constexpr int WB3_A_PLANE = WB3_AH * WB3_AW * 16, WB3_G_PLANE = WB3_H * WB3_W * PX_BYTES;
 constexpr int WB3_SMEM = 2 * WB3_A_PLANE + 2 * WB3_G_PLANE;   // 53.9 KB; the cross-warp sums (8 x 432 floats) reuse it
+// One image tile with a one-pixel halo, normalised exactly as the forward pass does (clip(x,0,255)/255 - 0.5, 0 outside the
+// image = the zero padding of the NORMALISED tensor), scaled by 64, as ONE 16-byte chunk per pixel (r, g, b, 0 x 5) in an
+// fp16 hi plane and a lo plane: rows of ldmatrix (.trans for the wgrad: K = pixels; plain for the conv: M = pixels).
+__device__ __forceinline__ void stage_image_tile(int tid, uint32_t aH, uint32_t aL, const float* __restrict__ i_b, int x0, int y0, int h, int wd) {
+  for (int i = tid; i < WB3_AH * WB3_AW; i += NT) {
+    const int ly = i / WB3_AW, lx = i - ly * WB3_AW;
+    const int gx = x0 + lx - 1, gy = y0 + ly - 1;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (gx >= 0 && gx < wd && gy >= 0 && gy < h) {
+      const float* px = i_b + ((size_t)gy * wd + gx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = __fsub_rn(__fdiv_rn(fminf(fmaxf(px[c], 0.f), 255.f), 255.f), 0.5f) * 64.f;
+    }
+    uint4 hi, lo;
+    hi.x = pack_h2(v[0], v[1]); hi.y = pack_h2(v[2], 0.f); hi.z = 0u; hi.w = 0u;
+    float2 f = unpack_h2(hi.x);
+    lo.x = pack_h2(v[0] - f.x, v[1] - f.y);
+    f = unpack_h2(hi.y);
+    lo.y = pack_h2(v[2] - f.x, 0.f); lo.z = 0u; lo.w = 0u;
+    sts128(aH + i * 16, hi);
+    sts128(aL + i * 16, lo);
+  }
+}
 __global__ void __launch_bounds__(NT, 4)
 wgrad_base3_x3_kernel(const float* __restrict__ img, const float* __restrict__ G, float* __restrict__ partial, int n, int h, int wd,
                       int tiles_x, int tiles_y, float g_scale, float out_scale) {
@@ -433,24 +456,7 @@ wgrad_base3_x3_kernel(const float* __restrict__ img, const float* __restrict__ G
     const float* i_b = img + (size_t)b * h * wd * 3;
     const float* g_b = G + (size_t)b * h * wd * C;
     __syncthreads();   // the previous tile's fragments are read
-    for (int i = tid; i < WB3_AH * WB3_AW; i += NT) {
-      const int ly = i / WB3_AW, lx = i - ly * WB3_AW;
-      const int gx = x0 + lx - 1, gy = y0 + ly - 1;
-      float v[3] = {0.f, 0.f, 0.f};
-      if (gx >= 0 && gx < wd && gy >= 0 && gy < h) {
-        const float* px = i_b + ((size_t)gy * wd + gx) * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = __fsub_rn(__fdiv_rn(fminf(fmaxf(px[c], 0.f), 255.f), 255.f), 0.5f) * 64.f;
-      }
-      uint4 hi, lo;
-      hi.x = pack_h2(v[0], v[1]); hi.y = pack_h2(v[2], 0.f); hi.z = 0u; hi.w = 0u;
-      float2 f = unpack_h2(hi.x);
-      lo.x = pack_h2(v[0] - f.x, v[1] - f.y);
-      f = unpack_h2(hi.y);
-      lo.y = pack_h2(v[2] - f.x, 0.f); lo.z = 0u; lo.w = 0u;
-      sts128(aH + i * 16, hi);
-      sts128(aL + i * 16, lo);
-    }
+    stage_image_tile(tid, aH, aL, i_b, x0, y0, h, wd);
     for (int i = tid; i < WB3_H * WB3_W * 2; i += NT) {
       const int hf = i & 1, pix = i >> 1;
       const int ly = pix / WB3_W, lx = pix - ly * WB3_W;
@@ -514,6 +520,79 @@ wgrad_base3_x3_kernel(const float* __restrict__ img, const float* __restrict__ G
 #pragma unroll
     for (int w8 = 0; w8 < 8; ++w8) a += s_red[w8 * 432 + i];
     dst[i] = a * out_scale;
+  }
+}
+
+// Base conv (k0 = 3) of the training forward on the same tile: out[p][co] = sum_{tap, c3} xn[p + tap][c3] * W[tap][c3][co], fp32
+// NHWC16 out.  M = 16 pixels of a tile row, K = two taps (8 padded channels each), N = 16: 5 k-tiles x 2 n-tiles x 3
+// products per 16 pixels; the weight fragments (hi + lo, scaled by W_SCALE) live in registers for the whole kernel.
+// (conv_f32.cu::base_conv_kernel<float>, the FFMA kernel it replaces in the step, normalised every pixel nine times:
+// 134 us at 32 x 256 x 256 against an HBM floor of 25 us.)
+__global__ void __launch_bounds__(NT, 3)
+base_conv3_x3_kernel(const float* __restrict__ img, float* __restrict__ out, const float* __restrict__ w /*[9][3][16]*/, int n, int h, int wd,
+                     int tiles_x, int tiles_y) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t aH = s0, aL = s0 + WB3_A_PLANE;
+  const int g = lane >> 2, q = lane & 3;
+  // B fragments: k-tile j = taps (2j, 2j + 1), b0 = k (2q, 2q + 1) of tap 2j, b1 = the same of tap 2j + 1; n = nt * 8 + g
+  uint32_t wh[5][2][2], wl[5][2][2];
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        const int t = 2 * j + hb, co = nt * 8 + g;
+        float v0 = 0.f, v1 = 0.f;
+        if (t < 9) {
+          if (2 * q < 3) v0 = w[(t * 3 + 2 * q) * C + co] * W_SCALE;
+          if (2 * q + 1 < 3) v1 = w[(t * 3 + 2 * q + 1) * C + co] * W_SCALE;
+        }
+        const uint32_t hh = pack_h2(v0, v1);
+        const float2 f = unpack_h2(hh);
+        wh[j][nt][hb] = hh;
+        wl[j][nt][hb] = pack_h2(v0 - f.x, v1 - f.y);
+      }
+  // ldmatrix (plain) row addresses: matrices (px 0-7, tap 2j), (px 8-15, tap 2j), (px 0-7, tap 2j + 1), (px 8-15, tap 2j + 1)
+  const int mi = lane >> 3, ri = lane & 7;
+  const float out_scale = 1.0f / (64.f * W_SCALE);
+  const int ntiles = tiles_x * tiles_y * n;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const int x0 = tx * WB3_W, y0 = ty * WB3_H;
+    __syncthreads();
+    stage_image_tile(tid, aH, aL, img + (size_t)b * h * wd * 3, x0, y0, h, wd);
+    __syncthreads();
+    const int r = warp, gy = y0 + r;
+    if (gy >= h) continue;
+    float* o_row = out + ((size_t)b * h + gy) * wd * C;
+#pragma unroll 1
+    for (int ks = 0; ks < WB3_W / 16; ++ks) {
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int t = min(2 * j + (mi >> 1), 8), dy = t / 3, dx = t - 3 * dy;   // j = 4: tap 9 does not exist, its weights are zero
+        const uint32_t off = (uint32_t)(((r + dy) * WB3_AW + ks * 16 + ri + 8 * (mi & 1) + dx) * 16);
+        uint32_t ah[4], al[4];
+        ldsm4(ah, aH + off);
+        ldsm4(al, aL + off);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          mma16816(acc[nt], al, make_uint2(wh[j][nt][0], wh[j][nt][1]));
+          mma16816(acc[nt], ah, make_uint2(wl[j][nt][0], wl[j][nt][1]));
+          mma16816(acc[nt], ah, make_uint2(wh[j][nt][0], wh[j][nt][1]));
+        }
+      }
+      // c0, c1 = (pixel g, co 2q, 2q + 1), c2, c3 = (pixel g + 8, ...)
+      const int gx0 = x0 + ks * 16;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        if (gx0 + g < wd) *reinterpret_cast<float2*>(o_row + (size_t)(gx0 + g) * C + nt * 8 + 2 * q) = make_float2(acc[nt][0] * out_scale, acc[nt][1] * out_scale);
+        if (gx0 + g + 8 < wd) *reinterpret_cast<float2*>(o_row + (size_t)(gx0 + g + 8) * C + nt * 8 + 2 * q) = make_float2(acc[nt][2] * out_scale, acc[nt][3] * out_scale);
+      }
+    }
   }
 }
 
@@ -599,6 +678,26 @@ int launch_wgrad_base3_x3(bfcnn_handle* h, const float* img, const float* grad, 
   h->launches++;
   BF_CUDA(cudaGetLastError());
   *parts_out = grid;
+  return BFCNN_OK;
+}
+
+// training forward: normalise + base conv k0 = 3 from the fp32 image [n,h,w,3] into the fp32 NHWC16 map
+int launch_base_conv3_x3(bfcnn_handle* h, const float* img, float* out, const float* w, const Extent& e, cudaStream_t st) {
+  using namespace x3;
+  static bool attr_set_dev[64] = {};
+  bool& attr_set = attr_set_dev[h->device & 63];
+  if (!attr_set) {
+    BF_CUDA(cudaFuncSetAttribute((const void*)base_conv3_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * WB3_A_PLANE));
+    attr_set = true;
+  }
+  BF_REQUIRE(e.he == e.h && e.we == e.w, "training maps have no canvas band");
+  const int tiles_x = (e.we + WB3_W - 1) / WB3_W, tiles_y = (e.he + WB3_H - 1) / WB3_H;
+  const long long ntiles = (long long)tiles_x * tiles_y * e.n;
+  BF_REQUIRE(ntiles < (1ll << 30), "too many tiles");
+  const int grid = (int)std::min<long long>(ntiles, 6ll * h->sm_count);
+  base_conv3_x3_kernel<<<grid, NT, 2 * WB3_A_PLANE, st>>>(img, out, w, e.n, e.he, e.we, tiles_x, tiles_y);
+  h->launches++;
+  BF_CUDA(cudaGetLastError());
   return BFCNN_OK;
 }
 

@@ -56,6 +56,8 @@ int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float*
 
 int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, float* partial, int max_parts, const Extent& e,
                        float g_scale, int* parts_out, cudaStream_t st);
+// training forward: normalise + base conv k0 = 3, fp32 image [n,h,w,3] (0..255) -> fp32 NHWC16, on the same arithmetic
+int launch_base_conv3_x3(bfcnn_handle* h, const float* img, float* out, const float* w, const Extent& e, cudaStream_t st);
 // base-conv wgrad (k0 = 3) on the same arithmetic: img = the fp32 image [n,h,w,3] (0..255), partial [grid][432]
 int launch_wgrad_base3_x3(bfcnn_handle* h, const float* img, const float* grad, float* partial, int max_parts, const Extent& e,
                           float g_scale, int* parts_out, cudaStream_t st);

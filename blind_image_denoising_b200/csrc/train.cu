@@ -1087,7 +1087,8 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   // tcgen05 engine: BN + Add of block i-1 is the prologue of block i's conv_a, and the BN backward of block i the prologue of
   // its conv_b dgrad (conv_t5.cu, PRO = 1); the element-wise kernels remain for the last block and for the other engines
   const bool fuse = t5;
-  BF_CHECK(launch_base_conv(h, noisy, false, Xm(0), vars + L.base, e, st));
+  if (k0 == 3 && x3_mode) BF_CHECK(launch_base_conv3_x3(h, noisy, Xm(0), vars + L.base, e, st));   // tensor cores (conv_x3.cu)
+  else BF_CHECK(launch_base_conv(h, noisy, false, Xm(0), vars + L.base, e, st));
   for (int i = 0; i < N; ++i) {
     if (fuse && i > 0)
       BF_CHECK(launch_conv3x3_t5(h, Xm(i - 1), Tm(i), vars + L.wa[i], nullptr, nullptr, CONV_RELU, e, 64.0f, st, Um(i - 1), Xm(i),
