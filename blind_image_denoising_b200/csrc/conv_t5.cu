@@ -68,16 +68,6 @@ struct Params : Split {   // rows_needed = h, seg_overhead = SEG_OVERHEAD
   float in_scale, out_scale;
 };
 
-// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread moves a whole 32-byte sector, so an fp32 NHWC16 pixel is
-// two full-sector stores instead of four half-sector ones (the 16-byte stores were the epilogue's critical path)
-__device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
-  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
-}
-__device__ __forceinline__ void stg256(float* p, const float4& a, const float4& b) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y),
-               "f"(b.z), "f"(b.w) : "memory");
-}
 // hi / lo split of 8 consecutive channels (one 16-byte chunk of each part)
 __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
   hi.x = pack_h2(a.x, a.y); hi.y = pack_h2(a.z, a.w); hi.z = pack_h2(b.x, b.y); hi.w = pack_h2(b.z, b.w);

@@ -35,6 +35,18 @@ __device__ __forceinline__ void pdl_wait_for_previous() {
   asm volatile("griddepcontrol.wait;\n" ::: "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread moves a whole 32-byte sector, so an fp32 NHWC16 pixel is
+// two full-sector accesses instead of four half-sector ones at a 64-byte stride (those were the critical path of the
+// training conv's epilogue: 115 -> 72 us, and of the head kernels)
+__device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float4& a, const float4& b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y),
+               "f"(b.z), "f"(b.w) : "memory");
+}
+
 // ---- conv_f32.cu
 int launch_base_conv(bfcnn_handle* h, const void* img, bool img_is_u8, float* out, const float* w,
                      const Extent& e, cudaStream_t st);

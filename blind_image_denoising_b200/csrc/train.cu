@@ -562,12 +562,11 @@ __device__ __forceinline__ void head_forward_px(const float (&x)[C], const float
 }
 
 __device__ __forceinline__ void load_px16(const float* __restrict__ p, float (&x)[C]) {
-  const float4* f = reinterpret_cast<const float4*>(p);
+  float4 v[4];
+  ldg256(p, v[0], v[1]);
+  ldg256(p + 8, v[2], v[3]);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 v = f[q];
-    x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
-  }
+  for (int q = 0; q < 4; ++q) { x[4 * q] = v[q].x; x[4 * q + 1] = v[q].y; x[4 * q + 2] = v[q].z; x[4 * q + 3] = v[q].w; }
 }
 
 // forward head + per-sample loss sums in one pass over the last feature map
@@ -634,9 +633,8 @@ head_backward_kernel(const float* __restrict__ feat, const float* __restrict__ g
 #pragma unroll
       for (int o = 0; o < 3; ++o) g[ci * 3 + o] = fmaf(x[ci], dy[o], g[ci * 3 + o]);
     }
-    float4* d = reinterpret_cast<float4*>(dfeat + p * C);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) d[q] = make_float4(dx[4 * q], dx[4 * q + 1], dx[4 * q + 2], dx[4 * q + 3]);
+    stg256(dfeat + p * C, make_float4(dx[0], dx[1], dx[2], dx[3]), make_float4(dx[4], dx[5], dx[6], dx[7]));
+    stg256(dfeat + p * C + 8, make_float4(dx[8], dx[9], dx[10], dx[11]), make_float4(dx[12], dx[13], dx[14], dx[15]));
   }
   block_accumulate<C * 3>(g, G, s_red);
 }
