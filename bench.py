@@ -52,43 +52,76 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 10 ms; only the samples that fall inside the timed region
-    (host timestamps around the CUDA-event bracket) are reported."""
+    """SM clock and throttle reasons DURING the timed region: `nvidia-smi -lms 10` (line-buffered through stdbuf: into a pipe
+    it otherwise flushes in 4 KB blocks, and the lines of a 0.2 s region arrive after it or never) and, beside it, the same
+    NVML counters polled from a thread every 5 ms.  Only samples whose host timestamp falls inside the region are reported;
+    nvidia-smi's are preferred, NVML's fill in when it delivered none (`source` says which)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.nvml, self._stop = index, None, [], [], False
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(self.index)]
+            if os.path.exists("/usr/bin/stdbuf"):
+                cmd = ["/usr/bin/stdbuf", "-oL"] + cmd
+            self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # the process may see a subset of the GPUs (CUDA_VISIBLE_DEVICES): NVML indexes the physical ones
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    phys = int(ids[self.index])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = pynvml
+            self.t2 = threading.Thread(target=self._poll, daemon=True)
+            self.t2.start()
+        except Exception:
+            self._nv = None
 
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append((time.time(), ln.strip()))
 
-    def stop(self, t0: float, t1: float):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
+    def _poll(self):
+        nv = self._nv
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
         try:
-            self.proc.wait(timeout=2)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        inside = [ln for (ts, ln) in self.lines if t0 <= ts <= t1 + 0.03]
-        if not inside:   # region shorter than a sampling period: the closest samples
-            inside = [ln for (ts, ln) in sorted(self.lines, key=lambda p: min(abs(p[0] - t0), abs(p[0] - t1)))[:2]]
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in inside:
+            mx = None
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                self.nvml.append((time.time(), sm, mx, [nm for nm, b in zip(self.NAMES, bits) if r & b]))
+            except Exception:
+                break
+            time.sleep(0.005)
+
+    def stop(self, t0: float, t1: float):
+        self._stop = True
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons, source = [], None, set(), "nvidia-smi -lms 10"
+        for ln in [ln for (ts, ln) in self.lines if t0 <= ts <= t1 + 0.03]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -96,12 +129,18 @@ class ClockSampler:
                 sm.append(float(f[0])); mx = float(f[1])
             except ValueError:
                 continue
-            for nm, v in zip(names, f[2:6]):
+            for nm, v in zip(self.NAMES, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
+        if not sm:
+            source = "NVML (nvmlDeviceGetClockInfo / CurrentClocksThrottleReasons every 5 ms; nvidia-smi delivered no sample inside the region)"
+            for (ts, v, m, rs) in self.nvml:
+                if t0 <= ts <= t1 + 0.005:
+                    sm.append(v); mx = m; reasons.update(rs)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sample inside the timed region"], "samples": 0}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "source": source}
 
 
 # --------------------------------------------------------------------------------------
