@@ -420,7 +420,7 @@ def main():
         from blind_image_denoising_b200 import synthetic_variables, _native
         from blind_image_denoising_b200.training import Trainer
 
-        def train_leg(t_layers: int, tsteps: int = 5):
+        def train_leg(t_layers: int, tsteps: int = 10):
             t_arch = Arch(no_layers=t_layers)
             comm = None
             if world > 1:   # the gradient exchange goes through the C ABI: bfcnn_allreduce_grads on a raw ncclComm_t
@@ -435,7 +435,7 @@ def main():
                 clean, noisy = tr.prepare_data(clean_u8, ncfg, 0, (step * world + rank) * 32)
                 _, _, _, g = tr.train_step_single_gpu(clean, noisy, sync=False)    # nothing read back: steps chain on the stream
                 tr.apply_grads(g)
-            for i in range(2):
+            for i in range(3):
                 train_once(i)
             dp = None
             if world > 1:
