@@ -15,6 +15,7 @@ the hot path over that batch.
   arms      : the fp32-grade arm (precision f16x3, the default of bfcnn.load_model) as a full record of its own:
               value, ms_per_step, e2e, roofline
   training  : BASELINE configs[3] / [4]: 1x18 data-parallel step on every N (and 1x6 at N = 1), with a dp_check at N > 1
+  small_images : BASELINE configs[0] / [1] (1 and 64 images of 256 x 256), device-resident, both tensor-core precisions
   strong    : ONE 4K frame split into row strips over the N ranks (BASELINE configs[2] as written), per-frame latency
   cpu_baseline / --impl reference : the oracle's torch-CPU fp32 restatement of the reference path (TensorFlow cannot be
               installed here), all host threads, on whole 3840x2160 frames with the reference's own pow2 canvas.
@@ -497,6 +498,32 @@ def main():
         if world == 1:
             training["1x6"] = train_leg(6)
 
+    # ---- BASELINE configs[0] / [1]: the 256 x 256 workloads of the metric (device-resident, the drop-in semantics), rank 0's GPU
+    small = None
+    if rank == 0 and not args.no_arms:
+        small = {}
+        for key, name, shape in (("configs[0]", "resnet_color_1x6_bn_16x3x3_256x256_l1_relu", (1, 256, 256, 3)),
+                                 ("configs[1]", "resnet_color_1x12_bn_16x3x3_256x256_l1_relu", (64, 256, 256, 3))):
+            xs = torch.from_numpy(np.random.default_rng(7).integers(0, 256, size=shape, dtype=np.uint8)).cuda()
+            os_ = torch.empty_like(xs)
+            rec = {"workload": f"{name} inference on {shape[0]}x256x256x3 uint8, device-resident"}
+            for prec in ("f16", "f16x3"):
+                ms_model = bfcnn.load_model(name, device=local_rank, precision=prec, allow_synthetic=True)
+                for _ in range(5):
+                    ms_model(xs, out=os_)
+                torch.cuda.synchronize()
+                reps = 50
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    ms_model(xs, out=os_)
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                rec[prec] = {"ms_per_call": ms, "value": shape[0] * 256 * 256 / 1e6 / (ms / 1e3), "unit": UNIT}
+                ms_model.close()
+            small[key] = rec
+    barrier()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         mp_s, med, cores = cpu_reference_mp_s(reps=1)
@@ -521,6 +548,7 @@ def main():
             "arms": arms,
             "strong_scaling": strong,
             "training": training,
+            "small_images": small,
         }
         _emit(line)
     if world > 1:
