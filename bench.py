@@ -41,6 +41,16 @@ UNIT = "MP/s"
 WORKLOAD = f"{MODEL_NAME} inference on synthetic 3840x2160x3 uint8 frames (BASELINE configs[2])"
 
 
+def WEIGHTS_NOTE() -> str:
+    """Where the weights of the benchmarked model directory come from (its pipeline.json says: the reference snapshot ships
+    no resnet weights; throughput does not depend on the values)."""
+    try:
+        with open(os.path.join(ROOT, "blind_image_denoising_b200", "pretrained", MODEL_NAME, "pipeline.json")) as f:
+            return str(json.load(f).get("weights", "unknown"))[:160]
+    except Exception:
+        return "unknown"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -192,7 +202,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "no_layers": N_LAYERS, "frames_per_step": 1, "pad_pow2": True,
-                   "weights": "synthetic seed 0 (reference ships none, SURVEY F2)",
+                   "weights": WEIGHTS_NOTE(),
                    "note": "reference TF path is not installable (tensorflow==2.13.1, no wheel for py3.12, no network); "
                            "this is the oracle's CPU restatement of it; a step is ONE frame (the GPU arm's step is "
                            "frames_per_gpu_per_step frames of the same size: the metric is per pixel)"},
@@ -535,7 +545,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": primary["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD,
-                       "frames_per_gpu_per_step": F, "no_layers": N_LAYERS, "weights": "synthetic seed 0 (reference ships none, SURVEY F2)",
+                       "frames_per_gpu_per_step": F, "no_layers": N_LAYERS, "weights": WEIGHTS_NOTE(),
                        "parity": PARITY[args.precision], "pad_pow2": True,
                        "api": "bfcnn.load_model(name)(uint8 [N,H,W,3]) with its defaults except precision",
                        "l2": f"working set {F * 24.9 * 2 + F * 8.52 * 32 * 2:.0f} MB per step > 126 MB L2 (no flush needed)",

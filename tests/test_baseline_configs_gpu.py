@@ -39,18 +39,23 @@ def _check_u8(u8, u8ref, prec):
 @pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16"])
 def test_config0_1x6_single_256(native_lib, prec):
     """configs[0]: pretrained resnet_color_1x6 on 1x256x256x3 through bfcnn.load_model(name), the drop-in call."""
+    import json
     import warnings
     import bfcnn
+    import blind_image_denoising_b200 as bf
     from oracle import bfcnn_oracle as O
+    name = "resnet_color_1x6_bn_16x3x3_256x256_l1_relu"
     x = np.random.default_rng(0).integers(0, 256, size=(1, 256, 256, 3), dtype=np.uint8)
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
-        m = bfcnn.load_model("resnet_color_1x6_bn_16x3x3_256x256_l1_relu", precision=prec)
-    assert any("SYNTHETIC" in str(i.message) for i in w)          # the shipped directories hold random weights: say so
+        m = bfcnn.load_model(name, precision=prec)
+    marker = json.load(open(os.path.join(bfcnn.models[name]["directory"], "pipeline.json")))["weights"]
+    # a directory that holds random weights says so at every load; trained weights load silently
+    assert any("SYNTHETIC" in str(i.message) for i in w) == marker.startswith("SYNTHETIC")
     with warnings.catch_warnings():
         warnings.simplefilter("error")
-        bfcnn.load_model("resnet_color_1x6_bn_16x3x3_256x256_l1_relu", allow_synthetic=True).close()
-    yref, u8ref = O.denoise(_vars(6), x, pad_pow2=True)
+        bfcnn.load_model(name, allow_synthetic=True).close()
+    yref, u8ref = O.denoise(bf.load_variables(bfcnn.models[name]["directory"]), x, pad_pow2=True)
     _check(m(x, return_float=True), yref, prec, "configs[0]")
     _check_u8(m(x), u8ref, prec)
     m.close()

@@ -117,12 +117,21 @@ def test_tensorbundle_reads_reference_bundle():
     assert len(v) == 95 and v[0].shape == (5, 5, 3, 32) and sum(x.size for x in v) == 334976
 
 
-def test_pretrained_dirs_hold_the_synthetic_weights():
+def test_pretrained_dirs_hold_loadable_weights():
+    """The three model directories `load_model` knows by name: variables of the family's shapes in Keras order, finite, and
+    a pipeline.json that says where the weights come from (trained here, or synthetic: the reference ships none)."""
+    import json
+    import os
     for n in (6, 12, 18):
         name = f"resnet_color_1x{n}_bn_16x3x3_256x256_l1_relu"
-        v = bf.load_variables(bf.models[name]["directory"])
+        d = bf.models[name]["directory"]
+        v = bf.load_variables(d)
         ref = synthetic_variables(Arch(no_layers=n), 0)
-        assert all(np.array_equal(x, y) for x, y in zip(v, ref))
+        assert len(v) == len(ref) and all(x.shape == y.shape and np.isfinite(x).all() for x, y in zip(v, ref))
+        marker = json.load(open(os.path.join(d, "pipeline.json")))["weights"]
+        assert marker.startswith("TRAINED") or marker.startswith("SYNTHETIC")
+        if marker.startswith("SYNTHETIC"):
+            assert all(np.array_equal(x, y) for x, y in zip(v, ref))
 
 
 def test_pipelined_denoiser_host_logic():

@@ -111,15 +111,17 @@ def test_torch_device_tensors(native_lib):
 
 
 def test_load_model_pretrained_dirs(native_lib):
-    """bfcnn.load_model(name) reads the (synthetic) TensorBundle shipped under pretrained/."""
+    """bfcnn.load_model(name) reads the TensorBundle shipped under pretrained/: the oracle on the same variables agrees."""
     import bfcnn
+    import blind_image_denoising_b200 as bf
+    from oracle import bfcnn_oracle as O
     name = "resnet_color_1x6_bn_16x3x3_256x256_l1_relu"
     assert name in bfcnn.models
-    m = bfcnn.load_model(name)
+    m = bfcnn.load_model(name, allow_synthetic=True)
     rng = np.random.default_rng(1)
     x = rng.integers(0, 256, size=(1, 256, 256, 3), dtype=np.uint8)
     y = m(x)
-    _, u8ref = _oracle(6, x)
+    _, u8ref = O.denoise(bf.load_variables(bfcnn.models[name]["directory"]), x, pad_pow2=True)
     du = np.abs(y.astype(np.int32) - u8ref.astype(np.int32))
     assert du.max() <= 1 and (du > 0).mean() < 0.01
 

@@ -1,0 +1,52 @@
+"""The reference's own test of its pretrained models (reference tests/bfcnn/test_pretrained.py:23-80) on the model directories
+shipped here: for every registered model and noise_std in {10, 15, 20, 25, 30}, original + truncated normal noise, clip,
+round, uint8 -> `bfcnn.models[name]["denoiser"]()` -> PSNR, SSIM and MAE against the original all improve.
+
+The images are the held-out set: 160 x 160 windows of the reference's four 512 x 512 stock images
+(tests/golden/natural_inputs.npz); the shipped weights were trained on other images (tools/train_pretrained.py).
+tf.random.truncated_normal(seed=0) cannot be reproduced without TensorFlow: the draws come from the oracle's sampler."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NAMES = [f"resnet_color_1x{n}_bn_16x3x3_256x256_l1_relu" for n in (6, 12, 18)]
+
+
+def _psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2, axis=(1, 2, 3))
+    return float(np.mean(10.0 * np.log10(255.0 ** 2 / mse)))
+
+
+@pytest.mark.parametrize("noise_std", [10.0, 15.0, 20.0, 25.0, 30.0])
+@pytest.mark.parametrize("model_name", NAMES)
+def test_pretrained_models(native_lib, noise_std, model_name):
+    import torch
+    import bfcnn
+    from oracle import bfcnn_oracle as O
+    from oracle import corrupt_oracle as C
+    assert model_name in bfcnn.models
+    module_denoiser = bfcnn.models[model_name]["denoiser"]()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "natural_inputs.npz"))
+    img_original = z["clean"]
+    pix = np.arange(160 * 160, dtype=np.uint32).reshape(160, 160)
+    noise = np.stack([np.stack([C.truncated_normal_det(pix, 3 + ch, 100 + k, int(noise_std)) for ch in range(3)], -1)
+                      for k in range(img_original.shape[0])])
+    img_noisy = np.rint(np.clip(img_original.astype(np.float32) + np.float32(noise_std) * noise, 0, 255)).astype(np.uint8)
+    img_denoised = module_denoiser(img_noisy)
+    module_denoiser.close()
+    assert img_denoised.shape == img_noisy.shape == img_original.shape and img_denoised.dtype == np.uint8
+    # psnr test
+    assert _psnr(img_original, img_noisy) < _psnr(img_original, img_denoised)
+    # ssim test (tf.image.ssim restated, max_val 255)
+    t = lambda a: torch.as_tensor(a.astype(np.float64))
+    ssim_noisy = float(O.ssim_tf(t(img_original), t(img_noisy), filter_size=11).mean())
+    ssim_denoised = float(O.ssim_tf(t(img_original), t(img_denoised), filter_size=11).mean())
+    assert ssim_noisy < ssim_denoised
+    # mae test
+    mae = lambda a, b: float(np.abs(a.astype(np.float64) - b.astype(np.float64)).mean())
+    assert mae(img_original, img_denoised) < mae(img_original, img_noisy)
+    print(f"{model_name} sigma {noise_std}: PSNR {_psnr(img_original, img_noisy):.2f} -> {_psnr(img_original, img_denoised):.2f} dB, "
+          f"SSIM {ssim_noisy:.4f} -> {ssim_denoised:.4f}, MAE {mae(img_original, img_noisy):.2f} -> {mae(img_original, img_denoised):.2f}")

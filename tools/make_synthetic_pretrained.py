@@ -3,7 +3,11 @@
 setup.py:59-73) with DETERMINISTIC SYNTHETIC weights, in the reference's on-disk
 format (SavedModel variables bundle + pipeline.json).  The real pretrained blobs are
 absent from the reference snapshot; drop real `saved_model/variables/`
-files over these and `load_model(name)` picks them up unchanged."""
+files over these and `load_model(name)` picks them up unchanged.
+
+The repository now ships weights TRAINED with its own training path (tools/train_pretrained.py); this tool leaves a
+directory whose pipeline.json says so alone unless called with --force (parity tests and the benchmark take their
+deterministic weights from `synthetic_variables` / `synthetic_model`, not from these directories)."""
 import json
 import sys
 from pathlib import Path
@@ -18,6 +22,10 @@ for n in (6, 12, 18):
     name = f"resnet_color_1x{n}_bn_16x3x3_256x256_l1_relu"
     arch = Arch(no_layers=n)
     d = root / "pretrained" / name
+    if (d / "pipeline.json").exists() and "--force" not in sys.argv:
+        if str(json.loads((d / "pipeline.json").read_text()).get("weights", "")).startswith("TRAINED"):
+            print("kept (trained weights)", d)
+            continue
     (d / "saved_model" / "variables").mkdir(parents=True, exist_ok=True)
     write_model_variables(str(d / "saved_model" / "variables"), synthetic_variables(arch, seed=0))
     cfg = default_pipeline_config(arch, name)
