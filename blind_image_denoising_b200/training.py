@@ -411,6 +411,17 @@ class ImagePipeline:
         per_rank = len(self.sources[self.rank::self.world])
         return (per_rank * self.crops_per_image) // self.batch_size
 
+    def _source(self, i: int, dev: str):
+        """Source i as the pipeline crops it: a file name (decoded on the host at every visit, as the reference's map stage
+        does), or -- in-memory images -- a uint8 CUDA tensor uploaded once, so that an epoch moves no pixels over PCIe."""
+        src = self.sources[i]
+        if isinstance(src, str):
+            return src
+        cache = self.__dict__.setdefault("_dev_sources", {})
+        if i not in cache:
+            cache[i] = _torch().from_numpy(src).to(dev)
+        return cache[i]
+
     def _crops(self, src, rng: np.random.Generator):
         img = load_image(src, num_channels=3, expand_dims=False) if isinstance(src, str) else src
         ch, cw = int(self.input_shape[0]), int(self.input_shape[1])
@@ -443,13 +454,16 @@ class ImagePipeline:
         for p0 in range(0, len(order), self.pool_images):
             crops, kept = [], 0
             for i in order[p0:p0 + self.pool_images]:
-                cr = self._crops(self.sources[int(i)], rng)
+                cr = self._crops(self._source(int(i), dev), rng)
                 if cr:
                     crops += cr
                     kept += 1
             if not crops:
                 continue
-            u8 = torch.from_numpy(np.stack(crops)).pin_memory().to(dev, non_blocking=True)
+            if torch.is_tensor(crops[0]):   # in-memory sources live on the GPU: the crops are device-side slices
+                u8 = torch.stack(crops)
+            else:
+                u8 = torch.from_numpy(np.stack(crops)).pin_memory().to(dev, non_blocking=True)
             # global sample index of the pool's first crop: unique per (rank, epoch, position), aligned to c
             sample_offset = ((self.rank << 40) + (int(e) * shard_len + p0)) * c
             clean, noisy = self.trainer.prepare_data(u8, self.noise_cfg, self.seed, sample_offset)
