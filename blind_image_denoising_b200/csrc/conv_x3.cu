@@ -2,7 +2,7 @@
 //
 // Same contract as conv3x3_c16_kernel (conv_f32.cu): fp32 NHWC16 in, fp32 NHWC16 out, zero "same" padding, fused
 // epilogue (ReLU / residual add / per-channel batch statistics / ReLU-mask for the backward pass).  The arithmetic is
-// the F16X3 scheme of fused_f16.cu: activations and weights are split into fp16 hi + lo parts on the fly and every tap
+// the F16X3 scheme: activations and weights are split into fp16 hi + lo parts on the fly and every tap
 // issues hi*hi + lo*hi + hi*lo on mma.sync.m16n8k16 with fp32 accumulation -- error ~2^-21 relative, i.e. FP32-grade,
 // which is what the gradient parity gate (cosine >= 0.9999, max error <= 1e-3 of the gradient scale) needs.
 // Used for the forward convs (backbone_blocks.py:167-246 in training mode) and for the dgrad convs of

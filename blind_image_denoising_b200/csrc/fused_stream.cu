@@ -1,8 +1,8 @@
 // fused_stream.cu -- the fused conv-BN-ReLU residual stack on tcgen05 as a ROW-STREAMING pipeline (sm_100a).
 //
-// Same arithmetic and operand layouts as fused_umma.cu (M = 128 pixels of one image row per MMA, channel-half planes in
-// the SWIZZLE_NONE K-major layout so that a dx tap is a descriptor shift, N = 48 dy-scatter into three accumulator
-// blocks), but the work unit is no longer a 128 x rh region with a vertical halo that every layer recomputes.  A CTA
+// M = 128 pixels of one image row per MMA, activations as channel-half planes in the SWIZZLE_NONE K-major layout so that a dx
+// tap is a descriptor shift, N = 48 dy-scatter into three accumulator blocks.  The work unit is not a
+// 128 x rh region with a vertical halo that every layer recomputes (the first engine of round 1, removed).  A CTA
 // owns a 128-pixel-wide column strip segment and streams DOWN it: all 2*nblk conv layers of the pass are in flight at
 // once, layer l+1 trailing layer l by LAG = 3 row groups, every layer advancing one group of 2 rows per step.  Only the
 // horizontal halo (2*nblk columns per side) is recomputed: 94 % of the MMAs are useful at nblk = 2 (the region kernel:

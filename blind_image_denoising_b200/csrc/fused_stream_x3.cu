@@ -6,8 +6,8 @@
 // parts (four channel-half planes), the feature map between passes carries both parts (the virtual-row map of
 // fused_stream.cu twice: the lo map behind the hi map, a second "image" to the tensor map).
 // One residual block (two convs) per pass: the rings of two blocks with both parts do not fit in shared memory.
-// It replaces the region kernel of fused_umma_x3.cu as the engine of precision "f16x3" (BFCNN_X3_REGIONS=1 selects the
-// region kernel); kept in its own translation unit so that the F16 kernel's code generation is untouched.
+// Kept in its own translation unit so that the F16 kernel's code generation is untouched; the shared pieces are in
+// stream_common.cuh.
 //
 // Reference arithmetic: module_denoiser.py:53-73, backbone_blocks.py:167-246 (block), model.py:297-342 (head),
 // utilities.py:435-443 (denormalise).

@@ -1,4 +1,4 @@
-// umma_ptx.cuh -- inline-PTX helpers shared by the tcgen05 kernels (fused_umma.cu, fused_stream.cu): shared-memory
+// umma_ptx.cuh -- inline-PTX helpers shared by the tcgen05 kernels (fused_stream*.cu, conv_t5.cu, base_conv_t5.cu): shared-memory
 // matrix / instruction descriptors, tcgen05.mma / commit / ld / st, mbarriers, TMA tile loads, fp16 packing.
 #pragma once
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
