@@ -134,7 +134,8 @@ def load_model(model_path: str, **kwargs) -> Denoiser:
     """reference bfcnn/__init__.py:81-97 (same argument checks and messages).
 
     Returns a callable mapping uint8 [N,H,W,3] to the denoised uint8 tensor.
-    Keyword-only extras: device=0, precision="f16x3"|"f16"|"fp32", pad_pow2=True, allow_synthetic=False (the shipped
+    Keyword-only extras: device=0, precision="f16x3"|"f16"|"fp32"|"auto" (auto: f16 when a calibration run at load shows
+    it within half the fp32 gate of f16x3 for these weights, Denoiser._calibrate), pad_pow2=True, allow_synthetic=False (the shipped
     model directories hold synthetic weights, SURVEY F2: loading them warns unless this is set)."""
     if model_path is None or len(model_path) <= 0:
         raise ValueError("model_path cannot be empty")

@@ -74,3 +74,48 @@ def test_pretrained_models_match_the_oracle(native_lib, model_name, prec):
     print(f"{model_name} [{prec}]: max-abs {d.max():.5f} mean-abs {d.mean():.6f}")
     assert d.max() <= gate[0] and d.mean() <= gate[1], (d.max(), d.mean())
     assert np.abs(u8.astype(int) - u8ref.astype(int)).max() <= (2 if prec == "f16" else 1)
+
+
+def test_auto_precision(native_lib):
+    """precision="auto" takes the fast arithmetic only when a calibration run at load keeps it within half the fp32 gate of
+    the fp32-grade one.  Glorot-scale random weights fail it (0.9 / 0.07), and so do the shipped trained models: on the
+    probe with saturated colours in a corner their residual stream grows to |X| ~ 200, where fp16 rounding of the stream
+    costs up to ~13 on the 0-255 scale (1x18) while f16x3 stays within 0.02 of the oracle -- the reason f16x3 is the
+    default of load_model."""
+    import bfcnn
+    import blind_image_denoising_b200 as bf
+    for name in NAMES:
+        m = bfcnn.load_model(name, precision="auto")
+        c = m.calibration
+        assert m.precision == c["chosen"] == ("f16" if (c["max_abs"] <= 0.25 and c["mean_abs"] <= 0.025) else "f16x3"), c
+        print(f"{name}: f16 vs f16x3 on the probes max-abs {c['max_abs']:.3f} mean-abs {c['mean_abs']:.4f} -> {c['chosen']}")
+        m.close()
+    s = bf.synthetic_model(18, precision="auto")
+    assert s.precision == "f16x3", s.calibration
+    x = np.random.default_rng(0).integers(0, 256, size=(1, 40, 50, 3), dtype=np.uint8)
+    assert np.array_equal(s(x), s(x, precision="f16x3"))
+    s.close()
+    with pytest.raises(ValueError):
+        bf.synthetic_model(6, precision="bf16")
+
+
+def test_default_precision_is_robust_where_f16_is_not(native_lib):
+    """A synthetic ramp with noise drives the trained 1x18 model's residual stream to |X| ~ 200 in the corner of saturated
+    colours.  The default arithmetic (f16x3) stays within the fp32 gate of the fp64 oracle there; f16 does not (its stated
+    gate holds on the noise and natural-image inputs of the other tests, not on this one)."""
+    import bfcnn
+    import blind_image_denoising_b200 as bf
+    from oracle import bfcnn_oracle as O
+    size = 128
+    yy, xx = np.mgrid[0:size, 0:size]
+    ramp = np.stack([(yy + xx) * 255.0 / (2 * size - 2), yy * 255.0 / (size - 1), xx * 255.0 / (size - 1)], -1)
+    x = np.clip(ramp + np.random.default_rng(0).normal(0.0, 20.0, ramp.shape), 0, 255).round().astype(np.uint8)[None]
+    variables = bf.load_variables(bfcnn.models[NAMES[2]]["directory"])
+    yref, _ = O.denoise(variables, x, pad_pow2=True)
+    m = bfcnn.load_model(NAMES[2])
+    d3 = np.abs(m(x, return_float=True).astype(np.float64) - yref)
+    d1 = np.abs(m(x, precision="f16", return_float=True).astype(np.float64) - yref)
+    m.close()
+    print(f"ramp probe, trained 1x18: f16x3 max-abs {d3.max():.4f} mean {d3.mean():.5f}; f16 max-abs {d1.max():.3f} mean {d1.mean():.4f}")
+    assert d3.max() <= 0.5 and d3.mean() <= 0.05
+    assert d1.max() > d3.max()
