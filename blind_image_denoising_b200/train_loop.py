@@ -167,7 +167,7 @@ def _load_weights_dir(weights_dir: str) -> List[np.ndarray]:
 def train_loop(pipeline_config_path: Union[str, Dict, Path],
                checkpoint_directory: Union[str, Path],
                weights_dir: Union[str, Path] = None,
-               *, images: Optional[Sequence[np.ndarray]] = None, device: Optional[int] = None):
+               *, images: Optional[Sequence[np.ndarray]] = None, device: Optional[int] = None, on_finish=None):
     """Trains a blind image denoiser (reference train_loop.py:40-601).
 
     :param pipeline_config_path: filepath to the configuration (or the dict itself)
@@ -175,6 +175,7 @@ def train_loop(pipeline_config_path: Union[str, Dict, Path],
     :param weights_dir: directory to load weights from
     :param images: (extension) in-memory uint8 images [H,W,3] instead of `dataset.inputs[*].directory`
     :param device: (extension) CUDA device ordinal; default LOCAL_RANK or 0
+    :param on_finish: (extension) callable(hydra) run on every rank after the last step, before the model is closed
     :return:
     """
     import torch
@@ -342,6 +343,8 @@ def train_loop(pipeline_config_path: Union[str, Dict, Path],
     if ckpt.step > 0:
         last_record = log_metrics({"training/learning_rate": float(lr_schedule(max(int(optimizer.iterations) - 1, 0))), "final": True})
     torch.cuda.synchronize(device)
+    if on_finish is not None:
+        on_finish(hydra)
     hydra.close()
     logger.info("finished training")
     return
