@@ -257,8 +257,8 @@ conv3x3_t5_kernel(const Params p) {
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
                   mma_lo(d, a_lo + arow + dx, b_hi + boff + dx * BDX, id);
-                  mma_lo(d, a_hi + arow + dx, b_lo + boff + dx * BDX, id);
-                  mma_lo(d, a_hi + arow + dx, b_hi + boff + dx * BDX, id);
+                  mma_lo_fill(d, a_hi + arow + dx, b_lo + boff + dx * BDX, id);      // hi*lo and hi*hi share their A operand:
+                  mma_lo_lastuse(d, a_hi + arow + dx, b_hi + boff + dx * BDX, id);   // one shared-memory read (A collector)
                 }
               }
             }

@@ -44,6 +44,22 @@ __device__ __forceinline__ void mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t 
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc)
       : "memory");
 }
+// The same with the A-operand collector: `fill` keeps the A operand this MMA fetched in the tensor core's collector buffer,
+// `lastuse` takes A from there instead of shared memory (same A descriptor, the next MMA of the issue stream) and releases
+// it.  SASS: UTCHMMA gdesc[..].A_KEEP / .A_REUSE.  In the F16X3 arithmetic hi*lo and hi*hi of a tap share their A operand
+// (the hi activations): one 4 KB shared-memory read instead of two.
+__device__ __forceinline__ void mma_lo_fill(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_lo_lastuse(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 1, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc)
+      : "memory");
+}
 // one lane of a converged warp; the compiler keeps the tcgen05 operands in uniform registers only on this path
 // (a plain `lane == 0` branch wraps every UTCHMMA in an ELECT/BRA.U.ANY loop: 392 instead of 143 cycles per row)
 __device__ __forceinline__ uint32_t elect_one_sync() {
