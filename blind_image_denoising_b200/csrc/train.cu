@@ -596,6 +596,10 @@ head_loss_kernel(const float* __restrict__ feat, const float* __restrict__ gt, c
 }
 
 // backward of loss + head: dX = Wc * dy ; G[ci][o] += x[ci]*dy[o]
+// Four lanes per pixel, lane q of the quad owns channels 4q..4q+3: one coalesced 16-byte load and store per lane, 12 G
+// accumulators (the one-thread-per-pixel version held 48 and a whole pixel, 153 registers: one CTA per SM and 126 us
+// against an HBM floor of 45 us).  Lane o < 3 of a quad evaluates output channel o (tanh, loss derivative); the three dy
+// travel through the quad by shuffle.
 __global__ void __launch_bounds__(256)
 head_backward_kernel(const float* __restrict__ feat, const float* __restrict__ gt, const float* __restrict__ wc,
                      const float* __restrict__ coef, const float* __restrict__ dpred_extra /* SSIM term or nullptr */,
@@ -603,40 +607,82 @@ head_backward_kernel(const float* __restrict__ feat, const float* __restrict__ g
   __shared__ float s_wc[C * 4];
   __shared__ float s_red[C * 3];
   if (threadIdx.x < C * 4) s_wc[threadIdx.x] = wc[threadIdx.x];
+  if (threadIdx.x < C * 3) s_red[threadIdx.x] = 0.f;
   __syncthreads();
   const int s = blockIdx.y;
+  const int q = threadIdx.x & 3, lane = threadIdx.x & 31;
   const float c_mae = coef[0], c_mse = coef[1 + s];
-  float g[C * 3];
+  float w4[4][3];   // this lane's rows of Wc
 #pragma unroll
-  for (int k = 0; k < C * 3; ++k) g[k] = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < px_per_sample; i += gridDim.x * blockDim.x) {
-    const size_t p = (size_t)s * px_per_sample + i;
-    float x[C], th[3], pr[3], dy[3];
-    load_px16(feat + p * C, x);
-    head_forward_px(x, s_wc, th, pr);
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int o = 0; o < 3; ++o) w4[k][o] = s_wc[(4 * q + k) * 4 + o];
+  float g[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int o = 0; o < 3; ++o) g[k][o] = 0.f;
+  const int quads = (gridDim.x * blockDim.x) >> 2;
+  // every lane of a warp runs the same number of iterations (shuffles inside): the bound is per quad-slot of the warp
+  for (int i0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 2; i0 < px_per_sample; i0 += quads) {
+    const int i = i0 + (lane >> 2);
+    const bool ok = i < px_per_sample;
+    const size_t p = (size_t)s * px_per_sample + (ok ? i : 0);
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) x = *reinterpret_cast<const float4*>(feat + p * C + 4 * q);
+    float y[3];
 #pragma unroll
     for (int o = 0; o < 3; ++o) {
-      const float e = gt[p * 3 + o] - pr[o];
+      float a = fmaf(x.x, w4[0][o], fmaf(x.y, w4[1][o], fmaf(x.z, w4[2][o], x.w * w4[3][o])));
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      y[o] = a;
+    }
+    float dyq = 0.f;
+    if (ok && q < 3) {
+      const float yo = q == 0 ? y[0] : (q == 1 ? y[1] : y[2]);
+      const float th = tanhf(2.0f * yo);
+      const float t = th * 0.51f;
+      const float pr = (fminf(fmaxf(t, -0.5f), 0.5f) + 0.5f) * 255.0f;
+      const float e = gt[p * 3 + q] - pr;
       const float ae = fabsf(e);
       const float sgn = (e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f);
       float de = c_mae * sgn * keras_relu_grad(ae, hinge, cutoff);
       de += c_mse * keras_relu(e, hinge, cutoff * cutoff) * keras_relu_grad(e, hinge, cutoff * cutoff);
-      const float dpred = -de + (dpred_extra ? dpred_extra[p * 3 + o] : 0.f);
-      const float t = th[o] * 0.51f;
+      const float dpred = -de + (dpred_extra ? dpred_extra[p * 3 + q] : 0.f);
       const float pass = (t >= -0.5f && t <= 0.5f) ? 1.f : 0.f;   // clip_by_value gradient
-      dy[o] = dpred * 255.0f * pass * 0.51f * 2.0f * (1.0f - th[o] * th[o]);
+      dyq = dpred * 255.0f * pass * 0.51f * 2.0f * (1.0f - th * th);
     }
-    float dx[C];
+    float dy[3];
 #pragma unroll
-    for (int ci = 0; ci < C; ++ci) {
-      dx[ci] = s_wc[ci * 4 + 0] * dy[0] + s_wc[ci * 4 + 1] * dy[1] + s_wc[ci * 4 + 2] * dy[2];
+    for (int o = 0; o < 3; ++o) dy[o] = __shfl_sync(0xffffffffu, dyq, (lane & ~3) + o);
+    if (ok) {
+      float4 dx;
+      dx.x = w4[0][0] * dy[0] + w4[0][1] * dy[1] + w4[0][2] * dy[2];
+      dx.y = w4[1][0] * dy[0] + w4[1][1] * dy[1] + w4[1][2] * dy[2];
+      dx.z = w4[2][0] * dy[0] + w4[2][1] * dy[1] + w4[2][2] * dy[2];
+      dx.w = w4[3][0] * dy[0] + w4[3][1] * dy[1] + w4[3][2] * dy[2];
+      *reinterpret_cast<float4*>(dfeat + p * C + 4 * q) = dx;
+      const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-      for (int o = 0; o < 3; ++o) g[ci * 3 + o] = fmaf(x[ci], dy[o], g[ci * 3 + o]);
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int o = 0; o < 3; ++o) g[k][o] = fmaf(xv[k], dy[o], g[k][o]);
     }
-    stg256(dfeat + p * C, make_float4(dx[0], dx[1], dx[2], dx[3]), make_float4(dx[4], dx[5], dx[6], dx[7]));
-    stg256(dfeat + p * C + 8, make_float4(dx[8], dx[9], dx[10], dx[11]), make_float4(dx[12], dx[13], dx[14], dx[15]));
   }
-  block_accumulate<C * 3>(g, G, s_red);
+  // lanes with equal q hold the same G entries: sum them inside the warp, then the CTA, then double atomics
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      float v = g[k][o];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4) atomicAdd(&s_red[(4 * q + k) * 3 + o], v);
+    }
+  __syncthreads();
+  if (threadIdx.x < C * 3) atomicAdd(&G[threadIdx.x], (double)s_red[threadIdx.x]);
 }
 
 // dH0 = G * H1^T ; dH1 = H0^T * G  (+ L2 regulariser gradient 2*0.01*lambda*w, model.py:275)
@@ -1124,7 +1170,8 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
                                          loss_coef);
   step_scalars_kernel<<<1, 32, 0, st>>>(loss_scal, regd, cfg->regularization, out4_d);
   // ---- backward: head
-  head_backward_kernel<<<lgrid, 256, 0, st>>>(Xm(N), clean, head_c, loss_coef, use_ssim ? ss_dpred : nullptr, dXa, Gd, px_per_sample,
+  const dim3 bgrid4((unsigned)std::max(1, std::min((px_per_sample * 4 + 255) / 256, (16 * h->sm_count + n - 1) / n)), (unsigned)n);
+  head_backward_kernel<<<bgrid4, 256, 0, st>>>(Xm(N), clean, head_c, loss_coef, use_ssim ? ss_dpred : nullptr, dXa, Gd, px_per_sample,
                                               cfg->hinge, cfg->cutoff);
   const float reg1 = cfg->regularization * 0.01f;          // d/dw lambda*0.01*|w|
   const float reg2 = cfg->regularization * 0.01f * 2.0f;   // d/dw lambda*0.01*w^2
