@@ -9,7 +9,9 @@ noise 5..40, multiplicative 0.05..0.1, flips), the loss of the `_l1_` models (hi
 Evaluation: the held-out 512 x 512 stock images at sigma = 20 (tests/golden/natural_inputs.npz, the recipe of the
 reference's tests/bfcnn/test_pretrained.py:41-80): MAE / PSNR of the noisy input against the denoised output.
 
-python tools/train_pretrained.py [steps] [layers ...]      # on the GPU box; results under gpurun_out/trained/"""
+python tools/train_pretrained.py [steps] [layers ...]      # on the GPU box; results under gpurun_out/trained/
+TRAIN_SSIM=1 adds the (1 - SSIM) term of the reference's default loss (ssim_multiplier 1.0, loss.py:171): results under
+gpurun_out/trained_ssim/ (an end-to-end check of the SSIM forward / backward kernels, not shipped)."""
 import json
 import logging
 import os
@@ -32,7 +34,8 @@ logging.basicConfig(level=logging.WARNING)
 z = np.load(os.path.join(ROOT, "data", "train_images.npz"))
 images = [z[k] for k in z.files]
 nat = np.load(os.path.join(ROOT, "tests", "golden", "natural_inputs.npz"))
-out_root = os.path.join(ROOT, "gpurun_out", "trained")
+with_ssim = os.environ.get("TRAIN_SSIM", "0") == "1"
+out_root = os.path.join(ROOT, "gpurun_out", "trained_ssim" if with_ssim else "trained")
 
 
 def psnr(a, b):
@@ -44,6 +47,8 @@ for n in layers:
     arch = Arch(no_layers=n)
     cfg = default_pipeline_config(arch, name)
     cfg["dataset"].update({"no_crops_per_image": 16, "seed": n})
+    if with_ssim:
+        cfg["loss"]["ssim_multiplier"] = 1.0
     cfg["train"] = {"epochs": -1, "total_steps": steps, "gpu_batches_per_step": 1, "exact_accumulation": True,
                     "checkpoints_to_keep": 2, "checkpoint_every": steps // 4, "visualization_every": max(steps // 20, 1),
                     "optimizer": {"type": "ADAM", "gradient_clipping_by_norm": 1.0,
