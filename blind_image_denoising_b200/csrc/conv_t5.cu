@@ -63,6 +63,8 @@ struct Params : Split {   // rows_needed = h, seg_overhead = SEG_OVERHEAD
   const float* in2;     // PRO = 1: second input map
   float* out2;          // PRO = 1: the combined input is written here
   const float* coef;    // PRO = 1: [3][16] per-channel ca, cb, cc
+  uint16_t* mask_out;   // CONV_RELU: bit c of pixel p = (output channel c > 0), or nullptr
+  const uint16_t* mask_in;   // CONV_MASK: that map instead of `res` (2 B/pixel instead of 64), or nullptr
   double* stats;        // [32]: per-channel sum, sum of squares (CONV_STATS)
   int n, h, wd;
   float in_scale, out_scale;
@@ -156,14 +158,20 @@ conv3x3_t5_kernel(const Params p) {
         // the residual / mask operand of BOTH rows of this step is fetched before the wait for the MMAs (its address does
         // not depend on them): the global-load latency hides behind the wait instead of sitting on the epilogue's path
         float4 rva[2][4];
+        uint32_t mva[2] = {0u, 0u};
+        const bool bitmask = (EPI == CONV_MASK) && p.mask_in != nullptr;   // warp-uniform
         if (EPI == CONV_RESIDUAL || EPI == CONV_MASK) {
 #pragma unroll
           for (int k2 = 0; k2 < 2; ++k2) {
             const int rho = G * w + rsel0 + 2 * k2;
             if (w >= 0 && col_out && rho >= 1 && rho < P - 1) {
-              const long long o = (px0 + (long long)rho * p.wd) * C;
-              ldg256(p.res + o, rva[k2][0], rva[k2][1]);
-              ldg256(p.res + o + 8, rva[k2][2], rva[k2][3]);
+              if (bitmask) {
+                mva[k2] = p.mask_in[px0 + (long long)rho * p.wd];
+              } else {
+                const long long o = (px0 + (long long)rho * p.wd) * C;
+                ldg256(p.res + o, rva[k2][0], rva[k2][1]);
+                ldg256(p.res + o + 8, rva[k2][2], rva[k2][3]);
+              }
             }
           }
         }
@@ -184,6 +192,7 @@ conv3x3_t5_kernel(const Params p) {
           tmem_zero16(taddr);
           if (ok) {
             float4 fo[4];
+            uint32_t mbits = 0u;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float4 f = make_float4(__uint_as_float(v[4 * q]) * p.out_scale, __uint_as_float(v[4 * q + 1]) * p.out_scale,
@@ -192,16 +201,25 @@ conv3x3_t5_kernel(const Params p) {
                 ssum[4 * q] += f.x; ssum[4 * q + 1] += f.y; ssum[4 * q + 2] += f.z; ssum[4 * q + 3] += f.w;
                 ssq[4 * q] += f.x * f.x; ssq[4 * q + 1] += f.y * f.y; ssq[4 * q + 2] += f.z * f.z; ssq[4 * q + 3] += f.w * f.w;
               }
-              if (EPI == CONV_RELU) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+              if (EPI == CONV_RELU) {
+                f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
+                mbits |= ((f.x > 0.f ? 1u : 0u) | (f.y > 0.f ? 2u : 0u) | (f.z > 0.f ? 4u : 0u) | (f.w > 0.f ? 8u : 0u)) << (4 * q);
+              }
               if (EPI == CONV_RESIDUAL) { f.x += rv[q].x; f.y += rv[q].y; f.z += rv[q].z; f.w += rv[q].w; }
               if (EPI == CONV_MASK) {   // ReLU backward: pass the gradient where the saved activation is > 0
-                f.x = rv[q].x > 0.f ? f.x : 0.f; f.y = rv[q].y > 0.f ? f.y : 0.f;
-                f.z = rv[q].z > 0.f ? f.z : 0.f; f.w = rv[q].w > 0.f ? f.w : 0.f;
+                if (bitmask) {
+                  const uint32_t mq = mva[k2] >> (4 * q);
+                  f.x = (mq & 1u) ? f.x : 0.f; f.y = (mq & 2u) ? f.y : 0.f; f.z = (mq & 4u) ? f.z : 0.f; f.w = (mq & 8u) ? f.w : 0.f;
+                } else {
+                  f.x = rv[q].x > 0.f ? f.x : 0.f; f.y = rv[q].y > 0.f ? f.y : 0.f;
+                  f.z = rv[q].z > 0.f ? f.z : 0.f; f.w = rv[q].w > 0.f ? f.w : 0.f;
+                }
               }
               fo[q] = f;
             }
             stg256(p.out + o, fo[0], fo[1]);
             stg256(p.out + o + 8, fo[2], fo[3]);
+            if (EPI == CONV_RELU && p.mask_out != nullptr) p.mask_out[px0 + (long long)rho * p.wd] = (uint16_t)mbits;
           }
           tmem_wait_st();
           tc_fence_before();
@@ -396,7 +414,7 @@ conv3x3_t5_kernel(const Params p) {
 
 int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
                       ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st, const float* in2, float* out2,
-                      const float* coef) {
+                      const float* coef, uint16_t* relu_mask) {
   using namespace t5;
   BF_REQUIRE(in_scale > 0.f, "in_scale must be a positive power of two");
   static bool attr_set_dev[64] = {};   // function attributes are per device: one flag per device ordinal
@@ -414,6 +432,9 @@ int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float*
   Params p;
   p.in = in; p.out = out; p.w = w; p.res = res; p.stats = stats;
   p.in2 = in2; p.out2 = out2; p.coef = coef;
+  p.mask_out = epi == CONV_RELU ? relu_mask : nullptr;
+  p.mask_in = epi == CONV_MASK ? relu_mask : nullptr;
+  BF_REQUIRE(epi != CONV_MASK || res != nullptr || relu_mask != nullptr, "mask epilogue needs the activation or its bit mask");
   const bool fused = in2 != nullptr;
   BF_REQUIRE(!fused || ((epi == CONV_RELU || epi == CONV_MASK) && out2 && coef), "fused conv prologue: ReLU / mask epilogues only");
   p.n = e.n; p.h = e.he; p.wd = e.we;

@@ -62,9 +62,11 @@ int launch_conv3x3_x3(bfcnn_handle* h, const float* in, float* out, const float*
 
 // ---- conv_t5.cu: the same layer contract on tcgen05 (row-streaming, F16X3 arithmetic); default training conv engine
 // in2 / out2 / coef: fused prologue (the conv input is ca*in + cb*in2 + cc per channel, written to out2), ReLU / mask epilogues
+// relu_mask: a [n,h,w] uint16 map, bit c = (channel c of the ReLU output > 0): written by CONV_RELU, read by CONV_MASK instead
+// of the 64 B/pixel activation `res`
 int launch_conv3x3_t5(bfcnn_handle* h, const float* in, float* out, const float* w, const float* res, double* stats,
                       ConvEpi epi, const Extent& e, float in_scale, cudaStream_t st, const float* in2 = nullptr,
-                      float* out2 = nullptr, const float* coef = nullptr);
+                      float* out2 = nullptr, const float* coef = nullptr, uint16_t* relu_mask = nullptr);
 
 int launch_wgrad3x3_x3(bfcnn_handle* h, const float* act, const float* grad, float* partial, int max_parts, const Extent& e,
                        float g_scale, int* parts_out, cudaStream_t st);

@@ -1049,7 +1049,9 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
 
   // ---- workspaces
   const int n_saved = 3 * N + 1;                       // X_0..X_N, T_i, U_i
-  BF_CHECK(h->ws_train.reserve((size_t)n_saved * map_floats * sizeof(float)));
+  // behind them: the ReLU masks of the T_i as 16-bit maps (tcgen05 engine: the conv_b dgrad reads 2 instead of 64 B/pixel)
+  const size_t mask_elems = (npx + 1) & ~(size_t)1;
+  BF_CHECK(h->ws_train.reserve((size_t)n_saved * map_floats * sizeof(float) + (size_t)N * mask_elems * sizeof(uint16_t)));
   const bool use_ssim = cfg->ssim_multiplier > 0.f;
   // SSIM scratch behind the 4 gradient maps: pred [npx*3], dpred [npx*3], derivative maps [<= npx*9]
   BF_CHECK(h->ws_grads.reserve(((size_t)4 * map_floats + (use_ssim ? npx * 15 : 0)) * sizeof(float)));
@@ -1077,6 +1079,7 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   auto Xm = [&](int i) { return saved + (size_t)i * map_floats; };               // X_0..X_N
   auto Tm = [&](int i) { return saved + (size_t)(N + 1 + i) * map_floats; };     // T_0..T_{N-1}
   auto Um = [&](int i) { return saved + (size_t)(2 * N + 1 + i) * map_floats; }; // U_0..U_{N-1}
+  auto Mm = [&](int i) { return reinterpret_cast<uint16_t*>(saved + (size_t)n_saved * map_floats) + (size_t)i * mask_elems; };
   float* gbuf = h->ws_grads.as<float>();
   float* dXa = gbuf; float* dXb = gbuf + map_floats; float* dU = gbuf + 2 * map_floats; float* dT = gbuf + 3 * map_floats;
   float* ss_pred = gbuf + 4 * map_floats; float* ss_dpred = ss_pred + npx * 3; float* ss_maps = ss_dpred + npx * 3;
@@ -1136,7 +1139,9 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
   for (int i = 0; i < N; ++i) {
     if (fuse && i > 0)
       BF_CHECK(launch_conv3x3_t5(h, Xm(i - 1), Tm(i), vars + L.wa[i], nullptr, nullptr, CONV_RELU, e, 64.0f, st, Um(i - 1), Xm(i),
-                                 bn_coef + (size_t)(i - 1) * 6 * C));
+                                 bn_coef + (size_t)(i - 1) * 6 * C, Mm(i)));
+    else if (fuse)
+      BF_CHECK(launch_conv3x3_t5(h, Xm(i), Tm(i), vars + L.wa[i], nullptr, nullptr, CONV_RELU, e, 64.0f, st, nullptr, nullptr, nullptr, Mm(i)));
     else
       BF_CHECK(conv(Xm(i), Tm(i), vars + L.wa[i], nullptr, nullptr, CONV_RELU));
     BF_CHECK(conv(Tm(i), Um(i), vars + L.wb[i], nullptr, bn_stats + (size_t)i * 2 * C, CONV_STATS));
@@ -1204,7 +1209,7 @@ int run_train_step(bfcnn_handle* h, const float* clean, const float* noisy, int 
       float* cf = bn_coef + (size_t)i * 6 * C + 3 * C;
       bn_bwd_coef_kernel<<<1, 32, 0, st>>>(bnp, bs, cnt, cf, flat_grads + L.t_gamma[i]);
       BF_CHECK(launch_conv3x3_t5(h, dX, dT, dgrad_w + (size_t)(2 * i + 1) * 9 * C * C, Tm(i), nullptr, CONV_MASK, e, gscale * 64.0f, st,
-                                 Um(i), dU, cf));
+                                 Um(i), dU, cf, Mm(i)));
     } else {
       bn_bwd_apply_kernel<<<ew_blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dX), reinterpret_cast<const float4*>(Um(i)), bnp, bs, cnt,
                                                      reinterpret_cast<float4*>(dU), flat_grads + L.t_gamma[i], n4);
